@@ -1,0 +1,271 @@
+/*
+ * xrtgpu.h — C ABI of libxrtgpu.so, the B200 (sm_100a) wavefront path tracer that sits
+ * behind the xRayTracer `Renderer` plug-in point.
+ *
+ * Reference interface each entry point replaces (paths relative to /root/reference/Src):
+ *   xrtg_scene_create     <- Scene::loadObj/addObj/addAreaLight/addDeltaLight + the empty hook
+ *                            Scene::build()                      scene.h:13-30, scene.cpp:46-170
+ *   xrtg_render[_device]  <- Renderer::render / NormalRenderer::doRender / ParallelRenderer::render
+ *                                                               renderer.h:8-20, renderer.cpp:8-99
+ *   xrtg_trace_primary    <- PinholeCamera::sampleRay + Scene::intersect (parity hook)
+ *                                                               camera.h:49-60, scene.cpp:190-200
+ *   xrtg_trace_rays       <- Scene::intersect / Scene::occluded  scene.cpp:190-211
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative xrtg_status; xrtg_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread.
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - all arithmetic on the path is fp32 (the reference's Vec3f, geometry.h:263).
+ *   - image layout is the reference's: row-major RGB, index = j + W*i (image.h:140-143).
+ *   - objects[] are listed in the reference's *iteration* order (std::unordered_map order,
+ *     scene.cpp:193) and global primitive ids are assigned by walking objects[] in that order
+ *     (mesh: one id per triangle, sphere/box: one id). Ties in t resolve to the lowest id, which
+ *     is exactly what the reference's "first strictly smaller t wins" loops produce.
+ *   - there is no CPU fallback anywhere behind this ABI: without a CUDA device every compute entry
+ *     point fails with XRTG_ERR_NO_DEVICE.
+ */
+#ifndef XRTGPU_H
+#define XRTGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRTG_ABI_VERSION 1
+
+typedef enum xrtg_status {
+    XRTG_OK = 0,
+    XRTG_ERR_INVALID = -1,     /* bad argument / malformed scene description            */
+    XRTG_ERR_NO_DEVICE = -2,   /* no CUDA device (there is no CPU fallback)              */
+    XRTG_ERR_CUDA = -3,        /* a CUDA runtime call failed; message has the error      */
+    XRTG_ERR_UNSUPPORTED = -4, /* integrator / scene feature outside the GPU path        */
+    XRTG_ERR_OOM = -5
+} xrtg_status;
+
+/* ---- geometry PODs --------------------------------------------------------------------- */
+
+/* One reference `Primitive` (primitive.h:6-35): 3 positions + 3 shading normals.
+ * Texcoords are not on the path (Lambert ignores them, material.h:39-48). */
+typedef struct xrtg_triangle {
+    float v0[3], v1[3], v2[3];
+    float n0[3], n1[3], n2[3];
+} xrtg_triangle;
+
+/* `Sphere` (primitive.h:97-184). */
+typedef struct xrtg_sphere {
+    float center[3];
+    float radius;
+} xrtg_sphere;
+
+/* `BoxMesh` (primitive.h:230-273), the bounding proxy of a medium. */
+typedef struct xrtg_box {
+    float pmin[3], pmax[3];
+} xrtg_box;
+
+typedef enum xrtg_object_kind { XRTG_OBJ_MESH = 0, XRTG_OBJ_SPHERE = 1, XRTG_OBJ_BOX = 2 } xrtg_object_kind;
+
+/* `Object` facade (primitive.h:40-95). */
+typedef struct xrtg_object {
+    int32_t kind;       /* xrtg_object_kind                                              */
+    int32_t first;      /* first triangle / sphere / box in the matching array          */
+    int32_t count;      /* number of triangles (mesh) or 1                              */
+    int32_t material;   /* index into materials[], -1 = nullptr (light proxies, media)   */
+    int32_t area_light; /* index into area_lights[], -1 = none                           */
+    int32_t medium;     /* index into media[], -1 = none                                 */
+    int32_t insert_seq; /* order in which the host Scene inserted it (addObj order)      */
+    int32_t _pad;
+    const char* name;   /* key in the reference's m_objects map; may be NULL            */
+} xrtg_object;
+
+typedef enum xrtg_material_kind { XRTG_MAT_LAMBERT = 0 } xrtg_material_kind;
+
+/* `Lambert` (material.h:28-77). */
+typedef struct xrtg_material {
+    int32_t kind;
+    float albedo[3];
+} xrtg_material;
+
+typedef enum xrtg_area_light_kind {
+    XRTG_LIGHT_QUAD = 0,     /* light.cpp:49-82  */
+    XRTG_LIGHT_TRIANGLE = 1, /* light.cpp:6-47   */
+    XRTG_LIGHT_SPHERE = 2    /* light.h:124-198 (cone-sampling branch), light.cpp:84-113 */
+} xrtg_area_light_kind;
+
+/* World-space (already multiplied by lightToWorld). Quad/triangle: v0,v1,v2; e1=v1-v0, e2=v2-v0,
+ * Ng=e1 x e2 are derived. Sphere: v0 = centre, radius. */
+typedef struct xrtg_area_light {
+    int32_t kind;
+    float v0[3], v1[3], v2[3];
+    float radius;
+    float Le[3];
+} xrtg_area_light;
+
+typedef enum xrtg_delta_light_kind { XRTG_DLIGHT_POINT = 0, XRTG_DLIGHT_DISTANT = 1 } xrtg_delta_light_kind;
+
+/* `PointLight` / `DistantLight` (light.cpp:115-142). radiance = color * intensity. */
+typedef struct xrtg_delta_light {
+    int32_t kind;
+    float pos_or_dir[3]; /* point: world position; distant: normalised travel direction `dir` */
+    float radiance[3];
+} xrtg_delta_light;
+
+typedef enum xrtg_medium_kind {
+    XRTG_MEDIUM_HOMOGENEOUS_MIS = 0,        /* medium.h:148-192 */
+    XRTG_MEDIUM_HOMOGENEOUS_ACHROMATIC = 1, /* medium.h:195-229 */
+    XRTG_MEDIUM_HOMOGENEOUS_NOMIS = 2,      /* medium.h:232-277 */
+    XRTG_MEDIUM_HETEROGENEOUS = 3           /* medium.h:280-387, medium.cpp:5-133 */
+} xrtg_medium_kind;
+
+typedef struct xrtg_medium {
+    int32_t kind;
+    float g;          /* Henyey-Greenstein asymmetry (medium.h:21-68)                    */
+    float sigma_a[3]; /* homogeneous: absorption;  heterogeneous: absorptionColor        */
+    float sigma_s[3]; /* homogeneous: scattering;  heterogeneous: scatteringColor        */
+    float density_mul;
+    int32_t grid;     /* heterogeneous: index into grids[], else -1                      */
+} xrtg_medium;
+
+/* Dense restatement of `DensityGrid`/`OpenVDBGrid` (grid.h:9-85): fp32 voxels at integer index
+ * coordinates [0,n) (x fastest), world = origin + voxel_size * index, trilinear (BoxSampler) lookup,
+ * `background` outside. bounds = indexToWorld of the active-voxel bbox [active_min, active_max]. */
+typedef struct xrtg_grid {
+    int32_t nx, ny, nz;
+    const float* data; /* host pointer, nx*ny*nz floats */
+    float origin[3];
+    float voxel_size;
+    float background;
+    int32_t active_min[3], active_max[3]; /* inclusive index bbox of non-background voxels */
+    float max_density;                    /* evalMinMax max (grid.h:79-84)                 */
+} xrtg_grid;
+
+typedef struct xrtg_scene_desc {
+    int32_t abi_version; /* XRTG_ABI_VERSION */
+    int32_t n_objects, n_triangles, n_spheres, n_boxes;
+    int32_t n_materials, n_area_lights, n_delta_lights, n_media, n_grids;
+    const xrtg_object* objects; /* reference iteration order */
+    const xrtg_triangle* triangles;
+    const xrtg_sphere* spheres;
+    const xrtg_box* boxes;
+    const xrtg_material* materials;
+    const xrtg_area_light* area_lights;   /* Scene::getAreaLights() order (scene.cpp:166-170) */
+    const xrtg_delta_light* delta_lights; /* Scene::getDeltaLights() order                    */
+    const xrtg_medium* media;
+    const xrtg_grid* grids;
+} xrtg_scene_desc;
+
+/* `PinholeCamera` (camera.h:34-60): c2w row-major with translation in row 3, scale = tan(FOV/2)
+ * evaluated on the host, aspect = W/H. */
+typedef struct xrtg_camera {
+    float c2w[16];
+    float scale;
+    float aspect;
+} xrtg_camera;
+
+typedef enum xrtg_integrator {
+    XRTG_INT_NORMAL = 0,   /* NormalIntegrator as shipped: 0.5*(ns+1)       integrator.h:29-36  */
+    XRTG_INT_FURNACE = 1,  /* the dead furnace block                        integrator.h:59-66  */
+    XRTG_INT_DIRECT = 2,   /* DirectIntegrator                              integrator.h:82-119 */
+    XRTG_INT_INDIRECT = 3, /* IndirectIntegrator                            integrator.h:129-186 */
+    XRTG_INT_GI = 4,       /* GIIntegrator                                  integrator.h:205-287 */
+    XRTG_INT_WHITTED = 5,  /* WhittedIntegrator, Lambert/delta-light branch integrator.h:328-343 */
+    XRTG_INT_VOLUME = 6,   /* VolumePathTracing                             integrator.h:409-473 */
+    XRTG_INT_VOLUME_NEE = 7 /* VolumePathTracingNEE                         integrator.h:489-631 */
+} xrtg_integrator;
+
+enum {
+    /* Reproduce the reference's sample stream: per-pixel std::mt19937 seeded j+W*i (renderer.cpp:35-36),
+     * libstdc++ uniform_real_distribution<float> mapping, no FMA contraction, one sample per pixel per
+     * wave. Slow; exists for parity. Without it: counter-based RNG keyed (seed,pixel,sample,dim). */
+    XRTG_FLAG_EXACT = 1u << 0,
+    /* Count closest-hit rays, shadow rays, BVH nodes visited, triangles tested, tracking steps. */
+    XRTG_FLAG_COUNTERS = 1u << 1,
+    /* Closest/any-hit by brute force in primitive order instead of the BVH (parity debugging). */
+    XRTG_FLAG_BRUTE_FORCE = 1u << 2,
+    /* Do not divide by spp: leave the per-pixel SUM in the output (multi-GPU partial results). */
+    XRTG_FLAG_SUM_ONLY = 1u << 3
+};
+
+typedef struct xrtg_render_params {
+    int32_t width, height;
+    int32_t spp;           /* samples rendered by THIS call                                  */
+    int32_t sample_offset; /* index of the first sample (spp split across GPUs / resumable)  */
+    int32_t spp_total;     /* divisor of the final mean; 0 = spp (renderer.cpp:98)           */
+    int32_t integrator;    /* xrtg_integrator                                                */
+    int32_t max_depth;
+    uint32_t seed;         /* counter RNG seed (ignored with XRTG_FLAG_EXACT)                */
+    uint32_t flags;
+    int32_t samples_per_wave; /* 0 = auto                                                    */
+} xrtg_render_params;
+
+typedef struct xrtg_stats {
+    uint64_t samples;
+    uint64_t closest_rays;   /* Scene::intersect calls the reference would make   */
+    uint64_t shadow_rays;    /* Scene::occluded calls the reference would make    */
+    uint64_t dropped_samples;/* NaN/inf/negative samples (renderer.cpp:57-73)     */
+    uint64_t nodes_visited;  /* with XRTG_FLAG_COUNTERS                            */
+    uint64_t tris_tested;    /* with XRTG_FLAG_COUNTERS                            */
+    uint64_t tracking_steps; /* with XRTG_FLAG_COUNTERS                            */
+    uint64_t kernel_launches;
+    float render_ms;         /* CUDA-event time of the device work                 */
+    float extend_ms;         /* time in closest-hit traversal kernels              */
+    float connect_ms;        /* time in any-hit traversal kernels                  */
+    float shade_ms;
+    float other_ms;
+    float h2d_ms, d2h_ms;
+} xrtg_stats;
+
+/* Closest-hit record of the parity hooks. prim = global primitive id (-1 = miss). */
+typedef struct xrtg_hit {
+    float t, u, v;
+    int32_t prim;
+} xrtg_hit;
+
+typedef struct xrtg_scene xrtg_scene;
+
+typedef struct xrtg_scene_info {
+    int32_t n_prims, n_triangles, n_bvh_nodes, bvh_depth;
+    float bvh_sah_cost;
+    float build_ms, upload_ms;
+    uint64_t device_bytes; /* scene data resident in HBM      */
+    uint64_t upload_bytes; /* bytes copied H2D by an upload    */
+} xrtg_scene_info;
+
+int xrtg_abi_version(void);
+int xrtg_device_count(void);
+const char* xrtg_last_error(void);
+
+/* Copies the PODs, builds the SAH BVH on the host, uploads everything to `device`. */
+int xrtg_scene_create(const xrtg_scene_desc* desc, int device, xrtg_scene** out);
+/* Re-copies the already-built scene arrays host(pinned)->device (the e2e H2D leg). */
+int xrtg_scene_upload(xrtg_scene* scene);
+int xrtg_scene_get_info(const xrtg_scene* scene, xrtg_scene_info* out);
+void xrtg_scene_destroy(xrtg_scene* scene);
+
+/* Render into a HOST buffer rgb[W*H*3]: mean radiance (or the sum with XRTG_FLAG_SUM_ONLY).
+ * The timed D2H copy is part of the call. stats may be NULL. */
+int xrtg_render(xrtg_scene* scene, const xrtg_camera* cam, const xrtg_render_params* p, float* rgb_host,
+                xrtg_stats* stats);
+/* Same, into a DEVICE buffer on the scene's device, asynchronously on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream). The caller synchronises. */
+int xrtg_render_device(xrtg_scene* scene, const xrtg_camera* cam, const xrtg_render_params* p,
+                       float* rgb_device, void* cuda_stream, xrtg_stats* stats);
+
+/* Parity hook: primary rays only. jitter_uv = W*H*spp*2 floats in [0,1) laid out [(i*W+j)*spp+k][2]
+ * (host pointer) or NULL to take them from the pixel's mt19937 stream as renderer.cpp:44-47 does.
+ * out = W*H*spp hits (host). flags: XRTG_FLAG_BRUTE_FORCE honoured. */
+int xrtg_trace_primary(xrtg_scene* scene, const xrtg_camera* cam, int width, int height, int spp,
+                       const float* jitter_uv, uint32_t flags, xrtg_hit* out);
+
+/* Parity hook: arbitrary rays. org/dir = n*3 floats (host), tmax = n floats or NULL (= +inf).
+ * any_hit=0: Scene::intersect semantics -> out_hits[n].  any_hit=1: Scene::occluded(ray,tmax)
+ * semantics (emitter proxies skipped) -> out_hits[i].prim = 0/1 occluded flag in prim>=0. */
+int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float* dir, const float* tmax,
+                    int any_hit, uint32_t flags, xrtg_hit* out_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRTGPU_H */

@@ -1,0 +1,193 @@
+"""Python-side handles with one interface over the three implementations that consume an xrtg_scene_desc:
+
+  GpuScene        libxrtgpu.so       the product: sm_100a wavefront kernels behind the C ABI (include/xrtgpu.h)
+  OracleScene     libxrtoracle.so    CPU restatement (oracle/port)            — tests / cpu_baseline only
+  ReferenceScene  libxrtref.so       the compiled reference (oracle/_ref)     — tests / cpu_baseline only
+
+Only GpuScene is product code; it raises when libxrtgpu.so is missing or no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.int32)])
+
+
+def _params(width, height, spp, integrator, max_depth, flags=0, seed=0, sample_offset=0, spp_total=0, samples_per_wave=0):
+    p = capi.RenderParams()
+    p.width, p.height, p.spp, p.sample_offset, p.spp_total = width, height, spp, sample_offset, spp_total
+    p.integrator, p.max_depth, p.seed, p.flags, p.samples_per_wave = integrator, max_depth, seed, flags, samples_per_wave
+    return p
+
+
+def _rays(org, dir, tmax):
+    org = np.ascontiguousarray(org, dtype=np.float32).reshape(-1, 3)
+    dir = np.ascontiguousarray(dir, dtype=np.float32).reshape(-1, 3)
+    assert org.shape == dir.shape
+    if tmax is not None:
+        tmax = np.ascontiguousarray(tmax, dtype=np.float32).reshape(-1)
+        assert len(tmax) == len(org)
+    return org, dir, tmax
+
+
+class GpuScene:
+    """Device scene (SAH BVH + flattened arrays resident in HBM) created through xrtg_scene_create."""
+
+    def __init__(self, desc, device: int = 0):
+        self.lib = capi.gpu()
+        h = C.c_void_p()
+        rc = self.lib.xrtg_scene_create(desc, device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"xrtg_scene_create failed ({rc}): {self.lib.xrtg_last_error().decode()}")
+        self.h = h
+        self.device = device
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.xrtg_scene_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.xrtg_last_error().decode()}")
+
+    def info(self) -> dict:
+        i = capi.SceneInfo()
+        self._chk(self.lib.xrtg_scene_get_info(self.h, C.byref(i)), "xrtg_scene_get_info")
+        return i.as_dict()
+
+    def upload(self):
+        self._chk(self.lib.xrtg_scene_upload(self.h), "xrtg_scene_upload")
+
+    def render(self, cam, width, height, spp, integrator, max_depth=1, flags=0, seed=0, sample_offset=0, spp_total=0,
+               samples_per_wave=0, out=None):
+        """Host-buffer render through xrtg_render. Returns (rgb[H,W,3] float32, stats dict)."""
+        p = _params(width, height, spp, integrator, max_depth, flags, seed, sample_offset, spp_total, samples_per_wave)
+        rgb = out if out is not None else np.empty((height, width, 3), dtype=np.float32)
+        st = capi.Stats()
+        self._chk(self.lib.xrtg_render(self.h, C.byref(cam), C.byref(p), rgb.ctypes.data, C.byref(st)), "xrtg_render")
+        return rgb, st.as_dict()
+
+    def render_device(self, cam, width, height, spp, integrator, max_depth, device_ptr: int, stream: int = 0, flags=0, seed=0,
+                      sample_offset=0, spp_total=0, samples_per_wave=0, want_stats=True):
+        """Asynchronous render into a device buffer (e.g. a torch tensor's data_ptr()) on `stream`."""
+        p = _params(width, height, spp, integrator, max_depth, flags, seed, sample_offset, spp_total, samples_per_wave)
+        st = capi.Stats()
+        self._chk(self.lib.xrtg_render_device(self.h, C.byref(cam), C.byref(p), C.c_void_p(device_ptr), C.c_void_p(stream),
+                                               C.byref(st) if want_stats else None), "xrtg_render_device")
+        return st.as_dict() if want_stats else None
+
+    def trace_primary(self, cam, width, height, spp, jitter=None, flags=0):
+        hits = np.empty(width * height * spp, dtype=HIT_DTYPE)
+        jp = None
+        if jitter is not None:
+            jitter = np.ascontiguousarray(jitter, dtype=np.float32)
+            assert jitter.size == width * height * spp * 2
+            jp = jitter.ctypes.data
+        self._chk(self.lib.xrtg_trace_primary(self.h, C.byref(cam), width, height, spp, jp, flags, hits.ctypes.data),
+                  "xrtg_trace_primary")
+        return hits.reshape(height, width, spp)
+
+    def trace_rays(self, org, dir, tmax=None, any_hit=False, flags=0):
+        org, dir, tmax = _rays(org, dir, tmax)
+        hits = np.empty(len(org), dtype=HIT_DTYPE)
+        self._chk(self.lib.xrtg_trace_rays(self.h, len(org), org.ctypes.data, dir.ctypes.data,
+                                            None if tmax is None else tmax.ctypes.data, int(any_hit), flags, hits.ctypes.data),
+                  "xrtg_trace_rays")
+        return hits
+
+
+class _CpuScene:
+    """Shared wrapper of the two CPU checkers (same entry-point shapes, different prefix)."""
+    pfx = ""
+    has_stats = False
+
+    def __init__(self, desc):
+        self.lib = self._lib()
+        h = C.c_void_p()
+        rc = self.fn("scene_create")(desc, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"{self.pfx}scene_create failed: {self.fn('last_error')().decode()}")
+        self.h = h
+
+    def fn(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.fn("scene_destroy")(self.h)
+            self.h = None
+
+    def max_threads(self):
+        return self.fn("max_threads")()
+
+    def render(self, cam, width, height, spp, integrator, max_depth=1, flags=0, nthreads=0, pixel_stride=1, spp_total=0):
+        """Returns (rgb[H,W,3], seconds of the pixel loop, stats dict or None)."""
+        p = _params(width, height, spp, integrator, max_depth, flags, 0, 0, spp_total)
+        rgb = np.zeros((height, width, 3), dtype=np.float32)
+        sec = C.c_double()
+        if self.has_stats:
+            st = capi.Stats()
+            rc = self.fn("render")(self.h, C.byref(cam), C.byref(p), nthreads, pixel_stride, rgb.ctypes.data, C.byref(sec), C.byref(st))
+            stats = st.as_dict()
+        else:
+            rc = self.fn("render")(self.h, C.byref(cam), C.byref(p), nthreads, pixel_stride, rgb.ctypes.data, C.byref(sec))
+            stats = None
+        if rc != 0:
+            raise RuntimeError(f"{self.pfx}render failed: {self.fn('last_error')().decode()}")
+        return rgb, sec.value, stats
+
+    def trace_primary(self, cam, width, height, spp, jitter=None):
+        hits = np.empty(width * height * spp, dtype=HIT_DTYPE)
+        jp = None
+        if jitter is not None:
+            jitter = np.ascontiguousarray(jitter, dtype=np.float32)
+            jp = jitter.ctypes.data
+        self.fn("trace_primary")(self.h, C.byref(cam), width, height, spp, jp, hits.ctypes.data)
+        return hits.reshape(height, width, spp)
+
+    def trace_rays(self, org, dir, tmax=None, any_hit=False):
+        org, dir, tmax = _rays(org, dir, tmax)
+        hits = np.empty(len(org), dtype=HIT_DTYPE)
+        self.fn("trace_rays")(self.h, len(org), org.ctypes.data, dir.ctypes.data, None if tmax is None else tmax.ctypes.data,
+                              int(any_hit), hits.ctypes.data)
+        return hits
+
+    # known-answer hooks
+    def kat_light_sample(self, li, pos, seed):
+        out = (C.c_float * 8)()
+        self.fn("kat_light_sample")(self.h, li, (C.c_float * 3)(*pos), seed, out)
+        return np.array(out[:], dtype=np.float32)
+
+
+class OracleScene(_CpuScene):
+    pfx = "xrto_"
+    has_stats = True
+
+    @staticmethod
+    def _lib():
+        return capi.oracle()
+
+
+class ReferenceScene(_CpuScene):
+    pfx = "xrtref_"
+    has_stats = False
+
+    @staticmethod
+    def _lib():
+        return capi.reference()
+
+    def object_order(self):
+        buf = (C.c_int32 * 4096)()
+        n = self.lib.xrtref_object_order(self.h, buf, 4096)
+        return list(buf[:n])
+
+
+def kat(lib, pfx, name, *args, n_out):
+    out = (C.c_float * n_out)()
+    getattr(lib, pfx + "kat_" + name)(*args, out)
+    return np.array(out[:], dtype=np.float32)

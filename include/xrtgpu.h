@@ -33,6 +33,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
 
 #define XRTG_ABI_VERSION 1
 
@@ -265,6 +268,9 @@ int xrtg_trace_primary(xrtg_scene* scene, const xrtg_camera* cam, int width, int
 int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float* dir, const float* tmax,
                     int any_hit, uint32_t flags, xrtg_hit* out_hits);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,703 @@
+// api.cu — C ABI of libxrtgpu.so (include/xrtgpu.h): scene ingest + SAH BVH build + HBM upload, the wave
+// scheduler that drives the wavefront kernels, and the parity hooks. No CPU rendering path exists here: every
+// compute entry point fails with XRTG_ERR_NO_DEVICE when no CUDA device is present.
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include <xrtgpu.h>
+#include "bvh.h"
+#include "device_types.h"
+#include "kernels.h"
+
+using namespace xrt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                                    \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+            return fail(e__ == cudaErrorMemoryAllocation ? XRTG_ERR_OOM : XRTG_ERR_CUDA,                            \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                                       \
+    } while (0)
+
+// pinned host array + device mirror
+struct Mirror {
+    void* h = nullptr;
+    void* d = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n)
+    {
+        release();
+        bytes = n;
+        if (n == 0) return 0;
+        CU(cudaMallocHost(&h, n));
+        CU(cudaMalloc(&d, n));
+        return 0;
+    }
+    void release()
+    {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        bytes = 0;
+    }
+    ~Mirror() { release(); }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        CU(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+float4 f4(const float* p, float w) { return make_float4(p[0], p[1], p[2], w); }
+float asF(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+float asF(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+} // namespace
+
+struct xrtg_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr; // uploads + host-buffer renders
+    // scene arrays (pinned host copy + device copy)
+    Mirror nodes, tris, trisId, prims, spheres, boxes, lights, dlights, media, grids;
+    std::vector<std::unique_ptr<Mirror>> gridData;
+    DScene ds{};
+    xrtg_scene_info info{};
+    int maxShadowPerPath = 1;
+    // workspace
+    DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
+    unsigned long long* statsHost = nullptr; // pinned
+    uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
+    cudaEvent_t ev[4] = {};
+    std::vector<cudaEvent_t> stageEvents; // pairs, with COUNTERS
+    std::vector<int> stageKinds;
+
+    ~xrtg_scene()
+    {
+        if (statsHost) cudaFreeHost(statsHost);
+        if (ctrlHost) cudaFreeHost(ctrlHost);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : stageEvents) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int uploadAll(xrtg_scene* s)
+{
+    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    size_t total = 0;
+    for (Mirror* m : all) {
+        if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
+        total += m->bytes;
+    }
+    for (auto& g : s->gridData) {
+        CU(cudaMemcpyAsync(g->d, g->h, g->bytes, cudaMemcpyHostToDevice, s->stream));
+        total += g->bytes;
+    }
+    s->info.upload_bytes = total;
+    return 0;
+}
+
+int checkDesc(const xrtg_scene_desc* d)
+{
+    if (!d) return fail(XRTG_ERR_INVALID, "scene desc is NULL");
+    if (d->abi_version != XRTG_ABI_VERSION) return fail(XRTG_ERR_INVALID, "scene desc abi_version mismatch");
+    if (d->n_objects < 0 || d->n_triangles < 0 || d->n_spheres < 0 || d->n_boxes < 0) return fail(XRTG_ERR_INVALID, "negative count in scene desc");
+    if (d->n_area_lights > 4000 || d->n_media > 4000) return fail(XRTG_ERR_UNSUPPORTED, "too many lights/media");
+    for (int i = 0; i < d->n_objects; ++i) {
+        const xrtg_object& o = d->objects[i];
+        const int lim = o.kind == XRTG_OBJ_MESH ? d->n_triangles : (o.kind == XRTG_OBJ_SPHERE ? d->n_spheres : d->n_boxes);
+        if (o.kind < 0 || o.kind > 2) return fail(XRTG_ERR_INVALID, "unknown object kind");
+        if (o.first < 0 || o.count < 0 || o.first + o.count > lim) return fail(XRTG_ERR_INVALID, "object geometry range out of bounds");
+        if (o.material >= d->n_materials || o.area_light >= d->n_area_lights || o.medium >= d->n_media)
+            return fail(XRTG_ERR_INVALID, "object references a missing material/light/medium");
+        if (o.kind == XRTG_OBJ_BOX && o.medium < 0) return fail(XRTG_ERR_INVALID, "box object without a medium");
+        if (o.kind != XRTG_OBJ_MESH && o.count != 1) return fail(XRTG_ERR_INVALID, "sphere/box object must have count 1");
+    }
+    for (int i = 0; i < d->n_media; ++i)
+        if (d->media[i].kind == XRTG_MEDIUM_HETEROGENEOUS && (d->media[i].grid < 0 || d->media[i].grid >= d->n_grids))
+            return fail(XRTG_ERR_INVALID, "heterogeneous medium without a grid");
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int xrtg_abi_version(void) { return XRTG_ABI_VERSION; }
+
+int xrtg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* xrtg_last_error(void) { return g_err.c_str(); }
+
+void xrtg_scene_destroy(xrtg_scene* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    delete s;
+}
+
+int xrtg_scene_create(const xrtg_scene_desc* d, int device, xrtg_scene** out)
+{
+    if (!out) return fail(XRTG_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (int rc = checkDesc(d)) return rc;
+    if (xrtg_device_count() <= 0) return fail(XRTG_ERR_NO_DEVICE, "no CUDA device (libxrtgpu has no CPU fallback)");
+    if (device < 0 || device >= xrtg_device_count()) return fail(XRTG_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    auto s = std::make_unique<xrtg_scene>();
+    s->device = device;
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) CU(cudaEventCreate(&e));
+    CU(cudaMallocHost(&s->statsHost, sizeof(unsigned long long) * kStatCount));
+    CU(cudaMallocHost(&s->ctrlHost, sizeof(uint32_t) * 16));
+
+    Timer tb;
+    // ---- global primitive ids in object (= reference iteration) order ----
+    int nPrims = 0;
+    std::vector<int> firstPrim(d->n_objects);
+    for (int i = 0; i < d->n_objects; ++i) {
+        firstPrim[i] = nPrims;
+        nPrims += d->objects[i].kind == XRTG_OBJ_MESH ? d->objects[i].count : 1;
+    }
+    int nMeshTris = 0, nSph = 0, nBox = 0;
+    for (int i = 0; i < d->n_objects; ++i) {
+        const xrtg_object& o = d->objects[i];
+        if (o.kind == XRTG_OBJ_MESH) nMeshTris += o.count;
+        else if (o.kind == XRTG_OBJ_SPHERE) nSph++;
+        else nBox++;
+    }
+    if (int rc = s->prims.alloc(sizeof(float4) * 4 * size_t(std::max(nPrims, 1)))) return rc;
+    if (int rc = s->trisId.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = s->tris.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = s->spheres.alloc(sizeof(float4) * 2 * size_t(std::max(nSph, 1)))) return rc;
+    if (int rc = s->boxes.alloc(sizeof(float4) * 2 * size_t(std::max(nBox, 1)))) return rc;
+    std::memset(s->prims.h, 0, s->prims.bytes);
+    float4* prims = static_cast<float4*>(s->prims.h);
+    float4* trisId = static_cast<float4*>(s->trisId.h);
+    float4* sph = static_cast<float4*>(s->spheres.h);
+    float4* box = static_cast<float4*>(s->boxes.h);
+    std::vector<float> buildTris(size_t(nMeshTris) * 9);
+    int ti = 0, si = 0, bi = 0;
+    for (int i = 0; i < d->n_objects; ++i) {
+        const xrtg_object& o = d->objects[i];
+        uint32_t meta = uint32_t(o.kind);
+        float alb[3] = {0, 0, 0};
+        if (o.material >= 0) {
+            meta |= kMetaHasMaterial;
+            std::memcpy(alb, d->materials[o.material].albedo, 12);
+        }
+        meta |= uint32_t(o.area_light + 1) << kMetaLightShift;
+        meta |= uint32_t(o.medium + 1) << kMetaMediumShift;
+        const float4 rec3 = make_float4(alb[0], alb[1], alb[2], asF(meta));
+        if (o.kind == XRTG_OBJ_MESH) {
+            for (int k = 0; k < o.count; ++k, ++ti) {
+                const xrtg_triangle& t = d->triangles[o.first + k];
+                const int id = firstPrim[i] + k;
+                // e1 = v1 - v0, e2 = v2 - v0 (primitive.cpp:142-143) and ng = normalize(e1 x e2)
+                // (primitive.cpp:105) with the reference's fp32 operation order (host code, no FMA)
+                float e1[3], e2[3], c[3];
+                for (int a = 0; a < 3; ++a) { e1[a] = t.v1[a] - t.v0[a]; e2[a] = t.v2[a] - t.v0[a]; }
+                c[0] = e1[1] * e2[2] - e1[2] * e2[1];
+                c[1] = e1[2] * e2[0] - e1[0] * e2[2];
+                c[2] = e1[0] * e2[1] - e1[1] * e2[0];
+                const float len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+                const float ng[3] = {c[0] / len, c[1] / len, c[2] / len};
+                trisId[3 * ti] = f4(t.v0, asF(id));
+                trisId[3 * ti + 1] = f4(e1, asF(int(o.area_light >= 0 ? 1 : 0)));
+                trisId[3 * ti + 2] = f4(e2, 0.f);
+                prims[4 * id] = f4(t.n0, ng[0]);
+                prims[4 * id + 1] = f4(t.n1, ng[1]);
+                prims[4 * id + 2] = f4(t.n2, ng[2]);
+                prims[4 * id + 3] = rec3;
+                std::memcpy(&buildTris[size_t(ti) * 9], t.v0, 12);
+                std::memcpy(&buildTris[size_t(ti) * 9 + 3], t.v1, 12);
+                std::memcpy(&buildTris[size_t(ti) * 9 + 6], t.v2, 12);
+            }
+        }
+        else if (o.kind == XRTG_OBJ_SPHERE) {
+            const xrtg_sphere& sp = d->spheres[o.first];
+            const int id = firstPrim[i];
+            sph[2 * si] = f4(sp.center, sp.radius);
+            sph[2 * si + 1] = make_float4(asF(id), asF(int(o.area_light >= 0 ? 1 : 0)), 0.f, 0.f);
+            prims[4 * id] = f4(sp.center, sp.radius);
+            prims[4 * id + 3] = rec3;
+            ++si;
+        }
+        else {
+            const xrtg_box& b = d->boxes[o.first];
+            const int id = firstPrim[i];
+            box[2 * bi] = f4(b.pmin, asF(id));
+            box[2 * bi + 1] = f4(b.pmax, 0.f);
+            prims[4 * id + 3] = rec3;
+            ++bi;
+        }
+    }
+    // ---- SAH BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
+    Bvh bvh;
+    buildBvh(buildTris.data(), uint32_t(nMeshTris), 4, bvh);
+    if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
+    std::memcpy(s->nodes.h, bvh.nodes.data(), s->nodes.bytes);
+    float4* tris = static_cast<float4*>(s->tris.h);
+    for (size_t k = 0; k < bvh.triOrder.size(); ++k) {
+        const uint32_t src = bvh.triOrder[k];
+        tris[3 * k] = trisId[3 * src];
+        tris[3 * k + 1] = trisId[3 * src + 1];
+        tris[3 * k + 2] = trisId[3 * src + 2];
+    }
+    // ---- lights, media, grids ----
+    if (int rc = s->lights.alloc(sizeof(DLight) * size_t(std::max(d->n_area_lights, 1)))) return rc;
+    DLight* L = static_cast<DLight*>(s->lights.h);
+    for (int i = 0; i < d->n_area_lights; ++i) {
+        const xrtg_area_light& a = d->area_lights[i];
+        float e1[3], e2[3], ng[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = a.v1[k] - a.v0[k]; e2[k] = a.v2[k] - a.v0[k]; }
+        ng[0] = e1[1] * e2[2] - e1[2] * e2[1];
+        ng[1] = e1[2] * e2[0] - e1[0] * e2[2];
+        ng[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        L[i].v0_kind = f4(a.v0, asF(int(a.kind)));
+        L[i].e1_r = f4(e1, a.radius);
+        L[i].e2 = f4(e2, 0.f);
+        L[i].Ng = f4(ng, 0.f);
+        L[i].Le = f4(a.Le, 0.f);
+        L[i].v1 = f4(a.v1, 0.f);
+        L[i].v2 = f4(a.v2, 0.f);
+    }
+    if (int rc = s->dlights.alloc(sizeof(DDelta) * size_t(std::max(d->n_delta_lights, 1)))) return rc;
+    DDelta* DL = static_cast<DDelta*>(s->dlights.h);
+    for (int i = 0; i < d->n_delta_lights; ++i) {
+        DL[i].p_kind = f4(d->delta_lights[i].pos_or_dir, asF(int(d->delta_lights[i].kind)));
+        DL[i].L = f4(d->delta_lights[i].radiance, 0.f);
+    }
+    if (int rc = s->grids.alloc(sizeof(DGrid) * size_t(std::max(d->n_grids, 1)))) return rc;
+    DGrid* G = static_cast<DGrid*>(s->grids.h);
+    for (int i = 0; i < d->n_grids; ++i) {
+        const xrtg_grid& g = d->grids[i];
+        if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0 || !g.data || !(g.voxel_size > 0)) return fail(XRTG_ERR_INVALID, "malformed density grid");
+        auto m = std::make_unique<Mirror>();
+        if (int rc = m->alloc(sizeof(float) * size_t(g.nx) * g.ny * g.nz)) return rc;
+        std::memcpy(m->h, g.data, m->bytes);
+        G[i].data = static_cast<const float*>(m->d);
+        G[i].nx = g.nx; G[i].ny = g.ny; G[i].nz = g.nz;
+        std::memcpy(G[i].origin, g.origin, 12);
+        G[i].voxel = g.voxel_size;
+        G[i].background = g.background;
+        s->gridData.push_back(std::move(m));
+    }
+    if (int rc = s->media.alloc(sizeof(DMedium) * size_t(std::max(d->n_media, 1)))) return rc;
+    DMedium* M = static_cast<DMedium*>(s->media.h);
+    for (int i = 0; i < d->n_media; ++i) {
+        const xrtg_medium& m = d->media[i];
+        M[i] = DMedium{};
+        M[i].kind = m.kind; M[i].g = m.g; M[i].grid = m.grid; M[i].densityMul = m.density_mul;
+        for (int k = 0; k < 3; ++k) { M[i].sigma_a[k] = m.sigma_a[k]; M[i].sigma_s[k] = m.sigma_s[k]; M[i].sigma_t[k] = m.sigma_a[k] + m.sigma_s[k]; }
+        if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) {
+            // HeterogeneousMedium ctor, medium.cpp:5-17
+            const float maxd = m.density_mul * d->grids[m.grid].max_density;
+            float mm[3];
+            for (int k = 0; k < 3; ++k) mm[k] = m.sigma_a[k] * maxd + m.sigma_s[k] * maxd;
+            M[i].majorant = std::max(mm[0], std::max(mm[1], mm[2]));
+            M[i].invMajorant = 1.0f / M[i].majorant;
+        }
+    }
+    s->info.build_ms = tb.ms();
+
+    Timer tu;
+    if (int rc = uploadAll(s.get())) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->info.upload_ms = tu.ms();
+
+    DScene& ds = s->ds;
+    ds.nodes = static_cast<const float4*>(s->nodes.d);
+    ds.tris = static_cast<const float4*>(s->tris.d);
+    ds.tris_id = static_cast<const float4*>(s->trisId.d);
+    ds.prims = static_cast<const float4*>(s->prims.d);
+    ds.spheres = static_cast<const float4*>(s->spheres.d);
+    ds.boxes = static_cast<const float4*>(s->boxes.d);
+    ds.lights = static_cast<const DLight*>(s->lights.d);
+    ds.dlights = static_cast<const DDelta*>(s->dlights.d);
+    ds.media = static_cast<const DMedium*>(s->media.d);
+    ds.grids = static_cast<const DGrid*>(s->grids.d);
+    ds.nTris = nMeshTris; ds.nBruteTris = nMeshTris; ds.nSpheres = nSph; ds.nBoxes = nBox;
+    ds.nLights = d->n_area_lights; ds.nDelta = d->n_delta_lights; ds.nPrims = nPrims;
+    s->maxShadowPerPath = std::max(1, std::max(d->n_area_lights, d->n_delta_lights));
+
+    s->info.n_prims = nPrims;
+    s->info.n_triangles = nMeshTris;
+    s->info.n_bvh_nodes = int(bvh.nodes.size());
+    s->info.bvh_depth = bvh.depth;
+    s->info.bvh_sah_cost = bvh.sahCost;
+    s->info.device_bytes = s->info.upload_bytes;
+    *out = s.release();
+    return 0;
+}
+
+int xrtg_scene_upload(xrtg_scene* s)
+{
+    if (!s) return fail(XRTG_ERR_INVALID, "scene is NULL");
+    CU(cudaSetDevice(s->device));
+    Timer t;
+    if (int rc = uploadAll(s)) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->info.upload_ms = t.ms();
+    return 0;
+}
+
+int xrtg_scene_get_info(const xrtg_scene* s, xrtg_scene_info* out)
+{
+    if (!s || !out) return fail(XRTG_ERR_INVALID, "NULL argument");
+    *out = s->info;
+    return 0;
+}
+
+} // extern "C"
+
+namespace {
+
+enum StageKind { kStageExtend = 0, kStageConnect, kStageShade, kStageOther };
+
+struct StageTimer {
+    xrtg_scene* s;
+    cudaStream_t st;
+    bool on;
+    size_t used = 0;
+    void begin(int kind)
+    {
+        if (!on) return;
+        if (used + 2 > s->stageEvents.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            s->stageEvents.push_back(a); s->stageEvents.push_back(b);
+        }
+        if (used / 2 >= s->stageKinds.size()) s->stageKinds.push_back(kind);
+        else s->stageKinds[used / 2] = kind;
+        cudaEventRecord(s->stageEvents[used], st);
+    }
+    void end()
+    {
+        if (!on) return;
+        cudaEventRecord(s->stageEvents[used + 1], st);
+        used += 2;
+    }
+};
+
+int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, int maxIter, bool exact)
+{
+    const size_t f4b = sizeof(float4);
+    for (int k = 0; k < 2; ++k) {
+        if (int rc = s->q0[k].ensure(f4b * maxPaths)) return rc;
+        if (int rc = s->q1[k].ensure(f4b * maxPaths)) return rc;
+        if (int rc = s->q2[k].ensure(f4b * maxPaths)) return rc;
+    }
+    if (int rc = s->hits.ensure(f4b * maxPaths)) return rc;
+    const size_t nShadow = size_t(maxPaths) * s->maxShadowPerPath;
+    if (int rc = s->s0.ensure(f4b * nShadow)) return rc;
+    if (int rc = s->s1.ensure(f4b * nShadow)) return rc;
+    if (int rc = s->s2.ensure(f4b * nShadow)) return rc;
+    if (int rc = s->radiance.ensure(f4b * maxPaths)) return rc;
+    if (int rc = s->ctrl.ensure(sizeof(uint32_t) * kCtrlStride * size_t(maxIter + 2))) return rc;
+    if (int rc = s->accum.ensure(sizeof(float) * 3 * size_t(nPixels))) return rc;
+    if (int rc = s->stats.ensure(sizeof(unsigned long long) * kStatCount)) return rc;
+    if (exact) {
+        if (int rc = s->mt.ensure(sizeof(uint32_t) * 624 * size_t(nPixels))) return rc;
+        if (int rc = s->mti.ensure(sizeof(uint32_t) * size_t(nPixels))) return rc;
+    }
+    return 0;
+}
+
+DQueues makeQueues(xrtg_scene* s)
+{
+    DQueues q{};
+    for (int k = 0; k < 2; ++k) {
+        q.q0[k] = static_cast<float4*>(s->q0[k].p);
+        q.q1[k] = static_cast<float4*>(s->q1[k].p);
+        q.q2[k] = static_cast<float4*>(s->q2[k].p);
+    }
+    q.hits = static_cast<float4*>(s->hits.p);
+    q.s0 = static_cast<float4*>(s->s0.p);
+    q.s1 = static_cast<float4*>(s->s1.p);
+    q.s2 = static_cast<float4*>(s->s2.p);
+    q.radiance = static_cast<float4*>(s->radiance.p);
+    q.ctrl = static_cast<uint32_t*>(s->ctrl.p);
+    return q;
+}
+
+DCamera makeCamera(const xrtg_camera* c)
+{
+    DCamera d;
+    std::memcpy(d.c2w, c->c2w, sizeof(d.c2w));
+    d.scale = c->scale;
+    d.aspect = c->aspect;
+    return d;
+}
+
+bool isVolume(int integ) { return integ == XRTG_INT_VOLUME || integ == XRTG_INT_VOLUME_NEE; }
+
+int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p)
+{
+    if (!s || !cam || !p) return fail(XRTG_ERR_INVALID, "NULL argument");
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0) return fail(XRTG_ERR_INVALID, "width/height/spp must be positive");
+    if (uint64_t(p->width) * uint64_t(p->height) > (1u << 28)) return fail(XRTG_ERR_UNSUPPORTED, "image too large");
+    if (p->integrator < XRTG_INT_NORMAL || p->integrator > XRTG_INT_VOLUME_NEE) return fail(XRTG_ERR_UNSUPPORTED, "unknown integrator");
+    if (p->max_depth < 0) return fail(XRTG_ERR_INVALID, "max_depth must be >= 0");
+    if ((p->flags & XRTG_FLAG_EXACT) && p->sample_offset != 0)
+        return fail(XRTG_ERR_UNSUPPORTED, "XRTG_FLAG_EXACT replays the per-pixel mt19937 stream from its seed: sample_offset must be 0");
+    if (p->integrator == XRTG_INT_VOLUME_NEE && s->ds.nLights == 0) return fail(XRTG_ERR_INVALID, "VolumePathTracingNEE needs an area light");
+    return 0;
+}
+
+// The whole render on `st`, result (mean or sum) written to device buffer `out`.
+int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats)
+{
+    const bool exact = (p->flags & XRTG_FLAG_EXACT) != 0;
+    const bool count = (p->flags & XRTG_FLAG_COUNTERS) != 0;
+    const bool brute = (p->flags & XRTG_FLAG_BRUTE_FORCE) != 0;
+    const KernelTable& K = exact ? exactKernels() : fastKernels();
+    const uint32_t nPixels = uint32_t(p->width) * uint32_t(p->height);
+    const int integ = p->integrator;
+    const bool volume = isVolume(integ);
+
+    // samples per wave: exact = 1 (the mt19937 stream of a pixel is sequential across its samples)
+    uint32_t S = 1;
+    if (!exact) {
+        const uint64_t target = 8u << 20; // ~8M paths in flight
+        S = p->samples_per_wave > 0 ? uint32_t(p->samples_per_wave) : uint32_t(std::max<uint64_t>(1, target / nPixels));
+        S = std::min<uint32_t>(S, uint32_t(p->spp));
+        while (uint64_t(S) * nPixels > (1ull << 31) - 64) --S;
+    }
+    int nIter;
+    if (integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI) nIter = p->max_depth;
+    else if (volume) nIter = std::min(4 * p->max_depth + 8, 4096);
+    else nIter = 1;
+    const bool hasShadow = (integ == XRTG_INT_DIRECT || integ == XRTG_INT_GI || integ == XRTG_INT_WHITTED);
+
+    if (int rc = ensureWorkspace(s, nPixels, S * nPixels, nIter, exact)) return rc;
+    DQueues q = makeQueues(s);
+    const DCamera dc = makeCamera(cam);
+    float* accum = static_cast<float*>(s->accum.p);
+    unsigned long long* dstats = static_cast<unsigned long long*>(s->stats.p);
+
+    DWave w{};
+    w.width = p->width; w.height = p->height; w.nPixels = nPixels;
+    w.integrator = integ; w.maxDepth = p->max_depth; w.seed = p->seed;
+    w.mt = static_cast<uint32_t*>(s->mt.p);
+    w.mti = static_cast<uint32_t*>(s->mti.p);
+
+    StageTimer tm{s, st, count};
+    uint64_t launches = 0;
+    CU(cudaEventRecord(s->ev[0], st));
+    CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
+    CU(cudaMemsetAsync(dstats, 0, sizeof(unsigned long long) * kStatCount, st));
+    if (exact) { K.seedMt(st, w); ++launches; }
+
+    for (uint32_t done = 0; done < uint32_t(p->spp); done += S) {
+        const uint32_t sw = std::min<uint32_t>(S, uint32_t(p->spp) - done);
+        w.samplesThisWave = sw;
+        w.nPaths = sw * nPixels;
+        w.sampleBase = uint32_t(p->sample_offset) + done;
+        tm.begin(kStageOther);
+        CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * size_t(nIter + 2), st));
+        K.raygen(st, dc, q, w, nullptr); ++launches;
+        tm.end();
+        for (int b = 0; b < nIter; ++b) {
+            const int src = b & 1;
+            tm.begin(kStageExtend);
+            K.extend(st, s->ds, q, src, b, brute, count, dstats); ++launches;
+            tm.end();
+            tm.begin(kStageShade);
+            if (volume) K.shadeVolume(st, s->ds, q, w, src, b, brute, count, dstats);
+            else K.shadeSurface(st, s->ds, q, w, src, b);
+            ++launches;
+            tm.end();
+            if (hasShadow) {
+                tm.begin(kStageConnect);
+                K.connect(st, s->ds, q, b, brute, count, dstats); ++launches;
+                tm.end();
+            }
+            if (volume) {
+                // the number of loop iterations of integrator.h:418 is data dependent: poll the next queue size
+                CU(cudaMemcpyAsync(s->ctrlHost, q.ctrl + (b + 1) * kCtrlStride + kCtrlRays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (s->ctrlHost[0] == 0) break;
+            }
+        }
+        tm.begin(kStageOther);
+        K.accumulate(st, q, w, accum, dstats); ++launches;
+        tm.end();
+    }
+    const int divisor = (p->flags & XRTG_FLAG_SUM_ONLY) ? 0 : (p->spp_total > 0 ? p->spp_total : p->spp);
+    K.finalize(st, accum, out, size_t(nPixels) * 3, float(divisor)); ++launches;
+    CU(cudaEventRecord(s->ev[1], st));
+    CU(cudaGetLastError());
+
+    if (stats) {
+        CU(cudaMemcpyAsync(s->statsHost, dstats, sizeof(unsigned long long) * kStatCount, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->samples = uint64_t(nPixels) * uint64_t(p->spp);
+        stats->closest_rays = s->statsHost[kStatClosest];
+        stats->shadow_rays = s->statsHost[kStatShadow];
+        stats->dropped_samples = s->statsHost[kStatDropped];
+        stats->nodes_visited = s->statsHost[kStatNodes];
+        stats->tris_tested = s->statsHost[kStatTris];
+        stats->tracking_steps = s->statsHost[kStatSteps];
+        stats->kernel_launches = launches;
+        CU(cudaEventElapsedTime(&stats->render_ms, s->ev[0], s->ev[1]));
+        if (count) {
+            float acc[4] = {0, 0, 0, 0};
+            for (size_t k = 0; k + 1 < tm.used; k += 2) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, s->stageEvents[k], s->stageEvents[k + 1]);
+                acc[s->stageKinds[k / 2]] += ms;
+            }
+            stats->extend_ms = acc[kStageExtend]; stats->connect_ms = acc[kStageConnect];
+            stats->shade_ms = acc[kStageShade]; stats->other_ms = acc[kStageOther];
+        }
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int xrtg_render_device(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgb_device, void* cuda_stream,
+                       xrtg_stats* stats)
+{
+    if (int rc = checkParams(s, cam, p)) return rc;
+    if (!rgb_device) return fail(XRTG_ERR_INVALID, "rgb_device is NULL");
+    CU(cudaSetDevice(s->device));
+    return renderOnStream(s, cam, p, rgb_device, static_cast<cudaStream_t>(cuda_stream), stats);
+}
+
+int xrtg_render(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgb_host, xrtg_stats* stats)
+{
+    if (int rc = checkParams(s, cam, p)) return rc;
+    if (!rgb_host) return fail(XRTG_ERR_INVALID, "rgb_host is NULL");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = sizeof(float) * 3 * size_t(p->width) * size_t(p->height);
+    if (int rc = s->outDev.ensure(bytes)) return rc;
+    xrtg_stats local{};
+    if (int rc = renderOnStream(s, cam, p, static_cast<float*>(s->outDev.p), s->stream, stats ? &local : nullptr)) return rc;
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    CU(cudaMemcpyAsync(rgb_host, s->outDev.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev[3], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (stats) {
+        *stats = local;
+        CU(cudaEventElapsedTime(&stats->d2h_ms, s->ev[2], s->ev[3]));
+    }
+    return 0;
+}
+
+int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int height, int spp, const float* jitter_uv, uint32_t flags,
+                       xrtg_hit* out)
+{
+    if (!s || !cam || !out) return fail(XRTG_ERR_INVALID, "NULL argument");
+    if (width <= 0 || height <= 0 || spp <= 0) return fail(XRTG_ERR_INVALID, "width/height/spp must be positive");
+    CU(cudaSetDevice(s->device));
+    const uint32_t nPixels = uint32_t(width) * uint32_t(height);
+    const uint64_t nPaths = uint64_t(nPixels) * uint64_t(spp);
+    if (nPaths > (1ull << 30)) return fail(XRTG_ERR_UNSUPPORTED, "too many primary rays for one call");
+    const KernelTable& K = exactKernels(); // primary-hit parity always uses the no-FMA instantiation
+    if (int rc = ensureWorkspace(s, nPixels, uint32_t(nPaths), 1, true)) return rc;
+    if (int rc = s->jitter.ensure(sizeof(float) * 2 * nPaths)) return rc;
+    DQueues q = makeQueues(s);
+    cudaStream_t st = s->stream;
+    DWave w{};
+    w.width = width; w.height = height; w.nPixels = nPixels; w.nPaths = uint32_t(nPaths);
+    w.samplesThisWave = uint32_t(spp); w.sampleBase = 0; w.integrator = XRTG_INT_NORMAL; w.maxDepth = 1;
+    w.mt = static_cast<uint32_t*>(s->mt.p);
+    w.mti = static_cast<uint32_t*>(s->mti.p);
+    float* dj = static_cast<float*>(s->jitter.p);
+    if (jitter_uv) CU(cudaMemcpyAsync(dj, jitter_uv, sizeof(float) * 2 * nPaths, cudaMemcpyHostToDevice, st));
+    else {
+        K.seedMt(st, w);
+        K.genJitter(st, w, spp, dj);
+    }
+    unsigned long long* dstats = static_cast<unsigned long long*>(s->stats.p);
+    CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
+    K.raygen(st, makeCamera(cam), q, w, dj);
+    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0, false, dstats);
+    CU(cudaGetLastError());
+    // hits are indexed by path id = s * nPixels + pixel; the ABI wants [(pixel * spp) + s]
+    std::vector<float4> tmp(nPaths);
+    CU(cudaMemcpyAsync(tmp.data(), q.hits, sizeof(float4) * nPaths, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (uint64_t pid = 0; pid < nPaths; ++pid) {
+        const uint64_t pix = pid % nPixels, k = pid / nPixels;
+        xrtg_hit& h = out[pix * spp + k];
+        const float4 v = tmp[pid];
+        std::memcpy(&h.prim, &v.w, 4);
+        h.t = h.prim >= 0 ? v.x : FLT_MAX;
+        h.u = v.y; h.v = v.z;
+    }
+    return 0;
+}
+
+int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir, const float* tmax, int any_hit, uint32_t flags,
+                    xrtg_hit* out_hits)
+{
+    if (!s || !org || !dir || !out_hits) return fail(XRTG_ERR_INVALID, "NULL argument");
+    if (n < 0) return fail(XRTG_ERR_INVALID, "negative ray count");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    if (int rc = s->rayTmp[0].ensure(sizeof(float) * 3 * size_t(n))) return rc;
+    if (int rc = s->rayTmp[1].ensure(sizeof(float) * 3 * size_t(n))) return rc;
+    if (int rc = s->rayTmp[2].ensure(sizeof(float) * size_t(n))) return rc;
+    if (int rc = s->rayTmp[3].ensure(sizeof(float4) * size_t(n))) return rc;
+    CU(cudaMemcpyAsync(s->rayTmp[0].p, org, sizeof(float) * 3 * size_t(n), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->rayTmp[1].p, dir, sizeof(float) * 3 * size_t(n), cudaMemcpyHostToDevice, st));
+    if (tmax) CU(cudaMemcpyAsync(s->rayTmp[2].p, tmax, sizeof(float) * size_t(n), cudaMemcpyHostToDevice, st));
+    const KernelTable& K = (flags & XRTG_FLAG_EXACT) || true ? exactKernels() : fastKernels();
+    K.traceRays(st, s->ds, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
+                tmax ? static_cast<const float*>(s->rayTmp[2].p) : nullptr, n, any_hit != 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0,
+                static_cast<float4*>(s->rayTmp[3].p));
+    CU(cudaGetLastError());
+    static_assert(sizeof(xrtg_hit) == sizeof(float4), "xrtg_hit must be 16 bytes");
+    CU(cudaMemcpyAsync(out_hits, s->rayTmp[3].p, sizeof(float4) * size_t(n), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+} // extern "C"

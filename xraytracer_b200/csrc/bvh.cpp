@@ -1,0 +1,225 @@
+// bvh.cpp — binned-SAH BVH2 builder (host, OpenMP tasks), see bvh.h.
+#include "bvh.h"
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace xrt {
+namespace {
+
+struct Box {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    void grow(const float* p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box& b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const
+    {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct BuildNode {
+    Box box;
+    int32_t left = -1, right = -1; // children (build-node indices) or -1
+    uint32_t first = 0, count = 0; // leaf range in `order`
+    int depth = 0;
+};
+
+struct Builder {
+    const float* tri;
+    std::vector<Box> tbox;
+    std::vector<float> cent; // 3 per triangle
+    std::vector<uint32_t> order;
+    std::vector<BuildNode> pool;
+    std::atomic<int32_t> next{0};
+    int maxLeaf = 4;
+    static constexpr int kBins = 16;
+    static constexpr int kMaxDepth = 56;
+
+    int32_t alloc() { return next.fetch_add(1); }
+
+    void build(int32_t ni, uint32_t first, uint32_t count, int depth)
+    {
+        BuildNode& node = pool[ni];
+        node.depth = depth;
+        Box b, cb;
+        for (uint32_t i = first; i < first + count; ++i) {
+            b.grow(tbox[order[i]]);
+            cb.grow(&cent[3 * order[i]]);
+        }
+        node.box = b;
+        auto makeLeaf = [&]() { node.first = first; node.count = count; };
+        if (count <= 1) { makeLeaf(); return; }
+
+        // binned SAH over the three axes
+        float bestCost = FLT_MAX;
+        int bestAxis = -1, bestSplit = -1;
+        if (depth < kMaxDepth) {
+            for (int a = 0; a < 3; ++a) {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Box bins[kBins];
+                uint32_t cnt[kBins] = {};
+                const float k = kBins * (1.f - 1e-6f) / ext;
+                for (uint32_t i = first; i < first + count; ++i) {
+                    const uint32_t t = order[i];
+                    int bi = int((cent[3 * t + a] - cb.lo[a]) * k);
+                    bi = std::min(std::max(bi, 0), kBins - 1);
+                    bins[bi].grow(tbox[t]);
+                    cnt[bi]++;
+                }
+                float rightArea[kBins];
+                uint32_t rightCnt[kBins];
+                Box acc;
+                uint32_t c = 0;
+                for (int i = kBins - 1; i > 0; --i) {
+                    acc.grow(bins[i]); c += cnt[i];
+                    rightArea[i] = acc.area(); rightCnt[i] = c;
+                }
+                acc = Box(); c = 0;
+                for (int i = 0; i < kBins - 1; ++i) {
+                    acc.grow(bins[i]); c += cnt[i];
+                    if (c == 0 || rightCnt[i + 1] == 0) continue;
+                    const float cost = acc.area() * float(c) + rightArea[i + 1] * float(rightCnt[i + 1]);
+                    if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = i; }
+                }
+            }
+        }
+        uint32_t mid = 0;
+        if (bestAxis >= 0) {
+            const float leafCost = b.area() * float(count);
+            if (count <= uint32_t(maxLeaf) && leafCost <= bestCost + b.area() /*traversal step*/) { makeLeaf(); return; }
+            const int a = bestAxis;
+            const float ext = cb.hi[a] - cb.lo[a];
+            const float k = kBins * (1.f - 1e-6f) / ext;
+            const float lo = cb.lo[a];
+            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t t) {
+                int bi = int((cent[3 * t + a] - lo) * k);
+                bi = std::min(std::max(bi, 0), kBins - 1);
+                return bi <= bestSplit;
+            });
+            mid = uint32_t(it - order.begin());
+        }
+        if (bestAxis < 0 || mid == first || mid == first + count) {
+            // identical centroids or depth limit: leaf if small enough, else split the index range in half
+            if (count <= uint32_t(maxLeaf)) { makeLeaf(); return; }
+            mid = first + count / 2;
+        }
+        const int32_t l = alloc(), r = alloc();
+        pool[ni].left = l;
+        pool[ni].right = r;
+        const uint32_t lc = mid - first, rc = first + count - mid;
+        if (count > 8192) {
+#pragma omp task default(shared) firstprivate(l, first, lc, depth)
+            build(l, first, lc, depth + 1);
+#pragma omp task default(shared) firstprivate(r, mid, rc, depth)
+            build(r, mid, rc, depth + 1);
+#pragma omp taskwait
+        }
+        else {
+            build(l, first, lc, depth + 1);
+            build(r, mid, rc, depth + 1);
+        }
+    }
+};
+
+void setChild(BvhNode& n, int slot, const Box& b, float pad, int32_t child, int32_t count)
+{
+    float* lo = slot ? n.lo1 : n.lo0;
+    float* hi = slot ? n.hi1 : n.hi0;
+    for (int a = 0; a < 3; ++a) { lo[a] = b.lo[a] - pad; hi[a] = b.hi[a] + pad; }
+    (slot ? n.child1 : n.child0) = child;
+    (slot ? n.count1 : n.count0) = count;
+}
+
+void setEmpty(BvhNode& n, int slot)
+{
+    float* lo = slot ? n.lo1 : n.lo0;
+    float* hi = slot ? n.hi1 : n.hi0;
+    for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
+    (slot ? n.child1 : n.child0) = 0;
+    (slot ? n.count1 : n.count0) = -1;
+}
+
+} // namespace
+
+void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out)
+{
+    out = Bvh();
+    if (n == 0) {
+        out.nodes.resize(1);
+        setEmpty(out.nodes[0], 0);
+        setEmpty(out.nodes[0], 1);
+        return;
+    }
+    Builder B;
+    B.tri = tri;
+    B.maxLeaf = maxLeaf;
+    B.tbox.resize(n);
+    B.cent.resize(size_t(n) * 3);
+    B.order.resize(n);
+    Box scene;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < int64_t(n); ++i) {
+        Box b;
+        b.grow(tri + 9 * i); b.grow(tri + 9 * i + 3); b.grow(tri + 9 * i + 6);
+        B.tbox[i] = b;
+        for (int a = 0; a < 3; ++a) B.cent[3 * i + a] = 0.5f * (b.lo[a] + b.hi[a]);
+        B.order[i] = uint32_t(i);
+    }
+    for (uint32_t i = 0; i < n; ++i) scene.grow(B.tbox[i]);
+    // conservative padding: 2^-15 of the largest absolute coordinate / extent of the scene
+    float mag = 0.f;
+    for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(scene.lo[a]), std::fabs(scene.hi[a])));
+    out.pad = std::max(mag * (1.f / 32768.f), 1e-30f);
+
+    B.pool.resize(size_t(2) * n + 1);
+    const int32_t root = B.alloc();
+#pragma omp parallel
+#pragma omp single nowait
+    B.build(root, 0, n, 0);
+
+    // flatten: every inner build node becomes one BvhNode holding its two children's boxes
+    const int32_t nBuild = B.next.load();
+    std::vector<int32_t> innerIndex(nBuild, -1);
+    int32_t nInner = 0;
+    for (int32_t i = 0; i < nBuild; ++i) if (B.pool[i].left >= 0) innerIndex[i] = nInner++;
+    // keep the root first
+    if (B.pool[root].left >= 0 && innerIndex[root] != 0) {
+        for (int32_t i = 0; i < nBuild; ++i) if (innerIndex[i] == 0) { std::swap(innerIndex[i], innerIndex[root]); break; }
+    }
+    out.triOrder = B.order;
+    const float rootArea = std::max(B.pool[root].box.area(), 1e-30f);
+    double cost = 0.0;
+    int depth = 0;
+    if (B.pool[root].left < 0) {
+        // single leaf: root with one real child
+        out.nodes.resize(1);
+        setChild(out.nodes[0], 0, B.pool[root].box, out.pad, int32_t(B.pool[root].first), int32_t(B.pool[root].count));
+        setEmpty(out.nodes[0], 1);
+        out.depth = 1;
+        out.sahCost = float(B.pool[root].count);
+        return;
+    }
+    out.nodes.resize(nInner);
+    for (int32_t i = 0; i < nBuild; ++i) {
+        const BuildNode& bn = B.pool[i];
+        depth = std::max(depth, bn.depth + 1);
+        if (bn.left < 0) { cost += double(bn.box.area() / rootArea) * bn.count; continue; }
+        cost += double(bn.box.area() / rootArea);
+        BvhNode& o = out.nodes[innerIndex[i]];
+        const int32_t ch[2] = {bn.left, bn.right};
+        for (int s = 0; s < 2; ++s) {
+            const BuildNode& c = B.pool[ch[s]];
+            if (c.left >= 0) setChild(o, s, c.box, out.pad, innerIndex[ch[s]], 0);
+            else setChild(o, s, c.box, out.pad, int32_t(c.first), int32_t(c.count));
+        }
+    }
+    out.depth = depth;
+    out.sahCost = float(cost);
+}
+
+} // namespace xrt

@@ -1,0 +1,98 @@
+// device_types.h — PODs shared by the host side of libxrtgpu.so (api.cpp) and the sm_100a kernels
+// (wavefront.cuh). Layouts are chosen for 128-bit coalesced loads: every array is an array of float4.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xrt {
+
+// meta word of a primitive's shading record (prims[4*id+3].w)
+enum : uint32_t {
+    kMetaKindMask = 3u,      // xrtg_object_kind
+    kMetaHasMaterial = 4u,
+    kMetaLightShift = 8,     // (area light index + 1) in bits 8..19
+    kMetaMediumShift = 20,   // (medium index + 1) in bits 20..31
+};
+
+struct DLight {      // area light, world space (light.cpp:6-14, 49-57, 84-90)
+    float4 v0_kind;  // v0 | kind as int bits   (sphere: centre)
+    float4 e1_r;     // e1 = v1 - v0 | radius
+    float4 e2;       // e2 = v2 - v0
+    float4 Ng;       // e1 x e2 (un-normalised)
+    float4 Le;
+    float4 v1, v2;   // triangle sampling uses A,B,C directly
+};
+
+struct DDelta {      // delta light (light.cpp:115-142)
+    float4 p_kind;   // position or direction | kind
+    float4 L;        // color * intensity
+};
+
+struct DMedium {
+    int kind;
+    float g;
+    float sigma_a[3], sigma_s[3], sigma_t[3];
+    float densityMul, majorant, invMajorant;
+    int grid;
+};
+
+struct DGrid {
+    const float* data; // nx*ny*nz, x fastest
+    int nx, ny, nz;
+    float origin[3];
+    float voxel, background;
+};
+
+// Everything the kernels need to know about the scene; passed by value (fits the 4 KB param space).
+struct DScene {
+    const float4* nodes;   // 4 float4 per BVH node (bvh.h: BvhNode)
+    const float4* tris;    // 3 float4 per triangle in LEAF order: v0|prim id, e1|flags(bit0 emitter), e2|0
+    const float4* tris_id; // same triangles in PRIMITIVE-ID order (brute-force parity path), mesh triangles only
+    const float4* prims;   // 4 float4 per primitive id: shading record
+                           //   tri:    n0|ng.x  n1|ng.y  n2|ng.z  albedo|meta
+                           //   sphere: centre|radius  -  -  albedo|meta          box: -  -  -  0|meta
+    const float4* spheres; // 2 float4 per sphere: centre|radius , (prim id, emitter flag, 0, 0) as int bits
+    const float4* boxes;   // 2 float4 per box: pmin|prim id bits , pmax|0
+    const DLight* lights;
+    const DDelta* dlights;
+    const DMedium* media;
+    const DGrid* grids;
+    int nTris, nSpheres, nBoxes, nLights, nDelta, nPrims, nBruteTris;
+};
+
+struct DCamera {
+    float c2w[16];
+    float scale, aspect;
+};
+
+// One wave of paths. Ray queue entry i (SoA over three float4 arrays):
+//   q0 = origin.xyz | throughput.x     q1 = direction.xyz | throughput.y
+//   q2 = throughput.z | path id | depth | rng counter            (last three as int bits)
+// Shadow queue entry: s0 = origin.xyz | tmax   s1 = direction.xyz | path id   s2 = contribution.rgb | 0
+struct DQueues {
+    float4 *q0[2], *q1[2], *q2[2]; // ping-pong ray queues
+    float4* hits;                  // t,u,v | prim id, indexed like the ray queue being extended
+    float4 *s0, *s1, *s2;          // shadow queue
+    float4* radiance;              // per path id: rgb | unused
+    uint32_t* ctrl;                // per bounce b: ctrl[8b+0]=#rays  +1=#shadow  +2..+4 = work-fetch cursors
+};
+
+enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
+
+// device-side statistics (uint64 each)
+enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatSteps, kStatCount };
+
+struct DWave {
+    int width, height;
+    uint32_t nPixels;
+    uint32_t nPaths;        // nPixels * samplesThisWave
+    uint32_t sampleBase;    // index of the first sample of this wave (sample_offset + done so far)
+    uint32_t samplesThisWave;
+    int integrator, maxDepth;
+    uint32_t seed;
+    // exact mode: per-pixel mt19937 state, word-major [624][nPixels], and the per-pixel cursor
+    uint32_t* mt;
+    uint32_t* mti;
+};
+
+} // namespace xrt

@@ -1,0 +1,1267 @@
+// wavefront.cuh — the sm_100a wavefront path-tracing kernels of libxrtgpu.so.
+//
+// Included by two translation units:
+//   kernels_exact.cu  XRT_EXACT=1, compiled with -fmad=false : reproduces the reference's arithmetic (no FMA
+//                     contraction, IEEE div/sqrt, same operation order) and its per-pixel std::mt19937 sample
+//                     stream (renderer.cpp:35-36, sampler.h:48-49). One sample per pixel per wave.
+//   kernels_fast.cu   XRT_EXACT=0, FMA allowed : counter-based Philox4x32-7 keyed (seed,pixel)/(sample,block),
+//                     several samples per pixel per wave.
+//
+// Pipeline per wave (all kernels are persistent: grid = k x 148 SMs, warps fetch 32 queue entries at a time
+// through an atomic cursor, queue sizes live in device memory so no host round trip is needed):
+//   raygen  -> [ extend (closest hit, SAH BVH) -> shade (Le, RR, NEE sample, BSDF sample; warp-ballot
+//   compaction into the next ray queue and the shadow queue) -> connect (any hit) ] x bounces -> accumulate
+//
+// Reference citations (paths relative to /root/reference/Src) are on each device function.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "device_types.h"
+#include <xrtgpu.h>
+
+#ifndef XRT_EXACT
+#error "define XRT_EXACT and XRT_NS before including wavefront.cuh"
+#endif
+
+namespace xrt {
+namespace XRT_NS {
+
+constexpr bool kExact = (XRT_EXACT != 0);
+constexpr int kBlock = 128;          // threads per CTA for every kernel
+constexpr int kStackSmem = 24;       // traversal stack entries kept in shared memory per thread
+constexpr int kStackLocal = 40;      // overflow entries (local memory); builder depth limit is 56
+constexpr float kPI = 3.14159265359; // geometry.h:10
+constexpr float kRayEps = 1e-3f;     // geometry.h:23
+
+// ---------------------------------------------------------------------------------------------------------
+// small vector algebra, operation order as in geometry.h:177-262
+// ---------------------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 mk(float s) { return V3{s, s, s}; }
+__device__ __forceinline__ V3 xyz(const float4& v) { return V3{v.x, v.y, v.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator/(V3 a, V3 b) { return mk(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ V3 operator+(V3 a, float k) { return mk(a.x + k, a.y + k, a.z + k); }
+__device__ __forceinline__ V3 operator*(V3 a, float k) { return mk(a.x * k, a.y * k, a.z * k); }
+__device__ __forceinline__ V3 operator*(float k, V3 a) { return a * k; }
+__device__ __forceinline__ V3 operator/(V3 a, float k) { return mk(a.x / k, a.y / k, a.z / k); }
+__device__ __forceinline__ V3 operator/(float k, V3 a) { return mk(k / a.x, k / a.y, k / a.z); }
+__device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float length(V3 v) { return sqrtf(dot(v, v)); }   // geometry.cpp:3-6
+__device__ __forceinline__ V3 normalize(V3 v) { return v / length(v); }       // geometry.cpp:13-16 (divide, not rsqrt)
+__device__ __forceinline__ V3 vexp(V3 v) { return mk(expf(v.x), expf(v.y), expf(v.z)); }
+__device__ __forceinline__ float comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// std::min / std::max with their NaN behaviour
+__device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ bool anyNan(V3 v) { return isnan(v.x) || isnan(v.y) || isnan(v.z); }
+
+// geometry.cpp:44-48
+__device__ __forceinline__ void orthonormalBasis(V3 n, V3& t, V3& b)
+{
+    const float sign = copysignf(1.0f, n.z);
+    const float a = -1.0f / (sign + n.z);
+    const float c = n.x * n.y * a;
+    t = mk(1.0f + sign * n.x * n.x * a, sign * c, -sign * n.x);
+    b = mk(c, sign + n.y * n.y * a, -n.y);
+}
+// geometry.h:693-701
+__device__ __forceinline__ V3 localToWorld(V3 v, V3 lx, V3 ly, V3 lz)
+{
+    return mk(v.x * lx.x + v.y * ly.x + v.z * lz.x, v.x * lx.y + v.y * ly.y + v.z * lz.y, v.x * lx.z + v.y * ly.z + v.z * lz.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RNG. Exact: std::mt19937 restated (state word-major in HBM: mt[word * nPixels + pixel]) with libstdc++'s
+// generate_canonical<float,24> mapping (sampler.h:37-50). Fast: Philox4x32-7, key = (seed, pixel),
+// counter = (sample, block): the union of samples over GPUs equals the 1-GPU sample set.
+// ---------------------------------------------------------------------------------------------------------
+struct Rng {
+    // exact
+    uint32_t* mt;
+    uint32_t* mti;
+    uint32_t stride, pix, idx;
+    // fast
+    uint32_t k0, k1, sample, ctr, bufBlock;
+    uint4 buf;
+
+    __device__ __forceinline__ void open(const DWave& w, uint32_t pid, uint32_t counter)
+    {
+        pix = pid % w.nPixels;
+        if constexpr (kExact) {
+            mt = w.mt; mti = w.mti; stride = w.nPixels;
+            idx = mti[pix];
+        }
+        else {
+            k0 = w.seed; k1 = pix;
+            sample = w.sampleBase + pid / w.nPixels;
+            ctr = counter;
+            bufBlock = 0xffffffffu;
+        }
+    }
+    __device__ __forceinline__ uint32_t close()
+    {
+        if constexpr (kExact) { mti[pix] = idx; return 0; }
+        else return ctr;
+    }
+    __device__ __forceinline__ void philox(uint32_t block)
+    {
+        uint32_t c0 = sample, c1 = block, c2 = 0x243F6A88u, c3 = 0x85A308D3u, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        buf = make_uint4(c0, c1, c2, c3);
+        bufBlock = block;
+    }
+    __device__ __forceinline__ float next()
+    {
+        if constexpr (kExact) {
+            const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
+            const uint32_t y = (mt[size_t(i) * stride + pix] & 0x80000000u) | (mt[size_t(i1) * stride + pix] & 0x7fffffffu);
+            uint32_t v = mt[size_t(im) * stride + pix] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            mt[size_t(i) * stride + pix] = v;
+            idx = i1;
+            v ^= v >> 11;
+            v ^= (v << 7) & 0x9d2c5680u;
+            v ^= (v << 15) & 0xefc60000u;
+            v ^= v >> 18;
+            const float r = __uint2float_rn(v) * 2.3283064365386963e-10f; // float(raw) / 2^32
+            return (r >= 1.0f) ? 0x1.fffffep-1f : r;
+        }
+        else {
+            const uint32_t blk = ctr >> 2;
+            if (blk != bufBlock) philox(blk);
+            const uint32_t lane = ctr & 3u;
+            ++ctr;
+            const uint32_t v = lane == 0 ? buf.x : (lane == 1 ? buf.y : (lane == 2 ? buf.z : buf.w));
+            return float(v >> 8) * 5.9604644775390625e-8f; // [0,1), 24 bits
+        }
+    }
+};
+
+// mt19937 seeding (gen.seed(j + W*i), renderer.cpp:36): one thread per pixel
+__global__ void __launch_bounds__(kBlock) k_seed_mt(uint32_t* mt, uint32_t* mti, uint32_t nPixels)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nPixels; p += gridDim.x * blockDim.x) {
+        uint32_t s = p; // seed = j + W*i = linear pixel index
+        mt[p] = s;
+        for (uint32_t i = 1; i < 624; ++i) {
+            s = 1812433253u * (s ^ (s >> 30)) + i;
+            mt[size_t(i) * nPixels + p] = s;
+        }
+        mti[p] = 0;
+    }
+}
+
+// jitter of the primary samples exactly as renderer.cpp:44-47 draws them when nothing else consumes the
+// stream (parity hook xrtg_trace_primary with jitter_uv == NULL): thread per pixel, samples in order.
+__global__ void __launch_bounds__(kBlock) k_gen_jitter(DWave w, int spp, float* __restrict__ jitter)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < w.nPixels; p += gridDim.x * blockDim.x) {
+        DWave w1 = w;
+        w1.samplesThisWave = 1;
+        for (int s = 0; s < spp; ++s) {
+            Rng rng;
+            w1.sampleBase = w.sampleBase + uint32_t(s);
+            rng.open(w1, p, 0);
+            jitter[(size_t(p) * spp + s) * 2] = rng.next();
+            jitter[(size_t(p) * spp + s) * 2 + 1] = rng.next();
+            rng.close();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// intersection primitives
+// ---------------------------------------------------------------------------------------------------------
+
+// Mesh::rayTriangleIntersect (primitive.cpp:140-168, CULLING undefined); e1 = v1-v0, e2 = v2-v0 precomputed
+// on the host with the same fp32 subtraction the reference performs per ray.
+__device__ __forceinline__ bool rayTriangle(V3 orig, V3 dir, V3 v0, V3 e1, V3 e2, float& t, float& u, float& v)
+{
+    const V3 pvec = cross(dir, e2);
+    const float det = dot(e1, pvec);
+    if (fabsf(det) < FLT_EPSILON) return false;
+    const float invDet = 1 / det;
+    const V3 tvec = orig - v0;
+    u = dot(tvec, pvec) * invDet;
+    if (u < 0 || u > 1) return false;
+    const V3 qvec = cross(tvec, e1);
+    v = dot(dir, qvec) * invDet;
+    if (v < 0 || u + v > 1) return false;
+    t = dot(e2, qvec) * invDet;
+    return t > FLT_EPSILON;
+}
+
+// Sphere::doIntersect / solveQuadratic (primitive.h:133-177); the -0.5 literals and the unqualified sqrt() make
+// the root computation double precision in the reference.
+__device__ __forceinline__ bool sphereT(float4 cr, V3 orig, V3 dir, float& tNear)
+{
+    const V3 L = orig - xyz(cr);
+    const float a = dot(dir, dir);
+    const float b = 2 * dot(dir, L);
+    const float r2 = cr.w * cr.w;
+    const float c = dot(L, L) - r2;
+    float t0, t1;
+    const float discr = b * b - 4 * a * c;
+    if (discr < 0) return false;
+    else if (discr == 0) { t0 = t1 = float(-0.5 * double(b) / double(a)); }
+    else {
+        const float q = (b > 0) ? float(-0.5 * (double(b) + sqrt(double(discr)))) : float(-0.5 * (double(b) - sqrt(double(discr))));
+        t0 = q / a;
+        t1 = c / q;
+    }
+    if (t0 > t1) { const float s = t0; t0 = t1; t1 = s; }
+    if (t0 < 0) {
+        t0 = t1;
+        if (t0 < 0) return false;
+    }
+    tNear = t0;
+    return true;
+}
+
+// BoxMesh::intersect slabs (primitive.h:243-264)
+__device__ __forceinline__ bool boxSlabs(V3 pmin, V3 pmax, V3 o, V3 d, float& t0, float& t1)
+{
+    const V3 inv = 1.0f / d;
+    const V3 top = inv * (pmax - o);
+    const V3 bot = inv * (pmin - o);
+    const V3 tmn = mk(smin(top.x, bot.x), smin(top.y, bot.y), smin(top.z, bot.z));
+    const V3 tmx = mk(smax(top.x, bot.x), smax(top.y, bot.y), smax(top.z, bot.z));
+    t0 = smax(smax(tmn.x, tmn.y), tmn.z);
+    t1 = smin(smin(tmx.x, tmx.y), tmx.z);
+    if (t0 > t1 || t1 <= 0.0f) return false;
+    t0 = smax(t0, 0.0f);
+    return true;
+}
+
+struct Hit {
+    float t, u, v;
+    int prim;
+};
+
+// Closest-hit candidate rule that reproduces "first strictly smaller t in primitive order wins"
+// (scene.cpp:193-197, primitive.cpp:100) under an arbitrary visiting order: lower t, or equal t and lower id.
+__device__ __forceinline__ void consider(Hit& h, float t, float u, float v, int id)
+{
+    if (t < h.t || (t == h.t && id < h.prim)) { h.t = t; h.u = u; h.v = v; h.prim = id; }
+}
+
+struct TraceCounters {
+    uint32_t nodes = 0, tris = 0;
+};
+
+// Conservative slab test against a PADDED child box (bvh.cpp pads by 2^-15 of the scene magnitude); fminf/fmaxf
+// drop NaNs (0*inf), which only ever makes the test pass. tmaxRay is inclusive: a node whose entry distance
+// equals the current best is still visited (tie-break by primitive id needs it).
+__device__ __forceinline__ bool slab(const float lo0, const float lo1, const float lo2, const float hi0, const float hi1,
+                                     const float hi2, V3 idir, V3 ood, float tmaxRay, float& tnear)
+{
+    const float x0 = fmaf(lo0, idir.x, -ood.x), x1 = fmaf(hi0, idir.x, -ood.x);
+    const float y0 = fmaf(lo1, idir.y, -ood.y), y1 = fmaf(hi1, idir.y, -ood.y);
+    const float z0 = fmaf(lo2, idir.z, -ood.z), z1 = fmaf(hi2, idir.z, -ood.z);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmaxRay));
+    tnear = tn;
+    return tn <= tf;
+}
+
+// BVH2 traversal, while-while, per-thread stack in shared memory ([entry][thread], conflict-free) with a
+// local-memory overflow. ANY=false: closest hit into `h` (h.t / h.prim pre-set by the caller = current best;
+// only primitives with id > minId are considered). ANY=true: returns true at the first triangle with
+// t < h.t that is not an emitter proxy (Scene::occluded, scene.cpp:202-211).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool traverse(const DScene& sc, V3 o, V3 d, Hit& h, int minId, int* sstack, TraceCounters& tc)
+{
+    const V3 idir = 1.0f / d;
+    const V3 ood = mk(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    int lstack[kStackLocal];
+    int sp = 0;
+    int node = 0; // root
+    const float4* __restrict__ nodes = sc.nodes;
+    const float4* __restrict__ tris = sc.tris;
+    while (true) {
+        // ---- inner nodes ----
+        const float4 n0 = __ldg(nodes + 4 * node), n1 = __ldg(nodes + 4 * node + 1), n2 = __ldg(nodes + 4 * node + 2);
+        const int4 n3 = __ldg(reinterpret_cast<const int4*>(nodes + 4 * node + 3));
+        if (COUNT) tc.nodes++;
+        float t0n, t1n;
+        const bool h0 = (n3.z >= 0) && slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, idir, ood, h.t, t0n);
+        const bool h1 = (n3.w >= 0) && slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, idir, ood, h.t, t1n);
+        // children to process now: leaves are intersected immediately, inner children pushed / descended
+        int next = -1;
+        int c0 = n3.x, k0 = n3.z, c1 = n3.y, k1 = n3.w;
+        bool a0 = h0, a1 = h1;
+        if (a0 && a1 && t1n < t0n) { // visit the nearer child first
+            const int tc_ = c0; c0 = c1; c1 = tc_;
+            const int tk = k0; k0 = k1; k1 = tk;
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const bool act = s == 0 ? a0 : a1;
+            const int c = s == 0 ? c0 : c1, k = s == 0 ? k0 : k1;
+            if (!act) continue;
+            if (k > 0) {
+                for (int i = 0; i < k; ++i) {
+                    const float4 q0 = __ldg(tris + 3 * (c + i)), q1 = __ldg(tris + 3 * (c + i) + 1), q2 = __ldg(tris + 3 * (c + i) + 2);
+                    if (COUNT) tc.tris++;
+                    const int id = __float_as_int(q0.w);
+                    float t, u, v;
+                    if (ANY) {
+                        if ((__float_as_int(q1.w) & 1) == 0 && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < h.t) return true;
+                    }
+                    else if (id > minId && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(h, t, u, v, id);
+                }
+            }
+            else if (next < 0) next = c;
+            else { // push the farther inner child
+                if (sp < kStackSmem) sstack[sp * kBlock] = c;
+                else lstack[sp - kStackSmem] = c;
+                ++sp;
+            }
+        }
+        if (next >= 0) { node = next; continue; }
+        if (sp == 0) break;
+        --sp;
+        node = (sp < kStackSmem) ? sstack[sp * kBlock] : lstack[sp - kStackSmem];
+    }
+    return false;
+}
+
+// Brute force in primitive-id order (parity/debug path; XRTG_FLAG_BRUTE_FORCE): the reference's own loops.
+template <bool ANY>
+__device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, int minId)
+{
+    for (int i = 0; i < sc.nBruteTris; ++i) {
+        const float4 q0 = __ldg(sc.tris_id + 3 * i), q1 = __ldg(sc.tris_id + 3 * i + 1), q2 = __ldg(sc.tris_id + 3 * i + 2);
+        const int id = __float_as_int(q0.w);
+        float t, u, v;
+        if (ANY) {
+            if ((__float_as_int(q1.w) & 1) == 0 && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < h.t) return true;
+        }
+        else if (id > minId && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(h, t, u, v, id);
+    }
+    return false;
+}
+
+// Scene::intersect (scene.cpp:190-200) for one ray: boxes first (the LAST box hit in object order overwrites
+// whatever came before it, primitive.h:259-261; objects after it win only with a strictly smaller t), then
+// triangles through the BVH, then analytic spheres. Box hits return t1 in h.u.
+template <bool COUNT>
+__device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool brute, Hit& h, int* sstack, TraceCounters& tc)
+{
+    h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
+    int minId = -1;
+    for (int b = 0; b < sc.nBoxes; ++b) { // boxes[] are in object order
+        const float4 bl = __ldg(sc.boxes + 2 * b), bh = __ldg(sc.boxes + 2 * b + 1);
+        float t0, t1;
+        if (boxSlabs(xyz(bl), xyz(bh), o, d, t0, t1)) { h.t = t0; h.u = t1; h.v = 0.f; h.prim = __float_as_int(bl.w); minId = h.prim; }
+    }
+    if (sc.nTris > 0) {
+        if (brute) bruteTris<false>(sc, o, d, h, minId);
+        else traverse<false, COUNT>(sc, o, d, h, minId, sstack, tc);
+    }
+    for (int s = 0; s < sc.nSpheres; ++s) {
+        const float4 cr = __ldg(sc.spheres + 2 * s);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * s + 1));
+        float t;
+        if (meta.x > minId && sphereT(cr, o, d, t)) consider(h, t, 0.f, 0.f, meta.x);
+    }
+    if (h.prim == 0x7fffffff) h.prim = -1;
+}
+
+// Scene::occluded (scene.cpp:202-211): BoxMesh::occluded is always true (primitive.h:266-268)
+template <bool COUNT>
+__device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax, bool brute, int* sstack, TraceCounters& tc)
+{
+    if (sc.nBoxes > 0) return true;
+    Hit h;
+    h.t = tmax; h.prim = 0x7fffffff; h.u = h.v = 0.f;
+    if (sc.nTris > 0) {
+        if (brute ? bruteTris<true>(sc, o, d, h, -1) : traverse<true, COUNT>(sc, o, d, h, -1, sstack, tc)) return true;
+    }
+    for (int s = 0; s < sc.nSpheres; ++s) {
+        const float4 cr = __ldg(sc.spheres + 2 * s);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * s + 1));
+        float t;
+        if (meta.y == 0 && sphereT(cr, o, d, t) && t < tmax) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent-kernel helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31u; }
+
+// warp grabs 32 consecutive work items
+__device__ __forceinline__ uint32_t fetch32(uint32_t* cursor)
+{
+    uint32_t base = 0;
+    if (laneId() == 0) base = atomicAdd(cursor, 32u);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// warp-aggregated append: returns the slot for this lane if `want`, one atomic per warp
+__device__ __forceinline__ uint32_t warpAppend(uint32_t* counter, bool want)
+{
+    const uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return 0;
+    uint32_t base = 0;
+    const uint32_t leader = __ffs(mask) - 1;
+    if (laneId() == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << laneId()) - 1u));
+}
+
+__device__ __forceinline__ void statAdd(unsigned long long* stats, int which, uint32_t v)
+{
+    // warp-reduce then one atomic
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (laneId() == 0 && v) atomicAdd(stats + which, (unsigned long long)v);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// raygen: renderer.cpp:42-52 + PinholeCamera::sampleRay (camera.h:49-60)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cameraRay(const DCamera& c, float u, float v, V3& o, V3& d)
+{
+    const V3 dir = mk((2 * u - 1) * c.scale, (1 - 2 * v) * c.scale / c.aspect, -1.0f);
+    const float* m = c.c2w;
+    const V3 w = mk(dir.x * m[0] + dir.y * m[4] + dir.z * m[8], dir.x * m[1] + dir.y * m[5] + dir.z * m[9],
+                    dir.x * m[2] + dir.y * m[6] + dir.z * m[10]);
+    d = normalize(w);
+    o = mk(m[12], m[13], m[14]);
+}
+
+// path id = s * nPixels + pixel, so consecutive threads own consecutive pixels of the same sample.
+// jitter (optional, device): [(pixel * spp + s) * 2] floats supplied by the parity hook.
+__global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DQueues q, DWave w, const float* __restrict__ jitter)
+{
+    const uint32_t n = w.nPaths;
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n; pid += gridDim.x * blockDim.x) {
+        const uint32_t pix = pid % w.nPixels, s = pid / w.nPixels;
+        const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+        float r0, r1;
+        uint32_t ctr = 0;
+        if (jitter) {
+            r0 = jitter[(size_t(pix) * w.samplesThisWave + s) * 2];
+            r1 = jitter[(size_t(pix) * w.samplesThisWave + s) * 2 + 1];
+        }
+        else {
+            Rng rng;
+            rng.open(w, pid, 0);
+            r0 = rng.next();
+            r1 = rng.next();
+            ctr = rng.close();
+        }
+        const float u = (float(j) + r0) / float(uint32_t(w.width));
+        const float v = (float(i) + r1) / float(uint32_t(w.height));
+        V3 o, d;
+        cameraRay(cam, u, v, o, d);
+        q.q0[0][pid] = make_float4(o.x, o.y, o.z, 1.0f);
+        q.q1[0][pid] = make_float4(d.x, d.y, d.z, 1.0f);
+        q.q2[0][pid] = make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr)));
+        q.radiance[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) q.ctrl[kCtrlRays] = n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// extend: closest hit for every ray of queue `src` at bounce b
+// ---------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    TraceCounters tc;
+    while (true) {
+        const uint32_t base = fetch32(ctrl + kCtrlFetchExtend);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            const float4 r0 = q.q0[src][i], r1 = q.q1[src][i];
+            Hit h;
+            closestHit<COUNT>(sc, xyz(r0), xyz(r1), brute != 0, h, s_stack + threadIdx.x, tc);
+            q.hits[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
+    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// connect: any hit for every shadow ray of bounce b; unoccluded contributions go to the path's radiance
+// ---------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_connect(DScene sc, DQueues q, int bounce, int brute, unsigned long long* stats)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlShadow];
+    TraceCounters tc;
+    while (true) {
+        const uint32_t base = fetch32(ctrl + kCtrlFetchConnect);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        if (i < n) {
+            const float4 s0 = q.s0[i], s1 = q.s1[i];
+            const bool occ = anyHit<COUNT>(sc, xyz(s0), xyz(s1), s0.w, brute != 0, s_stack + threadIdx.x, tc);
+            if (!occ) {
+                const float4 c = q.s2[i];
+                float* r = reinterpret_cast<float*>(q.radiance + __float_as_int(s1.w));
+                atomicAdd(r + 0, c.x); atomicAdd(r + 1, c.y); atomicAdd(r + 2, c.z);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatShadow, (unsigned long long)n);
+    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shading
+// ---------------------------------------------------------------------------------------------------------
+struct Surf {
+    V3 pos, ng, ns, dpdu, dpdv, albedo;
+    uint32_t meta;
+    float t1;
+};
+
+// Reconstructs what Mesh::intersect (primitive.cpp:100-110) / Sphere::intersect (primitive.h:112-122) store in
+// IntersectInfo. ng was normalised on the host with the reference's expression; ns is interpolated and NOT
+// re-normalised. A sphere hit leaves dpdu/dpdv at zero (the reference leaves them stale).
+__device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit& h, Surf& s)
+{
+    const float4 p3 = __ldg(sc.prims + 4 * h.prim + 3);
+    s.meta = __float_as_uint(p3.w);
+    s.albedo = xyz(p3);
+    s.pos = o + h.t * d;
+    s.t1 = h.u;
+    const uint32_t kind = s.meta & kMetaKindMask;
+    if (kind == XRTG_OBJ_MESH) {
+        const float4 p0 = __ldg(sc.prims + 4 * h.prim), p1 = __ldg(sc.prims + 4 * h.prim + 1), p2 = __ldg(sc.prims + 4 * h.prim + 2);
+        s.ng = mk(p0.w, p1.w, p2.w);
+        s.ns = xyz(p0) * (1.0f - h.u - h.v) + xyz(p1) * h.u + xyz(p2) * h.v;
+        orthonormalBasis(s.ns, s.dpdu, s.dpdv);
+    }
+    else if (kind == XRTG_OBJ_SPHERE) {
+        const float4 p0 = __ldg(sc.prims + 4 * h.prim);
+        s.ng = normalize(s.pos - xyz(p0));
+        s.ns = s.ng;
+        s.dpdu = mk(0.f); s.dpdv = mk(0.f);
+    }
+    else {
+        s.ng = mk(0.f); s.ns = mk(0.f); s.dpdu = mk(0.f); s.dpdv = mk(0.f);
+    }
+}
+__device__ __forceinline__ bool hasMaterial(const Surf& s) { return (s.meta & kMetaHasMaterial) != 0; }
+__device__ __forceinline__ int lightOf(const Surf& s) { return int((s.meta >> kMetaLightShift) & 0xfffu) - 1; }
+__device__ __forceinline__ int mediumOf(const Surf& s) { return int((s.meta >> kMetaMediumShift) & 0xfffu) - 1; }
+
+// AreaLight::Le (light.h:62-69)
+__device__ __forceinline__ V3 emitted(const DScene& sc, const Surf& s, V3 rayDir)
+{
+    const int li = lightOf(s);
+    if (li < 0) return mk(0.f);
+    return (dot(rayDir, s.ns) < 0) ? xyz(sc.lights[li].Le) : mk(0.f);
+}
+
+// AreaLight::sample: quad light.cpp:59-68, triangle light.cpp:21-30 + :43-47, sphere light.h:158-197.
+// Draw order as compiled by g++ (second-written getNext1D() draws first), pinned by the oracle KATs.
+__device__ __forceinline__ V3 sampleLight(const DLight& L, V3 position, V3& wi, float& pdf, float& tmax, Rng& rng)
+{
+    const int kind = __float_as_int(L.v0_kind.w);
+    const V3 v0 = xyz(L.v0_kind);
+    if (kind == XRTG_LIGHT_QUAD) {
+        const float rb = rng.next();
+        const float ra = rng.next();
+        const V3 d = (v0 + xyz(L.e1_r) * ra + xyz(L.e2) * rb) - position;
+        tmax = length(d);
+        const float dn = dot(d, xyz(L.Ng));
+        if (dn >= 0) return mk(0.f);
+        wi = d / tmax;
+        pdf = (tmax * tmax * tmax) / fabsf(dn);
+        return xyz(L.Le);
+    }
+    if (kind == XRTG_LIGHT_TRIANGLE) {
+        const float v = rng.next();
+        const float u = rng.next();
+        const float su = sqrtf(u);
+        const V3 A = v0, B = xyz(L.v1), C = xyz(L.v2);
+        const V3 p = C + (1.f - su) * (A - C) + (v * su) * (B - C);
+        const V3 d = p - position;
+        tmax = length(d);
+        const float dn = dot(d, xyz(L.Ng));
+        if (dn >= 0) return mk(0.f);
+        wi = d / tmax;
+        pdf = (2.f * tmax * tmax * tmax) / fabsf(dn);
+        return xyz(L.Le);
+    }
+    const float radius = L.e1_r.w;
+    V3 dz = v0 - position;
+    const float dz_len_2 = dot(dz, dz);
+    const float dz_len = sqrtf(dz_len_2);
+    dz = dz / mk(-dz_len);
+    V3 dx, dy;
+    orthonormalBasis(dz, dx, dy);
+    const float sin_theta_max_2 = radius * radius / dz_len_2;
+    const float sin_theta_max = sqrtf(sin_theta_max_2);
+    const float cos_theta_max = sqrtf(smax(0.f, 1.f - sin_theta_max_2));
+    const float cos_theta = 1 + (cos_theta_max - 1) * rng.next();
+    const float sin_theta_2 = 1.f - cos_theta * cos_theta;
+    const float cos_alpha = sin_theta_2 / sin_theta_max + cos_theta * sqrtf(smax(0.0f, 1 - sin_theta_2 / sin_theta_max_2));
+    const float sin_alpha = sqrtf(smax(0.0f, 1 - cos_alpha * cos_alpha));
+    const float phi = 2 * kPI * rng.next();
+    const V3 n = cosf(phi) * sin_alpha * dx + sinf(phi) * sin_alpha * dy + cos_alpha * dz;
+    const V3 p = v0 + n * radius;
+    const V3 d = p - position;
+    tmax = length(d);
+    const float d_dot_n = dot(d, n);
+    if (d_dot_n >= 0) return mk(0.f);
+    pdf = 1.f / (2.f * kPI * (1.f - cos_theta_max));
+    wi = d / tmax;
+    return xyz(L.Le);
+}
+
+// Lambert::sampleDir (material.h:55-73): UNIFORM hemisphere about ng using ns's tangent frame, pdf = 1/2PI
+__device__ __forceinline__ V3 lambertSampleDir(const Surf& s, Rng& rng, float& pdf)
+{
+    const float r1 = rng.next();
+    const float r2 = rng.next();
+    pdf = 1 / (2 * kPI);
+    const float sinTheta = sqrtf(1 - r1 * r1);
+    const float phi = 2 * kPI * r2;
+    const float x = sinTheta * cosf(phi);
+    const float z = sinTheta * sinf(phi);
+    return localToWorld(mk(x, r1, z), s.dpdu, s.ng, s.dpdv);
+}
+__device__ __forceinline__ V3 evalBxDF(const Surf& s) { return hasMaterial(s) ? s.albedo / kPI : mk(0.f); }
+__device__ __forceinline__ V3 sampleBxDF(const Surf& s, Rng& rng, V3& wi, float& pdf)
+{
+    if (!hasMaterial(s)) return mk(0.f);
+    wi = lambertSampleDir(s, rng, pdf);
+    return evalBxDF(s);
+}
+
+struct ShadeOut {
+    DQueues q;
+    uint32_t* ctrlNext; // ctrl block of bounce+1 (ray count)
+    uint32_t* ctrlCur;  // ctrl block of this bounce (shadow count)
+    int dst;
+};
+
+// Emit a shadow ray (warp-aggregated append). Must be called by all 32 lanes.
+__device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, V3 d, float tmax, uint32_t pid, V3 c)
+{
+    const uint32_t slot = warpAppend(so.ctrlCur + kCtrlShadow, want);
+    if (want) {
+        so.q.s0[slot] = make_float4(o.x, o.y, o.z, tmax);
+        so.q.s1[slot] = make_float4(d.x, d.y, d.z, __int_as_float(int(pid)));
+        so.q.s2[slot] = make_float4(c.x, c.y, c.z, 0.f);
+    }
+}
+__device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 d, V3 T, uint32_t pid, int depth, uint32_t ctr)
+{
+    const uint32_t slot = warpAppend(so.ctrlNext + kCtrlRays, want);
+    if (want) {
+        so.q.q0[so.dst][slot] = make_float4(o.x, o.y, o.z, T.x);
+        so.q.q1[so.dst][slot] = make_float4(d.x, d.y, d.z, T.y);
+        so.q.q2[so.dst][slot] = make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr)));
+    }
+}
+__device__ __forceinline__ void addRadiance(const DQueues& q, uint32_t pid, V3 c)
+{
+    float4 r = q.radiance[pid];
+    r.x += c.x; r.y += c.y; r.z += c.z;
+    q.radiance[pid] = r;
+}
+
+// Surface integrators: Normal (integrator.h:29-36), furnace (:59-66), Direct (:82-119), Indirect (:129-186),
+// GI (:205-287), Whitted's Lambert/delta-light branch (:302-394). One thread per ray-queue entry of bounce b.
+__global__ void __launch_bounds__(kBlock) k_shade_surface(DScene sc, DQueues q, DWave w, int src, int bounce)
+{
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
+    const int kind = w.integrator;
+    while (true) {
+        const uint32_t base = fetch32(ctrl + kCtrlFetchShade);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        const bool live = i < n;
+        // per-lane outputs, appended collectively at the end of the iteration
+        bool wantRay = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        uint32_t pid = 0, ctr = 0;
+        int depth = 0;
+        // shadow rays are appended inside the light loop (uniform trip count across the warp)
+        float4 r0, r1, r2, hv;
+        if (live) { r0 = q.q0[src][i]; r1 = q.q1[src][i]; r2 = q.q2[src][i]; hv = q.hits[i]; }
+        else { r0 = r1 = r2 = hv = make_float4(0, 0, 0, 0); hv.w = __int_as_float(-1); }
+        const V3 o = xyz(r0), d = xyz(r1);
+        V3 T = mk(r0.w, r1.w, r2.x);
+        pid = uint32_t(__float_as_int(r2.y));
+        depth = __float_as_int(r2.z);
+        Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+        Rng rng;
+        bool shadeLights = false, shadeDelta = false;
+        Surf s = {};
+        if (live) {
+            rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+            if (h.prim < 0) {
+                if (kind == XRTG_INT_DIRECT) addRadiance(q, pid, mk(float(0.18)));
+                else if (kind == XRTG_INT_WHITTED) addRadiance(q, pid, mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137)));
+            }
+            else {
+                makeSurf(sc, o, d, h, s);
+                if (kind == XRTG_INT_NORMAL) {
+                    addRadiance(q, pid, 0.5f * (s.ns + 1.0f));
+                }
+                else if (kind == XRTG_INT_FURNACE) {
+                    float pdf = 1.0f;
+                    V3 nextDir = mk(0.f);
+                    const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+                    const float cs = smax(0.0f, dot(nextDir, s.ng));
+                    addRadiance(q, pid, fr * cs * mk(1.0f) / pdf);
+                }
+                else if (kind == XRTG_INT_DIRECT) {
+                    if (lightOf(s) >= 0) addRadiance(q, pid, emitted(sc, s, d));
+                    else shadeLights = true;
+                }
+                else if (kind == XRTG_INT_WHITTED) {
+                    shadeDelta = hasMaterial(s);
+                }
+                else { // Indirect / GI
+                    bool alive = true;
+                    if (depth > 0) { // russian roulette (integrator.h:223-231)
+                        const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
+                        if (rng.next() >= p) alive = false;
+                        else T = T / mk(p);
+                    }
+                    if (alive && lightOf(s) >= 0) {
+                        if (kind == XRTG_INT_INDIRECT || depth == 0) addRadiance(q, pid, T * emitted(sc, s, d));
+                        alive = false;
+                    }
+                    if (alive) {
+                        shadeLights = (kind == XRTG_INT_GI);
+                        wantRay = true; // BSDF sampling happens after the light loop (draw order!)
+                    }
+                }
+            }
+        }
+        // ---- NEE over EVERY area light (integrator.h:95-108, :250-267) ----
+        if (__any_sync(0xffffffffu, shadeLights)) {
+            for (int li = 0; li < sc.nLights; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeLights) {
+                    float pdf = 0.0f;
+                    const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                    if (pdf != 0) {
+                        const float cs = smax(0.0f, dot(s.ng, wi));
+                        const V3 fr = evalBxDF(s);
+                        c = T * (fr * Lr * cs / pdf);
+                        want = true;
+                    }
+                }
+                const float bias = 0.01f;
+                pushShadow(so, want, s.pos + s.ng * bias, wi, tmax - bias, pid, c);
+            }
+        }
+        // ---- Whitted diffuse term over delta lights (integrator.h:328-343; PointLight/DistantLight light.cpp:120-142)
+        if (__any_sync(0xffffffffu, shadeDelta)) {
+            for (int li = 0; li < sc.nDelta; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeDelta) {
+                    const DDelta L = sc.dlights[li];
+                    float pdf;
+                    if (__float_as_int(L.p_kind.w) == XRTG_DLIGHT_POINT) {
+                        const V3 ld = xyz(L.p_kind) - s.pos;
+                        const float dist = length(ld);
+                        wi = ld / dist; pdf = dist * dist; tmax = dist;
+                    }
+                    else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
+                    c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
+                    want = true;
+                }
+                pushShadow(so, want, s.pos + s.ng * float(0.1), wi, tmax, pid, c);
+            }
+        }
+        // ---- BSDF bounce (integrator.h:271-283) ----
+        if (wantRay) {
+            float pdf = 1.0f;
+            V3 nextDir = mk(0.f);
+            const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+            const float cs = smax(.0f, dot(nextDir, s.ng));
+            nT = T * (fr * cs / pdf);
+            no = s.pos + s.ng * 0.01f;
+            nd = nextDir;
+            wantRay = (depth + 1 < w.maxDepth);
+        }
+        if (live) ctr = rng.close();
+        pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// participating media (medium.h, medium.cpp) — used by the volume shade kernel
+// ---------------------------------------------------------------------------------------------------------
+
+// DenseGrid lookup: fp32 restatement of OpenVDBGrid::getDensity (grid.h:71-77) — (p-origin)/voxel, floor,
+// eight point fetches with `background` outside the block, lerp z then y then x as a + (b-a)*w.
+__device__ __forceinline__ float gridVoxel(const DGrid& g, int x, int y, int z)
+{
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz) return g.background;
+    return __ldg(g.data + (size_t(z) * g.ny + y) * g.nx + x);
+}
+__device__ __forceinline__ float gridDensity(const DGrid& g, V3 p)
+{
+    const float fx = (p.x - g.origin[0]) / g.voxel, fy = (p.y - g.origin[1]) / g.voxel, fz = (p.z - g.origin[2]) / g.voxel;
+    const float bx = floorf(fx), by = floorf(fy), bz = floorf(fz);
+    const float wx = fx - bx, wy = fy - by, wz = fz - bz;
+    const int x = int(bx), y = int(by), z = int(bz);
+    const float v000 = gridVoxel(g, x, y, z), v001 = gridVoxel(g, x, y, z + 1);
+    const float v010 = gridVoxel(g, x, y + 1, z), v011 = gridVoxel(g, x, y + 1, z + 1);
+    const float v100 = gridVoxel(g, x + 1, y, z), v101 = gridVoxel(g, x + 1, y, z + 1);
+    const float v110 = gridVoxel(g, x + 1, y + 1, z), v111 = gridVoxel(g, x + 1, y + 1, z + 1);
+    const float c00 = v000 + (v001 - v000) * wz;
+    const float c01 = v010 + (v011 - v010) * wz;
+    const float c10 = v100 + (v101 - v100) * wz;
+    const float c11 = v110 + (v111 - v110) * wz;
+    const float c0 = c00 + (c01 - c00) * wy;
+    const float c1 = c10 + (c11 - c10) * wy;
+    return c0 + (c1 - c0) * wx;
+}
+
+// HenyeyGreenstein::evaluate / sampleDirection (medium.h:29-67); u[1] is drawn first (g++ argument order)
+__device__ __forceinline__ float hgEval(float g, V3 wo, V3 wi)
+{
+    const float cosTheta = dot(wo, wi);
+    const float denom = 1 + g * g - 2 * g * cosTheta;
+    const float pi4inv = 1.0f / (4.0f * kPI);
+    return pi4inv * (1 - g * g) / (denom * sqrtf(denom));
+}
+__device__ __forceinline__ void hgSample(float g, V3 wo, Rng& rng, V3& wi)
+{
+    const float u1 = rng.next();
+    const float u0 = rng.next();
+    float cosTheta;
+    if (fabsf(g) < 1e-3) cosTheta = 2 * u0 - 1.0f;
+    else {
+        const float sqrTerm = (1 - g * g) / (1 - g + 2 * g * u0);
+        cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
+    }
+    const float sinTheta = sqrtf(smax(1.0f - cosTheta * cosTheta, 0.0f));
+    const float phi = 2 * kPI * u1;
+    const V3 local = mk(cosf(phi) * sinTheta, cosTheta, sinf(phi) * sinTheta);
+    V3 t, b;
+    orthonormalBasis(wo, t, b);
+    wi = localToWorld(local, t, wo, b);
+}
+
+// Medium::sampleWavelength (medium.h:102-115) + DiscreteEmpiricalDistribution1D (sampler.h:53-97); the
+// std::lower_bound probe order over the 4-entry cdf is unrolled; channel clamped to 2 where the reference reads
+// past the cdf.
+__device__ __forceinline__ uint32_t sampleWavelength(V3 throughput, V3 albedo, Rng& rng, V3& pmf)
+{
+    const V3 ta = throughput * albedo;
+    float sum = 0;
+    sum += ta.x; sum += ta.y; sum += ta.z;
+    const float c0 = 0;
+    const float c1 = c0 + ta.x / sum;
+    const float c2 = c1 + ta.y / sum;
+    const float c3 = c2 + ta.z / sum;
+    pmf = mk(c1 - c0, c2 - c1, c3 - c2);
+    const float u = rng.next();
+    int x;
+    if (c2 < u) x = (c3 < u) ? 4 : 3;
+    else if (c1 < u) x = 2;
+    else x = (c0 < u) ? 1 : 0;
+    if (x == 0) x++;
+    if (x > 3) x = 3;
+    return uint32_t(x - 1);
+}
+__device__ __forceinline__ V3 analyticTr(float t, V3 sigma) { return vexp(-sigma * t); } // medium.h:95-98
+__device__ __forceinline__ V3 v3(const float* p) { return mk(p[0], p[1], p[2]); }
+
+// HomogeneousMedium{MIS,Achromatic,NoMIS}::sampleMedium (medium.h:154-191, 202-228, 239-276)
+__device__ __forceinline__ bool sampleHomogeneous(const DMedium& m, V3 o, V3 d, V3 rayT, float t0, float t1, Rng& rng, V3& pos, V3& dir, V3& thr)
+{
+    const V3 sa = v3(m.sigma_a), ss = v3(m.sigma_s), st = v3(m.sigma_t);
+    (void)sa;
+    const float distToSurface = t1 - t0;
+    if (m.kind == XRTG_MEDIUM_HOMOGENEOUS_MIS) {
+        V3 pmf = mk(1.0f);
+        const uint32_t ch = sampleWavelength(rayT, ss / st, rng, pmf);
+        const float t = -logf(smax(1.0f - rng.next(), 0.0f)) / comp(st, ch);
+        if (t > distToSurface - kRayEps) {
+            pos = o + (t1 + kRayEps) * d; dir = d;
+            const V3 tr = analyticTr(distToSurface, st);
+            const V3 pdf = pmf * tr;
+            thr = tr / (pdf.x + pdf.y + pdf.z);
+            return false;
+        }
+        hgSample(m.g, d, rng, dir);
+        pos = o + (t0 + t) * d;
+        const V3 tr = analyticTr(t, st);
+        const V3 pdf = pmf * (st * tr);
+        thr = (tr * ss) / (pdf.x + pdf.y + pdf.z);
+        return true;
+    }
+    if (m.kind == XRTG_MEDIUM_HOMOGENEOUS_ACHROMATIC) {
+        const float t = -logf(smax(1.0f - rng.next(), 0.0f)) / st.x;
+        if (t > distToSurface - kRayEps) { pos = o + (t1 + kRayEps) * d; dir = d; thr = mk(1.0f); return false; }
+        hgSample(m.g, d, rng, dir);
+        pos = o + (t0 + t) * d;
+        thr = ss / st;
+        return true;
+    }
+    int ch = int(3 * rng.next());
+    if (ch == 3) ch--;
+    const float pmfw = 1.0f / 3.0f;
+    const float sc_ = comp(st, ch);
+    const float t = -logf(smax(1.0f - rng.next(), 0.0f)) / sc_;
+    const float pdf_distance = sc_ * expf(-sc_ * t);
+    if (t > distToSurface - kRayEps) {
+        pos = o + (t1 + kRayEps) * d; dir = d;
+        const V3 tr = analyticTr(distToSurface, st);
+        const float p_surface = expf(-sc_ * distToSurface);
+        thr = 1.0f / 3.0f * tr / (pmfw * p_surface);
+        return false;
+    }
+    hgSample(m.g, d, rng, dir);
+    pos = o + (t0 + t) * d;
+    thr = 1.0f / 3.0f * analyticTr(t, st) * ss / (pmfw * pdf_distance);
+    return true;
+}
+
+// HeterogeneousMedium::sampleMedium — spectral delta tracking (medium.cpp:45-133)
+__device__ __forceinline__ bool sampleHeterogeneous(const DScene& sc, const DMedium& m, V3 o, V3 d, V3 rayT, float tEntry, float t1, Rng& rng,
+                                                    V3& pos, V3& dir, V3& thr, uint32_t& steps)
+{
+    const DGrid g = sc.grids[m.grid];
+    const V3 absC = v3(m.sigma_a), scatC = v3(m.sigma_s);
+    V3 tt = mk(1.f);
+    float t = tEntry;
+    float density = m.densityMul * gridDensity(g, o + t * d);
+    V3 sigma_a = absC * density;
+    const V3 maj = mk(m.majorant);
+    while (true) {
+        ++steps;
+        V3 pmf;
+        const uint32_t ch = sampleWavelength(rayT * tt, (maj - sigma_a) * m.invMajorant, rng, pmf);
+        const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
+        t += sd;
+        if (t > t1 - kRayEps) {
+            pos = o + (t1 + kRayEps) * d; dir = d;
+            const float rest = sd - (t - (t1 - kRayEps));
+            const V3 tr = analyticTr(rest, maj);
+            const V3 pdf = pmf * tr;
+            tt = tt * (tr / (pdf.x + pdf.y + pdf.z));
+            thr = anyNan(tt) ? mk(0.f) : tt;
+            return false;
+        }
+        density = m.densityMul * gridDensity(g, o + t * d);
+        const V3 sigma_s = scatC * density;
+        sigma_a = absC * density;
+        const V3 sigma_n = maj - sigma_a - sigma_s;
+        const V3 P_s = sigma_s / (sigma_s + sigma_n);
+        const V3 P_n = sigma_n / (sigma_s + sigma_n);
+        if (rng.next() < comp(P_s, ch)) {
+            pos = o + t * d;
+            hgSample(m.g, d, rng, dir);
+            const V3 tr = analyticTr(sd, maj);
+            const V3 pdf_distance = m.majorant * tr;
+            const V3 pdf = pmf * pdf_distance * P_s;
+            tt = tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
+            thr = anyNan(tt) ? mk(0.f) : tt;
+            return true;
+        }
+        const V3 tr = analyticTr(sd, maj);
+        const V3 pdf_distance = m.majorant * tr;
+        const V3 pdf = pmf * pdf_distance * P_n;
+        tt = tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+    }
+}
+
+// Medium::transmittance: analytic (medium.h:134-139) or ratio tracking (medium.h:360-386)
+__device__ __forceinline__ V3 transmittance(const DScene& sc, const DMedium& m, V3 p1, V3 p2, Rng& rng, uint32_t& steps)
+{
+    if (m.kind != XRTG_MEDIUM_HETEROGENEOUS) return analyticTr(length(p1 - p2), v3(m.sigma_t));
+    const DGrid g = sc.grids[m.grid];
+    const float distToEnd = length(p1 - p2);
+    float t = 0;
+    const V3 dir = normalize(p2 - p1);
+    V3 tr = mk(1.f);
+    while (true) {
+        const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
+        t += sd;
+        if (t > distToEnd) break;
+        ++steps;
+        const float density = m.densityMul * gridDensity(g, p1 + t * dir);
+        const V3 sigma_n = mk(m.majorant) - v3(m.sigma_a) * density - v3(m.sigma_s) * density;
+        tr = tr * (sigma_n * m.invMajorant);
+    }
+    return tr;
+}
+
+// VolumePathTracing (integrator.h:409-473) and VolumePathTracingNEE (integrator.h:489-631): one loop iteration
+// of the reference per wavefront bounce; the tracking loop runs inside the thread.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, DWave w, int src, int bounce, int brute, unsigned long long* stats)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
+    const bool nee = (w.integrator == XRTG_INT_VOLUME_NEE);
+    uint32_t steps = 0, extraClosest = 0;
+    TraceCounters tc;
+    while (true) {
+        const uint32_t base = fetch32(ctrl + kCtrlFetchShade);
+        if (base >= n) break;
+        const uint32_t i = base + laneId();
+        bool wantRay = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        uint32_t pid = 0, ctr = 0;
+        int depth = 0;
+        if (i < n) {
+            const float4 r0 = q.q0[src][i], r1 = q.q1[src][i], r2 = q.q2[src][i], hv = q.hits[i];
+            const V3 o = xyz(r0), d = xyz(r1);
+            V3 T = mk(r0.w, r1.w, r2.x);
+            pid = uint32_t(__float_as_int(r2.y));
+            depth = __float_as_int(r2.z);
+            Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+            Rng rng;
+            rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+            if (h.prim >= 0) { // a miss adds throughput*background*(depth!=0) = 0
+                Surf s;
+                makeSurf(sc, o, d, h, s);
+                bool alive = true;
+                if (depth > 0) {
+                    const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
+                    if (rng.next() >= p) alive = false;
+                    else T = T / mk(p);
+                }
+                if (alive && lightOf(s) >= 0) {
+                    if (!nee || depth == 0) addRadiance(q, pid, T * emitted(sc, s, d));
+                    alive = false;
+                }
+                if (alive) {
+                    const int mi = mediumOf(s);
+                    if (mi >= 0) {
+                        const DMedium m = sc.media[mi];
+                        V3 pos, dir, tm;
+                        bool scattered;
+                        if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) scattered = sampleHeterogeneous(sc, m, o, d, T, h.t, s.t1, rng, pos, dir, tm, steps);
+                        else scattered = sampleHomogeneous(m, o, d, T, h.t, s.t1, rng, pos, dir, tm);
+                        if (nee && scattered) {
+                            // sampleDirectionToLight (integrator.h:583-602), Scene::sampleAreaLight (scene.cpp:182-188)
+                            unsigned int li = (unsigned int)(float(sc.nLights) * rng.next());
+                            if (li == (unsigned int)sc.nLights) li--;
+                            const float choose = 1.0f / float(sc.nLights);
+                            V3 dl = mk(0.f);
+                            float dist, lp = 0.0f;
+                            const V3 Le = sampleLight(sc.lights[li], pos, dl, lp, dist, rng);
+                            const float pdf_dir = choose * lp;
+                            if (pdf_dir > 0.0f) {
+                                // isVisible (integrator.h:604-631): ONE closest-hit query, dist_to_light ignored
+                                V3 trn = mk(1.0f);
+                                bool visible = true;
+                                Hit sh;
+                                closestHit<COUNT>(sc, pos, dl, brute != 0, sh, s_stack + threadIdx.x, tc);
+                                ++extraClosest;
+                                if (sh.prim >= 0) {
+                                    Surf ss;
+                                    makeSurf(sc, pos, dl, sh, ss);
+                                    if (hasMaterial(ss)) visible = false;
+                                    else if (mediumOf(ss) >= 0)
+                                        trn = trn * transmittance(sc, sc.media[mediumOf(ss)], pos + sh.t * dl, pos + ss.t1 * dl, rng, steps);
+                                }
+                                if (visible) {
+                                    const V3 f = mk(hgEval(m.g, d, dl));
+                                    const V3 Ls = trn * f * Le / pdf_dir;
+                                    addRadiance(q, pid, T * tm * Ls);
+                                }
+                            }
+                        }
+                        nT = T * tm;
+                        no = pos; nd = dir;
+                        if (scattered) depth++;
+                        wantRay = depth < w.maxDepth;
+                    }
+                    else {
+                        // A plain surface: the reference never advances here (infinite loop).
+                        // The sample is poisoned so that it is DROPPED and counted, like the oracle port does.
+                        addRadiance(q, pid, mk(__int_as_float(0x7fc00000)));
+                    }
+                }
+            }
+            ctr = rng.close();
+        }
+        pushRay(so, wantRay, no, nd, nT, pid, depth, ctr);
+    }
+    if (extraClosest) atomicAdd(stats + kStatClosest, (unsigned long long)extraClosest);
+    statAdd(stats, kStatSteps, steps);
+    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// accumulate: validate each sample like renderer.cpp:57-73 (NaN / inf / any negative channel -> dropped, the
+// divisor is unchanged) and add the wave's samples to the pixel sum IN SAMPLE ORDER (bit-exact vs
+// Image::addPixel order). One thread per pixel, no atomics.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_accumulate(DQueues q, DWave w, float* __restrict__ accum, unsigned long long* stats)
+{
+    uint32_t dropped = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < w.nPixels; p += gridDim.x * blockDim.x) {
+        float ax = accum[3 * size_t(p)], ay = accum[3 * size_t(p) + 1], az = accum[3 * size_t(p) + 2];
+        for (uint32_t s = 0; s < w.samplesThisWave; ++s) {
+            const float4 r = q.radiance[size_t(s) * w.nPixels + p];
+            if (isnan(r.x) || isnan(r.y) || isnan(r.z)) { ++dropped; continue; }
+            else if (isinf(r.x) || isinf(r.y) || isinf(r.z)) { ++dropped; continue; }
+            else if (r.x < 0 || r.y < 0 || r.z < 0) { ++dropped; continue; }
+            ax += r.x; ay += r.y; az += r.z;
+        }
+        accum[3 * size_t(p)] = ax; accum[3 * size_t(p) + 1] = ay; accum[3 * size_t(p) + 2] = az;
+    }
+    if (dropped) atomicAdd(stats + kStatDropped, (unsigned long long)dropped);
+}
+
+// image /= Vec3f(n_samples) (renderer.cpp:98) — IEEE division like the reference; divisor 0 = leave the sum
+__global__ void __launch_bounds__(kBlock) k_finalize(const float* __restrict__ accum, float* __restrict__ out, size_t n, float divisor)
+{
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        out[i] = divisor > 0.f ? accum[i] / divisor : accum[i];
+}
+
+// parity hook: arbitrary rays (org/dir/tmax arrays) -> closest hit or occlusion flag
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace_rays(DScene sc, const float* __restrict__ org, const float* __restrict__ dir,
+                                                       const float* __restrict__ tmax, long long n, int anyhit, int brute, float4* out)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    TraceCounters tc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const V3 o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        if (anyhit) {
+            const bool occ = anyHit<COUNT>(sc, o, d, tmax ? tmax[i] : FLT_MAX, brute != 0, s_stack + threadIdx.x, tc);
+            out[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(occ ? 1 : 0));
+        }
+        else {
+            Hit h;
+            closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+            out[i] = make_float4(h.prim >= 0 ? h.t : FLT_MAX, h.u, h.v, __int_as_float(h.prim));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launchers (called from api.cpp through the table in kernels.h)
+// ---------------------------------------------------------------------------------------------------------
+struct LaunchCfg {
+    int sms = 0;
+    int persistentBlocks(const void* fn)
+    {
+        int perSm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, kBlock, 0);
+        if (perSm < 1) perSm = 1;
+        return sms * perSm;
+    }
+};
+
+inline int gridFor(const void* fn)
+{
+    static thread_local int cachedDev = -1;
+    static thread_local int sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cachedDev) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cachedDev = dev;
+    }
+    LaunchCfg c;
+    c.sms = sms;
+    return c.persistentBlocks(fn);
+}
+
+inline void launchSeedMt(cudaStream_t st, const DWave& w)
+{
+    const int grid = int((w.nPixels + kBlock - 1) / kBlock);
+    k_seed_mt<<<grid, kBlock, 0, st>>>(w.mt, w.mti, w.nPixels);
+}
+inline void launchGenJitter(cudaStream_t st, const DWave& w, int spp, float* jitter)
+{
+    const int grid = int((w.nPixels + kBlock - 1) / kBlock);
+    k_gen_jitter<<<grid, kBlock, 0, st>>>(w, spp, jitter);
+}
+inline void launchRaygen(cudaStream_t st, const DCamera& cam, const DQueues& q, const DWave& w, const float* jitter)
+{
+    static thread_local int grid = 0;
+    if (!grid) grid = gridFor((const void*)k_raygen);
+    k_raygen<<<grid, kBlock, 0, st>>>(cam, q, w, jitter);
+}
+inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, bool brute, bool count, unsigned long long* stats)
+{
+    static thread_local int g0 = 0, g1 = 0;
+    if (!g0) { g0 = gridFor((const void*)k_extend<false>); g1 = gridFor((const void*)k_extend<true>); }
+    if (count) k_extend<true><<<g1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
+    else k_extend<false><<<g0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
+}
+inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, bool brute, bool count, unsigned long long* stats)
+{
+    static thread_local int g0 = 0, g1 = 0;
+    if (!g0) { g0 = gridFor((const void*)k_connect<false>); g1 = gridFor((const void*)k_connect<true>); }
+    if (count) k_connect<true><<<g1, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
+    else k_connect<false><<<g0, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
+}
+inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce)
+{
+    static thread_local int grid = 0;
+    if (!grid) grid = gridFor((const void*)k_shade_surface);
+    k_shade_surface<<<grid, kBlock, 0, st>>>(sc, q, w, src, bounce);
+}
+inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, bool brute, bool count,
+                              unsigned long long* stats)
+{
+    static thread_local int g0 = 0, g1 = 0;
+    if (!g0) { g0 = gridFor((const void*)k_shade_volume<false>); g1 = gridFor((const void*)k_shade_volume<true>); }
+    if (count) k_shade_volume<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
+    else k_shade_volume<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
+}
+inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
+{
+    const int grid = int((w.nPixels + kBlock - 1) / kBlock);
+    k_accumulate<<<grid, kBlock, 0, st>>>(q, w, accum, stats);
+}
+inline void launchFinalize(cudaStream_t st, const float* accum, float* out, size_t n, float divisor)
+{
+    const int grid = int(std::min<size_t>((n + kBlock - 1) / kBlock, 148 * 16));
+    k_finalize<<<grid, kBlock, 0, st>>>(accum, out, n, divisor);
+}
+inline void launchTraceRays(cudaStream_t st, const DScene& sc, const float* org, const float* dir, const float* tmax, long long n, bool anyhit,
+                            bool brute, float4* out)
+{
+    const int grid = int(std::min<long long>((n + kBlock - 1) / kBlock, 148 * 16));
+    k_trace_rays<false><<<grid > 0 ? grid : 1, kBlock, 0, st>>>(sc, org, dir, tmax, n, anyhit, brute, out);
+}
+
+} // namespace XRT_NS
+} // namespace xrt

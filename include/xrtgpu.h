@@ -188,7 +188,10 @@ enum {
     /* Closest/any-hit by brute force in primitive order instead of the BVH (parity debugging). */
     XRTG_FLAG_BRUTE_FORCE = 1u << 2,
     /* Do not divide by spp: leave the per-pixel SUM in the output (multi-GPU partial results). */
-    XRTG_FLAG_SUM_ONLY = 1u << 3
+    XRTG_FLAG_SUM_ONLY = 1u << 3,
+    /* Bracket every kernel launch with CUDA events and report per-stage device time in xrtg_stats
+     * (extend_ms / shade_ms / connect_ms / other_ms). Cheap: no extra work inside the kernels. */
+    XRTG_FLAG_STAGE_TIMES = 1u << 4
 };
 
 typedef struct xrtg_render_params {
@@ -208,13 +211,16 @@ typedef struct xrtg_stats {
     uint64_t closest_rays;   /* Scene::intersect calls the reference would make   */
     uint64_t shadow_rays;    /* Scene::occluded calls the reference would make    */
     uint64_t dropped_samples;/* NaN/inf/negative samples (renderer.cpp:57-73)     */
-    uint64_t nodes_visited;  /* with XRTG_FLAG_COUNTERS                            */
-    uint64_t tris_tested;    /* with XRTG_FLAG_COUNTERS                            */
-    uint64_t tracking_steps; /* with XRTG_FLAG_COUNTERS                            */
+    uint64_t nodes_visited;  /* closest-hit BVH nodes fetched, with XRTG_FLAG_COUNTERS */
+    uint64_t tris_tested;    /* closest-hit triangles tested, with XRTG_FLAG_COUNTERS */
+    uint64_t nodes_visited_shadow; /* any-hit BVH nodes fetched, with XRTG_FLAG_COUNTERS */
+    uint64_t tris_tested_shadow;   /* any-hit triangles tested, with XRTG_FLAG_COUNTERS */
+    uint64_t tracking_steps; /* delta/ratio tracking steps (always counted)        */
     uint64_t kernel_launches;
+    uint64_t extend_launches, shade_launches, connect_launches;
     float render_ms;         /* CUDA-event time of the device work                 */
-    float extend_ms;         /* time in closest-hit traversal kernels              */
-    float connect_ms;        /* time in any-hit traversal kernels                  */
+    float extend_ms;         /* closest-hit traversal kernels (XRTG_FLAG_STAGE_TIMES or _COUNTERS) */
+    float connect_ms;        /* any-hit traversal kernels                          */
     float shade_ms;
     float other_ms;
     float h2d_ms, d2h_ms;

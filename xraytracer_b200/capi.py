@@ -81,7 +81,9 @@ class RenderParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("dropped_samples", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64),
-                ("tracking_steps", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_float),
+                ("nodes_visited_shadow", C.c_uint64), ("tris_tested_shadow", C.c_uint64),
+                ("tracking_steps", C.c_uint64), ("kernel_launches", C.c_uint64), ("extend_launches", C.c_uint64),
+                ("shade_launches", C.c_uint64), ("connect_launches", C.c_uint64), ("render_ms", C.c_float),
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
 
@@ -105,7 +107,7 @@ class SceneInfo(C.Structure):
 # enums of xrtgpu.h
 INT_NORMAL, INT_FURNACE, INT_DIRECT, INT_INDIRECT, INT_GI, INT_WHITTED, INT_VOLUME, INT_VOLUME_NEE = range(8)
 INTEGRATOR_NAMES = ["normal", "furnace", "direct", "indirect", "gi", "whitted", "volume", "volume_nee"]
-FLAG_EXACT, FLAG_COUNTERS, FLAG_BRUTE_FORCE, FLAG_SUM_ONLY = 1, 2, 4, 8
+FLAG_EXACT, FLAG_COUNTERS, FLAG_BRUTE_FORCE, FLAG_SUM_ONLY, FLAG_STAGE_TIMES = 1, 2, 4, 8, 16
 OBJ_MESH, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
 LIGHT_QUAD, LIGHT_TRIANGLE, LIGHT_SPHERE = 0, 1, 2
 MEDIUM_HOMOGENEOUS_MIS, MEDIUM_HOMOGENEOUS_ACHROMATIC, MEDIUM_HOMOGENEOUS_NOMIS, MEDIUM_HETEROGENEOUS = range(4)

@@ -522,8 +522,8 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     w.mt = static_cast<uint32_t*>(s->mt.p);
     w.mti = static_cast<uint32_t*>(s->mti.p);
 
-    StageTimer tm{s, st, count};
-    uint64_t launches = 0;
+    StageTimer tm{s, st, count || (p->flags & XRTG_FLAG_STAGE_TIMES) != 0};
+    uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0;
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
     CU(cudaMemsetAsync(dstats, 0, sizeof(unsigned long long) * kStatCount, st));
@@ -541,16 +541,16 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
             tm.begin(kStageExtend);
-            K.extend(st, s->ds, q, src, b, brute, count, dstats); ++launches;
+            K.extend(st, s->ds, q, src, b, brute, count, dstats); ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
             if (volume) K.shadeVolume(st, s->ds, q, w, src, b, brute, count, dstats);
             else K.shadeSurface(st, s->ds, q, w, src, b);
-            ++launches;
+            ++launches; ++nShade;
             tm.end();
             if (hasShadow) {
                 tm.begin(kStageConnect);
-                K.connect(st, s->ds, q, b, brute, count, dstats); ++launches;
+                K.connect(st, s->ds, q, b, brute, count, dstats); ++launches; ++nConnect;
                 tm.end();
             }
             if (volume) {
@@ -579,10 +579,13 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         stats->dropped_samples = s->statsHost[kStatDropped];
         stats->nodes_visited = s->statsHost[kStatNodes];
         stats->tris_tested = s->statsHost[kStatTris];
+        stats->nodes_visited_shadow = s->statsHost[kStatNodesAny];
+        stats->tris_tested_shadow = s->statsHost[kStatTrisAny];
         stats->tracking_steps = s->statsHost[kStatSteps];
         stats->kernel_launches = launches;
+        stats->extend_launches = nExtend; stats->shade_launches = nShade; stats->connect_launches = nConnect;
         CU(cudaEventElapsedTime(&stats->render_ms, s->ev[0], s->ev[1]));
-        if (count) {
+        if (tm.on) {
             float acc[4] = {0, 0, 0, 0};
             for (size_t k = 0; k + 1 < tm.used; k += 2) {
                 float ms = 0.f;

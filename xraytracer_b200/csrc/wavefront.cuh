@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kBlock) k_connect(DScene sc, DQueues q, int bo
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatShadow, (unsigned long long)n);
-    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+    if (COUNT) { statAdd(stats, kStatNodesAny, tc.nodes); statAdd(stats, kStatTrisAny, tc.tris); }
 }
 
 // ---------------------------------------------------------------------------------------------------------

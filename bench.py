@@ -308,13 +308,19 @@ def main():
         value = samples / (ms * 1e-3) / 1e6
         rays = agg_all[0] + agg_all[1]
         # ---- roofline of the dominant kernel: k_extend (closest-hit BVH traversal), rank 0's launches ----
+        # achieved  = COMPULSORY HBM bytes of the launches / their CUDA-event time: every ray is read once (32 B: origin,
+        #             direction) and its hit written once (16 B), plus the BVH + triangle arrays once per launch. BVH nodes
+        #             and triangles re-fetched per ray are served by L1/L2, not HBM, so they are reported separately as
+        #             `fetch` = rays x (64 B x nodes visited + 48 B x triangles tested) / time  (SURVEY §8(d)'s B_ray).
         peak, peak_src = measured_peak_hbm()
         n_cl = max(cst["closest_rays"], 1)
         nodes_per_ray = cst["nodes_visited"] / n_cl
         tris_per_ray = cst["tris_tested"] / n_cl
-        bytes_per_ray = 64.0 * nodes_per_ray + 48.0 * tris_per_ray + 32.0 + 16.0  # node + triangle fetches, ray read, hit write
         ext_ms, ext_launches, closest_r0 = agg[3], max(agg[6], 1), agg[0]
-        achieved = (closest_r0 * bytes_per_ray) / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        bvh_bytes = 64.0 * info["n_bvh_nodes"] + 48.0 * info["n_triangles"]
+        hbm_bytes = closest_r0 * 48.0 + ext_launches * bvh_bytes
+        fetch_bytes = closest_r0 * (64.0 * nodes_per_ray + 48.0 * tris_per_ray)
+        achieved = hbm_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         traffic = None
         tp = ROOT / "profiles" / f"extend_traffic_{args.workload}.json"
         if tp.exists():
@@ -324,11 +330,15 @@ def main():
                 traffic = None
         roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit SAH-BVH traversal)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                    "algorithmic_bytes_per_launch": hbm_bytes / ext_launches,
+                    "bytes_per_ray_hbm": 48.0, "bvh_bytes": bvh_bytes,
+                    "fetch": {"achieved": fetch_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0, "unit": "GB/s",
+                              "level": "L1/L2 (BVH node + triangle fetches, 64 B and 48 B records)",
+                              "bytes_per_ray": 64.0 * nodes_per_ray + 48.0 * tris_per_ray,
+                              "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray},
                     "launches": int(ext_launches), "avg_launch_ms": ext_ms / ext_launches,
-                    "share_of_step": {"extend": agg[3] / (ms * 1.0), "shade": agg[4] / ms, "connect": agg[5] / ms},
-                    "note": "algorithmic bytes = closest rays x (64 B x BVH nodes fetched + 48 B x triangles tested + 32 B ray read "
-                            "+ 16 B hit write), counters from an instrumented run of the same kernels on the same scene"}
+                    "share_of_step": {"extend": agg[3] / ms, "shade": agg[4] / ms, "connect": agg[5] / ms},
+                    "note": "node/triangle counters from an instrumented run (XRTG_FLAG_COUNTERS) of the same kernels on the same scene"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             _, cpu = cpu_baseline(desc, cam, wl, integ_id)

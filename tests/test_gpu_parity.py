@@ -52,7 +52,7 @@ def test_c1_primary_hits_bit_exact(gpu_cornell):
     assert np.array_equal(bits(a["t"]), bits(b["t"])) and np.array_equal(bits(a["u"]), bits(b["u"])) and np.array_equal(bits(a["v"]), bits(b["v"]))
     c = gpu.trace_primary(cam, W, H, 16, flags=capi.FLAG_BRUTE_FORCE)
     assert np.array_equal(a, c), "SAH-BVH traversal and brute force disagree"
-    assert (a["prim"] >= 0).mean() > 0.5
+    assert 0.3 < (a["prim"] >= 0).mean() < 0.6   # the box is open towards the camera
 
 
 def test_c1_primary_hits_with_supplied_jitter(gpu_cornell):
@@ -142,7 +142,7 @@ def test_bvh_equals_brute_force_and_oracle_on_mesh_scene():
     c = orc.trace_rays(org, d)
     assert np.array_equal(a, b), "BVH vs GPU brute force"
     assert np.array_equal(a, c), "GPU vs oracle"
-    assert (a["prim"] >= 0).mean() > 0.9
+    assert (a["prim"] >= 0).mean() > 0.8
     oa = gpu.trace_rays(org, d, tmax, any_hit=True)
     ob = gpu.trace_rays(org, d, tmax, any_hit=True, flags=capi.FLAG_BRUTE_FORCE)
     oc = orc.trace_rays(org, d, tmax, any_hit=True)

@@ -285,7 +285,14 @@ __device__ __forceinline__ bool slab(const float lo0, const float lo1, const flo
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool traverse(const DScene& sc, V3 o, V3 d, Hit& h, int minId, int* sstack, TraceCounters& tc)
 {
-    const V3 idir = 1.0f / d;
+    // Box tests only: a zero (or denormal) direction component would make lo*idir - o*idir evaluate inf - inf = NaN,
+    // which fminf/fmaxf then drop on the wrong side. Clamping |d| to 1e-20 keeps every slab distance finite and
+    // ordered (a ray parallel to a slab and outside it still misses, inside it still spans (-huge, +huge)); the
+    // triangle test below always uses the true direction.
+    const float kTiny = 1e-20f;
+    const V3 ds = mk(fabsf(d.x) < kTiny ? copysignf(kTiny, d.x) : d.x, fabsf(d.y) < kTiny ? copysignf(kTiny, d.y) : d.y,
+                     fabsf(d.z) < kTiny ? copysignf(kTiny, d.z) : d.z);
+    const V3 idir = 1.0f / ds;
     const V3 ood = mk(o.x * idir.x, o.y * idir.y, o.z * idir.z);
     int lstack[kStackLocal];
     int sp = 0;

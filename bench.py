@@ -119,7 +119,8 @@ def cpu_baseline(desc, cam, wl, integ_id):
     from xraytracer_b200 import api, capi
     kind = "reference" if capi.have_reference() else "port"
     cpu = api.ReferenceScene(desc) if kind == "reference" else api.OracleScene(desc)
-    cores = cpu.max_threads()
+    # all host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     W, H = wl["width"], wl["height"]
     stride = wl["cpu_stride"]
     spp = wl["cpu_spp"]

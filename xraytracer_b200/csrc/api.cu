@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -97,7 +98,7 @@ struct xrtg_scene {
     xrtg_scene_info info{};
     int maxShadowPerPath = 1;
     // workspace
-    DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
+    DevBuf q0[2], q1[2], q2[2], hits, hitIdx, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
     unsigned long long* statsHost = nullptr; // pinned
     uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
     cudaEvent_t ev[4] = {};
@@ -429,6 +430,7 @@ int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, int maxI
         if (int rc = s->q2[k].ensure(f4b * maxPaths)) return rc;
     }
     if (int rc = s->hits.ensure(f4b * maxPaths)) return rc;
+    if (int rc = s->hitIdx.ensure(sizeof(uint32_t) * size_t(maxPaths))) return rc;
     const size_t nShadow = size_t(maxPaths) * s->maxShadowPerPath;
     if (int rc = s->s0.ensure(f4b * nShadow)) return rc;
     if (int rc = s->s1.ensure(f4b * nShadow)) return rc;
@@ -453,6 +455,7 @@ DQueues makeQueues(xrtg_scene* s)
         q.q2[k] = static_cast<float4*>(s->q2[k].p);
     }
     q.hits = static_cast<float4*>(s->hits.p);
+    q.hitIdx = static_cast<uint32_t*>(s->hitIdx.p);
     q.s0 = static_cast<float4*>(s->s0.p);
     q.s1 = static_cast<float4*>(s->s1.p);
     q.s2 = static_cast<float4*>(s->s2.p);
@@ -523,6 +526,17 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     w.mti = static_cast<uint32_t*>(s->mti.p);
 
     StageTimer tm{s, st, count || (p->flags & XRTG_FLAG_STAGE_TIMES) != 0};
+    // traversal tunables (development overrides through the environment)
+    auto envInt = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+    // Traversal kernel choice (measured sweep + ncu, profiles/r01_notes.md): deep BVHs use the refillable state-machine
+    // kernel k_trace (threshold 16, 4 steps per vote: 1.25x on the 1M-triangle scene); shallow BVHs (Cornell: 17 nodes,
+    // ~7 node visits per ray) use the simple run-to-completion kernels (threshold 0), which execute ~30 % fewer
+    // instructions per ray.
+    const bool deep = s->info.n_bvh_nodes > 512;
+    const int thrExt0 = envInt("XRT_THR_EXT0", deep ? 1 : 0), thrExt = envInt("XRT_THR_EXT", deep ? 16 : 0);
+    const int thrCon = envInt("XRT_THR_CON", deep ? 16 : 0);
+    const int spv = envInt("XRT_SPV", deep ? 4 : 1);
+    const bool dump = std::getenv("XRT_STAGE_DUMP") != nullptr;
     uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0;
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
@@ -541,7 +555,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
             tm.begin(kStageExtend);
-            K.extend(st, s->ds, q, src, b, brute, count, dstats); ++launches; ++nExtend;
+            K.extend(st, s->ds, q, src, b, brute, count, dstats, b == 0 ? thrExt0 : thrExt, spv); ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
             if (volume) K.shadeVolume(st, s->ds, q, w, src, b, brute, count, dstats);
@@ -550,7 +564,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             tm.end();
             if (hasShadow) {
                 tm.begin(kStageConnect);
-                K.connect(st, s->ds, q, b, brute, count, dstats); ++launches; ++nConnect;
+                K.connect(st, s->ds, q, b, brute, count, dstats, thrCon, spv); ++launches; ++nConnect;
                 tm.end();
             }
             if (volume) {
@@ -591,6 +605,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, s->stageEvents[k], s->stageEvents[k + 1]);
                 acc[s->stageKinds[k / 2]] += ms;
+                if (dump) std::fprintf(stderr, "stage %zu kind %d %.3f ms\n", k / 2, s->stageKinds[k / 2], ms);
             }
             stats->extend_ms = acc[kStageExtend]; stats->connect_ms = acc[kStageConnect];
             stats->shade_ms = acc[kStageShade]; stats->other_ms = acc[kStageOther];
@@ -660,7 +675,7 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
     unsigned long long* dstats = static_cast<unsigned long long*>(s->stats.p);
     CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
     K.raygen(st, makeCamera(cam), q, w, dj);
-    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0, false, dstats);
+    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0, false, dstats, 16, 1);
     CU(cudaGetLastError());
     // hits are indexed by path id = s * nPixels + pixel; the ABI wants [(pixel * spp) + s]
     std::vector<float4> tmp(nPaths);
@@ -683,8 +698,15 @@ int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir
     if (!s || !org || !dir || !out_hits) return fail(XRTG_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(XRTG_ERR_INVALID, "negative ray count");
     if (n == 0) return 0;
+    if (n > (1ll << 30)) return fail(XRTG_ERR_UNSUPPORTED, "too many rays for one call");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
+    // the rays are staged into the renderer's own queues and traced by the renderer's own traversal kernel
+    const int shadowPerPath = s->maxShadowPerPath;
+    s->maxShadowPerPath = 1;
+    const int rc0 = ensureWorkspace(s, 1, uint32_t(n), 1, false);
+    s->maxShadowPerPath = shadowPerPath;
+    if (rc0) return rc0;
     if (int rc = s->rayTmp[0].ensure(sizeof(float) * 3 * size_t(n))) return rc;
     if (int rc = s->rayTmp[1].ensure(sizeof(float) * 3 * size_t(n))) return rc;
     if (int rc = s->rayTmp[2].ensure(sizeof(float) * size_t(n))) return rc;
@@ -692,13 +714,15 @@ int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir
     CU(cudaMemcpyAsync(s->rayTmp[0].p, org, sizeof(float) * 3 * size_t(n), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s->rayTmp[1].p, dir, sizeof(float) * 3 * size_t(n), cudaMemcpyHostToDevice, st));
     if (tmax) CU(cudaMemcpyAsync(s->rayTmp[2].p, tmax, sizeof(float) * size_t(n), cudaMemcpyHostToDevice, st));
-    const KernelTable& K = (flags & XRTG_FLAG_EXACT) || true ? exactKernels() : fastKernels();
-    K.traceRays(st, s->ds, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
+    DQueues q = makeQueues(s);
+    CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
+    const KernelTable& K = exactKernels(); // parity hooks always use the no-FMA instantiation
+    K.traceRays(st, s->ds, q, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
                 tmax ? static_cast<const float*>(s->rayTmp[2].p) : nullptr, n, any_hit != 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0,
-                static_cast<float4*>(s->rayTmp[3].p));
+                static_cast<float4*>(s->rayTmp[3].p), static_cast<unsigned long long*>(s->stats.p));
     CU(cudaGetLastError());
     static_assert(sizeof(xrtg_hit) == sizeof(float4), "xrtg_hit must be 16 bytes");
-    CU(cudaMemcpyAsync(out_hits, s->rayTmp[3].p, sizeof(float4) * size_t(n), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_hits, any_hit ? s->rayTmp[3].p : static_cast<void*>(q.hits), sizeof(float4) * size_t(n), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return 0;
 }

@@ -8,15 +8,17 @@ namespace xrt {
 struct KernelTable {
     void (*seedMt)(cudaStream_t, const DWave&);
     void (*raygen)(cudaStream_t, const DCamera&, const DQueues&, const DWave&, const float* jitter);
-    void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, bool brute, bool count, unsigned long long* stats);
-    void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, bool brute, bool count, unsigned long long* stats);
+    void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, bool brute, bool count, unsigned long long* stats,
+                   int refillThreshold, int stepsPerVote);
+    void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, bool brute, bool count, unsigned long long* stats,
+                    int refillThreshold, int stepsPerVote);
     void (*shadeSurface)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce);
     void (*shadeVolume)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, bool brute, bool count,
                         unsigned long long* stats);
     void (*accumulate)(cudaStream_t, const DQueues&, const DWave&, float* accum, unsigned long long* stats);
     void (*finalize)(cudaStream_t, const float* accum, float* out, size_t n, float divisor);
-    void (*traceRays)(cudaStream_t, const DScene&, const float* org, const float* dir, const float* tmax, long long n, bool anyhit, bool brute,
-                      float4* out);
+    void (*traceRays)(cudaStream_t, const DScene&, const DQueues&, const float* org, const float* dir, const float* tmax, long long n,
+                      bool anyhit, bool brute, float4* out, unsigned long long* stats);
     void (*genJitter)(cudaStream_t, const DWave&, int spp, float* jitter);
 };
 

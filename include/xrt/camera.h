@@ -5,6 +5,11 @@
 #include "ray.h"
 #include "sampler.h"
 #include <xrtgpu.h>
+#if defined(__has_include)
+#if __has_include(<spdlog/spdlog.h>)
+#include <spdlog/spdlog.h> // the reference's camera.h:5 exposes spdlog transitively; examples/vpt.cpp:25 relies on it
+#endif
+#endif
 
 class Camera {
 protected:

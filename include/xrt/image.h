@@ -4,6 +4,9 @@
 #include <fstream>
 #include <string>
 #include <vector>
+#ifdef XRT_WITH_OPENCV
+#include <opencv2/opencv.hpp>
+#endif
 #include "geometry.h"
 
 class Image {
@@ -36,6 +39,22 @@ public:
         f << "PF\n" << width << " " << height << "\n-1.0\n";
         for (int i = int(height) - 1; i >= 0; --i) f.write(reinterpret_cast<const char*>(&pixels[size_t(i) * width]), sizeof(Vec3f) * width);
     }
+#ifdef XRT_WITH_OPENCV
+    // BGR 8-bit export exactly as the reference's Image::writeMat (image.h:116-136); only with an OpenCV (or stub) cv::Mat
+    cv::Mat writeMat()
+    {
+        cv::Mat mat(height, width, CV_8UC3);
+        for (uint32_t i = 0; i < height; ++i) {
+            auto prow = mat.ptr<uchar>(i);
+            for (uint32_t j = 0; j < width; ++j) {
+                const Vec3f rgb = getPixel(i, j);
+                for (int c = 0; c < 3; ++c)
+                    prow[3 * j + (2 - c)] = uint8_t(std::clamp(static_cast<uint32_t>(255.0f * rgb[c]), 0u, 255u));
+            }
+        }
+        return mat;
+    }
+#endif
     // additive: contiguous W*H*3 floats, the layout xrtg_render writes
     float* data() { return &pixels[0][0]; }
     const float* data() const { return pixels[0].getPtr(); }

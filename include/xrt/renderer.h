@@ -34,6 +34,7 @@ struct GpuOptions {
     int samplesPerWave = 0;  // 0 = auto
 };
 
+#pragma GCC visibility push(default)
 class GpuRenderer : public Renderer {
 public:
     GpuRenderer(uint32_t spp, Camera* cam, Integrator* inte, GpuOptions opt = GpuOptions());
@@ -42,13 +43,36 @@ public:
     // statistics of the last render() (ray counts, dropped samples, device milliseconds)
     const xrtg_stats& lastStats() const { return m_stats; }
 
-private:
+protected:
     const uint32_t n_samples;
     GpuOptions m_opt;
+
+private:
     // device scene cached across render() calls, keyed on (Scene*, Scene::version())
     mutable xrtg_scene* m_scene = nullptr;
     mutable const Scene* m_cachedFor = nullptr;
     mutable uint64_t m_cachedVersion = 0;
     mutable xrt::FlatScene m_flat;
     mutable xrtg_stats m_stats{};
+};
+
+#pragma GCC visibility pop
+
+// The reference's two renderer names (renderer.h:22-47), kept so that its examples compile and run unchanged
+// (`std::make_unique<NormalRenderer>(n_samples, camera.get(), integrator.get())`). The reference's NormalRenderer (serial)
+// and ParallelRenderer (PSTL) produce the SAME image — every pixel owns a std::mt19937 seeded with its linear index
+// (renderer.cpp:35-36). Here both run on the GPU in exact mode, i.e. they replay that very sample stream with the
+// reference's un-fused fp32 arithmetic, so their output matches the CPU renderers' (bit-exact for NormalIntegrator /
+// DirectIntegrator, ~1e-7 elsewhere). Use GpuRenderer for the counter-RNG throughput path. Neither has a CPU code path.
+class NormalRenderer : public GpuRenderer {
+public:
+    NormalRenderer(uint32_t spp, Camera* cam, Integrator* inte) : GpuRenderer(spp, cam, inte, exactOptions()) {}
+
+protected:
+    static GpuOptions exactOptions() { GpuOptions o; o.exact = true; return o; }
+};
+
+class ParallelRenderer : public NormalRenderer {
+public:
+    ParallelRenderer(uint32_t spp, Camera* cam, Integrator* inte) : NormalRenderer(spp, cam, inte) {}
 };

@@ -31,6 +31,7 @@ struct FlatScene {
 } // namespace xrt
 
 class Sampler;
+#pragma GCC visibility push(default) // libxrthost.so is built with hidden visibility; the C++ API is exported explicitly
 class Scene {
 public:
     ~Scene() = default;
@@ -62,3 +63,4 @@ private:
     int m_nextSeq = 0;
     uint64_t m_version = 0;
 };
+#pragma GCC visibility pop

@@ -40,9 +40,10 @@ def test_only_c_abi_is_exported():
     out = subprocess.run(["nm", "-D", "--defined-only", str(capi.GPU_LIB)], capture_output=True, text=True).stdout
     names = [l.split()[-1] for l in out.splitlines() if " T " in l]
     assert names and all(n.startswith("xrtg_") for n in names), names
-    out = subprocess.run(["nm", "-D", "--defined-only", str(capi.HOST_LIB)], capture_output=True, text=True).stdout
-    names = [l.split()[-1] for l in out.splitlines() if " T " in l]
-    assert names and all(n.startswith("xrth_") for n in names), names
+    # the host library exports the scripting surface plus the C++ drop-in API (Scene, GpuRenderer) and nothing else
+    out = subprocess.run(["nm", "-D", "-C", "--defined-only", str(capi.HOST_LIB)], capture_output=True, text=True).stdout
+    names = [l.split(" T ", 1)[1] for l in out.splitlines() if " T " in l]
+    assert names and all(n.startswith(("xrth_", "Scene::", "GpuRenderer::")) for n in names), names
 
 
 def test_invalid_arguments_are_rejected(cornell):

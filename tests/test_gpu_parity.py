@@ -254,6 +254,24 @@ def test_converged_volume_matches_reference_estimator():
         assert rel_rmse(a, b) < 0.2, integ
 
 
+def test_volume_large_wave_with_mostly_missing_rays():
+    """Regression: with millions of paths per wave and long runs of rays that miss the medium, every warp of the volume
+    kernel must keep fetching until the queue is exhausted (an early version stopped after an all-miss batch)."""
+    require_gpu()
+    s = scenes.volume_scene(n=32, light="quad")
+    gpu = api.GpuScene(s.flatten(), 0)
+    W, H = 1600, 900
+    cam = scenes.make_camera(W, H)
+    big, st = gpu.render(cam, W, H, 2, capi.INT_VOLUME, 16, seed=1)
+    assert st["tracking_steps"] > 0 and st["kernel_launches"] > 10
+    # same samples rendered with one sample per wave and as horizontal strips must give the same image
+    small, st1 = gpu.render(cam, W, H, 2, capi.INT_VOLUME, 16, seed=1, samples_per_wave=1)
+    assert st1["tracking_steps"] == st["tracking_steps"] and st1["closest_rays"] == st["closest_rays"]
+    assert np.allclose(big, small, rtol=1e-5, atol=1e-6)
+    lo = gpu.render(scenes.make_camera(160, 90), 160, 90, 64, capi.INT_VOLUME, 16, seed=2)[0]
+    assert abs(float(lo.mean()) - float(big.mean())) < 0.1 * float(lo.mean())
+
+
 def test_fast_mode_is_deterministic_and_seed_dependent(gpu_cornell):
     gpu, _, _ = gpu_cornell
     cam = scenes.make_camera(64, 48)

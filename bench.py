@@ -162,10 +162,33 @@ def run_reference(args, wl, rank, world):
             "config": {"workload": args.workload + ": " + wl["desc"], "step": "bounded CPU sample: " + last["sample"]},
             "cpu_baseline": last, "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Exactly ONE JSON line may reach stdout: libraries (NCCL prints its version banner there) are diverted to stderr by
+    pointing fd 1 at fd 2 for the whole run; emit() writes the result line to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -358,7 +381,7 @@ def main():
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "scene_build_ms": info["build_ms"], "scene_upload_ms": info["upload_ms"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,6 +10,7 @@
  *   xrtg_trace_primary    <- PinholeCamera::sampleRay + Scene::intersect (parity hook)
  *                                                               camera.h:49-60, scene.cpp:190-200
  *   xrtg_trace_rays       <- Scene::intersect / Scene::occluded  scene.cpp:190-211
+ *   xrtg_image_to_u8      <- Image::gammaCorrection + writePPM / writeMat quantisation   image.h:80-136
  *
  * Conventions
  *   - every function returns 0 on success or a negative xrtg_status; xrtg_last_error() returns a
@@ -273,6 +274,12 @@ int xrtg_trace_primary(xrtg_scene* scene, const xrtg_camera* cam, int width, int
  * semantics (emitter proxies skipped) -> out_hits[i].prim = 0/1 occluded flag in prim>=0. */
 int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float* dir, const float* tmax,
                     int any_hit, uint32_t flags, xrtg_hit* out_hits);
+
+/* Image post of the reference's Image class on the device (image.h:80-136): optional gammaCorrection — pow(x, 1/gamma) per
+ * channel (image.h:80-90), gamma <= 0 skips it — followed by the 8-bit quantisation shared by writePPM and writeMat,
+ * clamp(uint32(255*x), 0, 255), written RGB (PPM order, bgr = 0) or BGR (cv::Mat order, bgr = 1). rgb_host = W*H*3 floats,
+ * out_host = W*H*3 bytes (both host pointers). */
+int xrtg_image_to_u8(int device, const float* rgb_host, int width, int height, float gamma, int bgr, uint8_t* out_host);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

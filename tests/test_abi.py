@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_symbols():
     text = (ROOT / "include" / "xrtgpu.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(xrtg_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(xrtg_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_all_exported():

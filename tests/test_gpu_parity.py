@@ -374,3 +374,18 @@ def test_host_cpp_gpu_renderer_matches_c_abi(cornell):
     assert rc == 0
     ref, _, _ = api.OracleScene(desc).render(scenes.make_camera(W, H), W, H, 4, capi.INT_NORMAL, 1)
     assert np.array_equal(bits(rgb), bits(ref))
+
+
+def test_device_image_post_matches_reference_formula(gpu_cornell):
+    """gammaCorrection (image.h:80-90) + 8-bit quantisation (image.h:99-108, 116-136) on the device vs numpy; powf may
+    differ by an ulp between libms, so quantised values may differ by one LSB at a rounding boundary."""
+    gpu, _, _ = gpu_cornell
+    img, _ = gpu.render(scenes.make_camera(96, 64), 96, 64, 16, capi.INT_GI, 3, seed=1)
+    for gamma, bgr in ((0.0, False), (1.2, False), (2.2, True)):
+        got = api.image_to_u8(img, gamma, bgr)
+        v = img if gamma <= 0 else np.power(img, np.float32(1.0 / gamma), dtype=np.float32)
+        want = np.clip((np.float32(255.0) * v).astype(np.int64), 0, 255).astype(np.uint8)
+        if bgr:
+            want = want[..., ::-1]
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+        assert (got != want).mean() < 1e-3

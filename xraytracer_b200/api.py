@@ -101,6 +101,18 @@ class GpuScene:
         return hits
 
 
+def image_to_u8(rgb: np.ndarray, gamma: float = 0.0, bgr: bool = False, device: int = 0) -> np.ndarray:
+    """Image::gammaCorrection + the 8-bit quantisation of writePPM / writeMat (image.h:80-136) on the device."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    h, w, _ = rgb.shape
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    lib = capi.gpu()
+    rc = lib.xrtg_image_to_u8(device, rgb.ctypes.data, w, h, gamma, int(bgr), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"xrtg_image_to_u8 failed ({rc}): {lib.xrtg_last_error().decode()}")
+    return out
+
+
 class _CpuScene:
     """Shared wrapper of the two CPU checkers (same entry-point shapes, different prefix)."""
     pfx = ""

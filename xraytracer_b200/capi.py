@@ -116,7 +116,7 @@ ABI_VERSION = 1
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
-               "xrtg_trace_rays"]
+               "xrtg_trace_rays", "xrtg_image_to_u8"]
 
 GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
 HOST_LIB = PKG / "host" / "libxrthost.so"
@@ -155,6 +155,7 @@ def gpu():
     lib.xrtg_render_device.argtypes = [VP, P(Camera), P(RenderParams), VP, VP, P(Stats)]
     lib.xrtg_trace_primary.argtypes = [VP, P(Camera), C.c_int, C.c_int, C.c_int, VP, C.c_uint32, VP]
     lib.xrtg_trace_rays.argtypes = [VP, C.c_int64, VP, VP, VP, C.c_int, C.c_uint32, VP]
+    lib.xrtg_image_to_u8.argtypes = [C.c_int, VP, C.c_int, C.c_int, C.c_float, C.c_int, VP]
     lib._typed = True
     return lib
 

@@ -616,7 +616,43 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
 
 } // namespace
 
+__global__ void k_image_to_u8(const float* __restrict__ rgb, unsigned char* __restrict__ out, size_t nPixels, float invGamma, int bgr)
+{
+    for (size_t p = size_t(blockIdx.x) * blockDim.x + threadIdx.x; p < nPixels; p += size_t(gridDim.x) * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = rgb[3 * p + c];
+            if (invGamma > 0.f) v = powf(v, invGamma);               // image.h:85-87
+            const float s = 255.0f * v;                              // image.h:103-108 / 123-128
+            const unsigned int q = s >= 255.0f ? 255u : (s > 0.f ? (unsigned int)s : 0u);
+            out[3 * p + (bgr ? 2 - c : c)] = (unsigned char)q;
+        }
+    }
+}
+
 extern "C" {
+
+int xrtg_image_to_u8(int device, const float* rgb_host, int width, int height, float gamma, int bgr, uint8_t* out_host)
+{
+    if (!rgb_host || !out_host || width <= 0 || height <= 0) return fail(XRTG_ERR_INVALID, "bad image arguments");
+    if (xrtg_device_count() <= 0) return fail(XRTG_ERR_NO_DEVICE, "no CUDA device (libxrtgpu has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t n = size_t(width) * height;
+    float* d_in = nullptr;
+    unsigned char* d_out = nullptr;
+    CU(cudaMalloc(&d_in, n * 3 * sizeof(float)));
+    if (cudaMalloc(&d_out, n * 3) != cudaSuccess) { cudaFree(d_in); return fail(XRTG_ERR_OOM, "cudaMalloc failed"); }
+    cudaError_t e = cudaMemcpy(d_in, rgb_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_image_to_u8<<<int(std::min<size_t>((n + 255) / 256, 148 * 8)), 256>>>(d_in, d_out, n, gamma > 0.f ? 1.0f / gamma : 0.f, bgr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d_out, n * 3, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(XRTG_ERR_CUDA, std::string("xrtg_image_to_u8: ") + cudaGetErrorString(e));
+    return 0;
+}
 
 int xrtg_render_device(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgb_device, void* cuda_stream,
                        xrtg_stats* stats)

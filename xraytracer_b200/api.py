@@ -37,10 +37,10 @@ def _rays(org, dir, tmax):
 class GpuScene:
     """Device scene (SAH BVH + flattened arrays resident in HBM) created through xrtg_scene_create."""
 
-    def __init__(self, desc, device: int = 0):
+    def __init__(self, desc, device: int = 0, build_flags: int = 0):
         self.lib = capi.gpu()
         h = C.c_void_p()
-        rc = self.lib.xrtg_scene_create(desc, device, C.byref(h))
+        rc = self.lib.xrtg_scene_create2(desc, device, build_flags, C.byref(h))
         if rc != 0:
             raise RuntimeError(f"xrtg_scene_create failed ({rc}): {self.lib.xrtg_last_error().decode()}")
         self.h = h

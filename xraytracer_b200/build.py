@@ -44,7 +44,7 @@ def build_gpu(force=False, verbose=False) -> Path:
     """libxrtgpu.so. kernels_exact.cu is compiled with -fmad=false (parity), kernels_fast.cu with FMA."""
     out = CSRC / "libxrtgpu.so"
     headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "xrtgpu.h"]
-    units = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", []), ("api.cu", []), ("bvh.cpp", [])]
+    units = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", []), ("api.cu", []), ("lbvh.cu", []), ("bvh.cpp", [])]
     objs = []
     jobs = []
     for src, extra in units:

@@ -98,7 +98,8 @@ class Hit(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_prims", C.c_int32), ("n_triangles", C.c_int32), ("n_bvh_nodes", C.c_int32),
                 ("bvh_depth", C.c_int32), ("bvh_sah_cost", C.c_float), ("build_ms", C.c_float),
-                ("upload_ms", C.c_float), ("device_bytes", C.c_uint64), ("upload_bytes", C.c_uint64)]
+                ("upload_ms", C.c_float), ("device_bytes", C.c_uint64), ("upload_bytes", C.c_uint64),
+                ("bvh_build_ms", C.c_float), ("bvh_builder", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -112,9 +113,10 @@ OBJ_MESH, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
 LIGHT_QUAD, LIGHT_TRIANGLE, LIGHT_SPHERE = 0, 1, 2
 MEDIUM_HOMOGENEOUS_MIS, MEDIUM_HOMOGENEOUS_ACHROMATIC, MEDIUM_HOMOGENEOUS_NOMIS, MEDIUM_HETEROGENEOUS = range(4)
 ABI_VERSION = 1
+BUILD_LBVH_GPU = 1
 
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
-GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_upload",
+GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_create2", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
                "xrtg_trace_rays", "xrtg_image_to_u8"]
 
@@ -147,6 +149,7 @@ def gpu():
     lib.xrtg_device_count.restype = C.c_int
     lib.xrtg_last_error.restype = C.c_char_p
     lib.xrtg_scene_create.argtypes = [P(SceneDesc), C.c_int, P(VP)]
+    lib.xrtg_scene_create2.argtypes = [P(SceneDesc), C.c_int, C.c_uint32, P(VP)]
     lib.xrtg_scene_upload.argtypes = [VP]
     lib.xrtg_scene_get_info.argtypes = [VP, P(SceneInfo)]
     lib.xrtg_scene_destroy.argtypes = [VP]

@@ -16,6 +16,7 @@
 #include "bvh.h"
 #include "device_types.h"
 #include "kernels.h"
+#include "lbvh.h"
 
 using namespace xrt;
 
@@ -177,7 +178,9 @@ void xrtg_scene_destroy(xrtg_scene* s)
     delete s;
 }
 
-int xrtg_scene_create(const xrtg_scene_desc* d, int device, xrtg_scene** out)
+int xrtg_scene_create(const xrtg_scene_desc* d, int device, xrtg_scene** out) { return xrtg_scene_create2(d, device, 0u, out); }
+
+int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flags, xrtg_scene** out)
 {
     if (!out) return fail(XRTG_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -273,17 +276,45 @@ int xrtg_scene_create(const xrtg_scene_desc* d, int device, xrtg_scene** out)
             ++bi;
         }
     }
-    // ---- SAH BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
+    // ---- BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
     Bvh bvh;
-    buildBvh(buildTris.data(), uint32_t(nMeshTris), 4, bvh);
-    if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
-    std::memcpy(s->nodes.h, bvh.nodes.data(), s->nodes.bytes);
-    float4* tris = static_cast<float4*>(s->tris.h);
-    for (size_t k = 0; k < bvh.triOrder.size(); ++k) {
-        const uint32_t src = bvh.triOrder[k];
-        tris[3 * k] = trisId[3 * src];
-        tris[3 * k + 1] = trisId[3 * src + 1];
-        tris[3 * k + 2] = trisId[3 * src + 2];
+    bool builtOnGpu = false;
+    if ((build_flags & XRTG_BUILD_LBVH_GPU) && nMeshTris >= 2) {
+        // GPU build: triangles go up first, the tree and the leaf-ordered triangles are produced on the device and
+        // mirrored back into the pinned host copies (xrtg_scene_upload re-sends them)
+        if (int rc = s->nodes.alloc(sizeof(BvhNode) * size_t(nMeshTris - 1))) return rc;
+        CU(cudaMemcpyAsync(s->trisId.d, s->trisId.h, s->trisId.bytes, cudaMemcpyHostToDevice, s->stream));
+        LbvhInfo li;
+        CU(cudaStreamSynchronize(s->stream));
+        Timer tbv;
+        const cudaError_t e = buildLbvhDevice(static_cast<const float4*>(s->trisId.d), uint32_t(nMeshTris), static_cast<float4*>(s->tris.d),
+                                              static_cast<BvhNode*>(s->nodes.d), s->stream, &li);
+        if (e != cudaSuccess) return fail(XRTG_ERR_CUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e));
+        if (li.depth <= 60) { // deeper than the traversal stacks allow (pathological duplicates): fall back to the host SAH build
+            CU(cudaMemcpyAsync(s->nodes.h, s->nodes.d, s->nodes.bytes, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaMemcpyAsync(s->tris.h, s->tris.d, s->tris.bytes, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            bvh.depth = li.depth; bvh.pad = li.pad; bvh.sahCost = 0.f;
+            bvh.nodes.resize(size_t(li.nNodes)); // size bookkeeping only
+            builtOnGpu = true;
+            s->info.bvh_build_ms = tbv.ms();
+            s->info.bvh_builder = 1;
+        }
+    }
+    if (!builtOnGpu) {
+        Timer tbv;
+        buildBvh(buildTris.data(), uint32_t(nMeshTris), 4, bvh);
+        s->info.bvh_build_ms = tbv.ms();
+        s->info.bvh_builder = 0;
+        if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
+        std::memcpy(s->nodes.h, bvh.nodes.data(), s->nodes.bytes);
+        float4* tris = static_cast<float4*>(s->tris.h);
+        for (size_t k = 0; k < bvh.triOrder.size(); ++k) {
+            const uint32_t src = bvh.triOrder[k];
+            tris[3 * k] = trisId[3 * src];
+            tris[3 * k + 1] = trisId[3 * src + 1];
+            tris[3 * k + 2] = trisId[3 * src + 2];
+        }
     }
     // ---- lights, media, grids ----
     if (int rc = s->lights.alloc(sizeof(DLight) * size_t(std::max(d->n_area_lights, 1)))) return rc;

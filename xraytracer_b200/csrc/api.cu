@@ -567,6 +567,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     const int thrExt0 = envInt("XRT_THR_EXT0", deep ? 1 : 0), thrExt = envInt("XRT_THR_EXT", deep ? 16 : 0);
     const int thrCon = envInt("XRT_THR_CON", deep ? 16 : 0);
     const int spv = envInt("XRT_SPV", deep ? 4 : 1);
+    const int missMode = integ == XRTG_INT_DIRECT ? 1 : (integ == XRTG_INT_WHITTED ? 2 : 0);
     const bool dump = std::getenv("XRT_STAGE_DUMP") != nullptr;
     uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0;
     CU(cudaEventRecord(s->ev[0], st));
@@ -581,12 +582,19 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         w.sampleBase = uint32_t(p->sample_offset) + done;
         tm.begin(kStageOther);
         CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * size_t(nIter + 2), st));
-        K.raygen(st, dc, q, w, nullptr); ++launches;
+        // Shallow BVHs: ray generation is fused with the primary closest hit (k_primary, compact hit-only queue).
+        // Deep BVHs: separate raygen + the refillable traversal kernel, which is faster there even on primary rays.
+        // No bounce at all (maxDepth 0): only the per-path radiance has to be cleared.
+        const bool fusedPrimary = !deep && nIter > 0;
+        if (nIter == 0) CU(cudaMemsetAsync(q.radiance, 0, sizeof(float4) * size_t(w.nPaths), st));
+        else if (!fusedPrimary) { K.raygen(st, dc, q, w, nullptr); ++launches; }
         tm.end();
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
             tm.begin(kStageExtend);
-            K.extend(st, s->ds, q, src, b, brute, count, dstats, b == 0 ? thrExt0 : thrExt, spv); ++launches; ++nExtend;
+            if (b == 0 && fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats);
+            else K.extend(st, s->ds, q, src, b, brute, count, dstats, b == 0 ? thrExt0 : thrExt, spv);
+            ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
             if (volume) K.shadeVolume(st, s->ds, q, w, src, b, brute, count, dstats);

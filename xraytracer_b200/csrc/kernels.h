@@ -8,6 +8,8 @@ namespace xrt {
 struct KernelTable {
     void (*seedMt)(cudaStream_t, const DWave&);
     void (*raygen)(cudaStream_t, const DCamera&, const DQueues&, const DWave&, const float* jitter);
+    void (*primary)(cudaStream_t, const DScene&, const DCamera&, const DQueues&, const DWave&, bool brute, int missMode, bool count,
+                    unsigned long long* stats);
     void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, bool brute, bool count, unsigned long long* stats,
                    int refillThreshold, int stepsPerVote);
     void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, bool brute, bool count, unsigned long long* stats,

@@ -779,6 +779,82 @@ __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q,
     if (COUNT) { statAdd(stats, kStatNodesAny, tc.nodes); statAdd(stats, kStatTrisAny, tc.tris); }
 }
 
+// Block-aggregated append: ONE global atomic per CTA per call (same-address L2 atomics retire at ~1/ns; with one atomic per
+// warp the three queue counters were the whole duration of the bounce-0 shade launch). Must be called by every thread of
+// the CTA; `scratch` is kShadeWarps + 1 words of shared memory owned by this call site.
+constexpr int kShadeBlock = 256;
+constexpr int kShadeWarps = kShadeBlock / 32;
+template <int NWARPS = kShadeWarps>
+__device__ __forceinline__ uint32_t blockAppend(uint32_t* counter, bool want, uint32_t* scratch)
+{
+    const uint32_t mask = __ballot_sync(0xffffffffu, want);
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    if (lane == 0) scratch[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) { const uint32_t c = scratch[w]; scratch[w] = total; total += c; }
+        scratch[NWARPS] = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    const uint32_t slot = scratch[NWARPS] + scratch[warp] + __popc(mask & ((1u << lane) - 1u));
+    __syncthreads(); // scratch may be reused by the next call
+    return slot;
+}
+// ---------------------------------------------------------------------------------------------------------
+// primary: ray generation (renderer.cpp:42-52, camera.h:49-60) FUSED with the bounce-0 closest hit. Primary rays are
+// coherent and most of them miss in the benchmark views (59 % Cornell, 86 % volume), so instead of writing 8.3 M rays,
+// reading them back, writing 8.3 M hit records and letting shade skip the misses, this kernel resolves misses inline
+// (background 0, DirectIntegrator's 0.18 grey integrator.h:114, Whitted's sky integrator.h:385-389) and appends ONLY the
+// hits — ray + hit record — to a COMPACT bounce-0 queue (one atomic per CTA per 128 rays). It also initialises the
+// per-path radiance. Static tile partition: CTA b owns path ids [128 b, 128 b + 128), b += grid.
+// ---------------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQueues q, DWave w, int brute, int missMode, unsigned long long* stats)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    __shared__ uint32_t s_scratch[kBlock / 32 + 1];
+    const uint32_t n = w.nPaths;
+    TraceCounters tc;
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
+        const uint32_t pid = tile * kBlock + threadIdx.x;
+        bool hit = false;
+        V3 o = mk(0.f), d = mk(0.f);
+        Hit h{FLT_MAX, 0.f, 0.f, -1};
+        uint32_t ctr = 0;
+        if (pid < n) {
+            const uint32_t pix = pid % w.nPixels;
+            const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+            Rng rng;
+            rng.open(w, pid, 0);
+            const float r0 = rng.next();
+            const float r1 = rng.next();
+            ctr = rng.close();
+            const float u = (float(j) + r0) / float(uint32_t(w.width));
+            const float v = (float(i) + r1) / float(uint32_t(w.height));
+            cameraRay(cam, u, v, o, d);
+            closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+            hit = h.prim >= 0;
+            V3 c = mk(0.f);
+            if (!hit) {
+                if (missMode == 1) c = mk(float(0.18));
+                else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
+            }
+            q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        }
+        const uint32_t slot = blockAppend<kBlock / 32>(q.ctrl + kCtrlRays, hit, s_scratch);
+        if (hit) {
+            q.q0[0][slot] = make_float4(o.x, o.y, o.z, 1.0f);
+            q.q1[0][slot] = make_float4(d.x, d.y, d.z, 1.0f);
+            q.q2[0][slot] = make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr)));
+            q.hits[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
+    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // shading
 // ---------------------------------------------------------------------------------------------------------
@@ -911,28 +987,6 @@ struct ShadeOut {
     int dst;
 };
 
-// Block-aggregated append: ONE global atomic per CTA per call (same-address L2 atomics retire at ~1/ns; with one atomic per
-// warp the three queue counters were the whole duration of the bounce-0 shade launch). Must be called by every thread of
-// the CTA; `scratch` is kShadeWarps + 1 words of shared memory owned by this call site.
-constexpr int kShadeBlock = 256;
-constexpr int kShadeWarps = kShadeBlock / 32;
-__device__ __forceinline__ uint32_t blockAppend(uint32_t* counter, bool want, uint32_t* scratch)
-{
-    const uint32_t mask = __ballot_sync(0xffffffffu, want);
-    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
-    if (lane == 0) scratch[warp] = __popc(mask);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < kShadeWarps; ++w) { const uint32_t c = scratch[w]; scratch[w] = total; total += c; }
-        scratch[kShadeWarps] = total ? atomicAdd(counter, total) : 0u;
-    }
-    __syncthreads();
-    const uint32_t slot = scratch[kShadeWarps] + scratch[warp] + __popc(mask & ((1u << lane) - 1u));
-    __syncthreads(); // scratch may be reused by the next call
-    return slot;
-}
 __device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, V3 d, float tmax, uint32_t pid, V3 c, uint32_t* scratch)
 {
     const uint32_t slot = blockAppend(so.ctrlCur + kCtrlShadow, want, scratch);
@@ -1475,6 +1529,14 @@ inline void launchRaygen(cudaStream_t st, const DCamera& cam, const DQueues& q, 
     static thread_local int grid = 0;
     if (!grid) grid = gridFor((const void*)k_raygen);
     k_raygen<<<grid, kBlock, 0, st>>>(cam, q, w, jitter);
+}
+inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam, const DQueues& q, const DWave& w, bool brute, int missMode,
+                          bool count, unsigned long long* stats)
+{
+    static thread_local int g0 = 0, g1 = 0;
+    if (!g0) { g0 = gridFor((const void*)k_primary<false>); g1 = gridFor((const void*)k_primary<true>); }
+    if (count) k_primary<true><<<g1, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
+    else k_primary<false><<<g0, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
 }
 inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, bool brute, bool count, unsigned long long* stats,
                          int thr, int spv)

@@ -10,9 +10,9 @@ struct KernelTable {
     void (*raygen)(cudaStream_t, const DCamera&, const DQueues&, const DWave&, const float* jitter);
     void (*primary)(cudaStream_t, const DScene&, const DCamera&, const DQueues&, const DWave&, bool brute, int missMode, bool count,
                     unsigned long long* stats);
-    void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, bool brute, bool count, unsigned long long* stats,
+    void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, int brute /*0 BVH, 1 brute force, 2 small-scene smem*/, bool count, unsigned long long* stats,
                    int refillThreshold, int stepsPerVote);
-    void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, bool brute, bool count, unsigned long long* stats,
+    void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, int brute, bool count, unsigned long long* stats,
                     int refillThreshold, int stepsPerVote);
     void (*shadeSurface)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce);
     void (*shadeVolume)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, bool brute, bool count,

@@ -363,11 +363,45 @@ __device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, 
     return false;
 }
 
+// Small scenes (<= kSmallSceneTris triangles, e.g. every scene the reference ships): for INCOHERENT rays a warp that walks
+// a BVH diverges (8-11 of 32 lanes active per instruction, ncu), whereas testing every triangle — the reference's own loop,
+// primitive.cpp:83-138 — keeps all 32 lanes converged. Triangles are staged once per CTA in shared memory (48 B each,
+// broadcast reads) and the Moeller-Trumbore test is evaluated branch-free: the same operations in the same order as
+// rayTriangle(), the rejections of primitive.cpp:153-167 folded into one predicate (a NaN anywhere ends in `t > eps`
+// being false, exactly like the reference's early returns).
+constexpr int kSmallSceneTris = 64;
+template <bool ANY>
+__device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, int n, V3 o, V3 d, Hit& h, int minId)
+{
+    bool occluded = false;
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const float4 q0 = st[3 * i], q1 = st[3 * i + 1], q2 = st[3 * i + 2];
+        const V3 v0 = xyz(q0), e1 = xyz(q1), e2 = xyz(q2);
+        const V3 pvec = cross(d, e2);
+        const float det = dot(e1, pvec);
+        const float invDet = 1 / det;
+        const V3 tvec = o - v0;
+        const float u = dot(tvec, pvec) * invDet;
+        const V3 qvec = cross(tvec, e1);
+        const float v = dot(d, qvec) * invDet;
+        const float t = dot(e2, qvec) * invDet;
+        const bool ok = !(fabsf(det) < FLT_EPSILON) && !(u < 0 || u > 1) && !(v < 0 || u + v > 1) && (t > FLT_EPSILON);
+        if (ANY) occluded = occluded || (ok && (__float_as_int(q1.w) & 1) == 0 && t < h.t);
+        else {
+            const int id = __float_as_int(q0.w);
+            if (ok && id > minId) consider(h, t, u, v, id);
+        }
+    }
+    return occluded;
+}
+
 // Scene::intersect (scene.cpp:190-200) for one ray: boxes first (the LAST box hit in object order overwrites
 // whatever came before it, primitive.h:259-261; objects after it win only with a strictly smaller t), then
 // triangles through the BVH, then analytic spheres. Box hits return t1 in h.u.
 template <bool COUNT>
-__device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool brute, Hit& h, int* sstack, TraceCounters& tc)
+__device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool brute, Hit& h, int* sstack, TraceCounters& tc,
+                                           const float4* smallTris = nullptr)
 {
     h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
     int minId = -1;
@@ -377,7 +411,8 @@ __device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool br
         if (boxSlabs(xyz(bl), xyz(bh), o, d, t0, t1)) { h.t = t0; h.u = t1; h.v = 0.f; h.prim = __float_as_int(bl.w); minId = h.prim; }
     }
     if (sc.nTris > 0) {
-        if (brute) bruteTris<false>(sc, o, d, h, minId);
+        if (smallTris) smallSceneTris<false>(smallTris, sc.nBruteTris, o, d, h, minId);
+        else if (brute) bruteTris<false>(sc, o, d, h, minId);
         else traverse<false, COUNT>(sc, o, d, h, minId, sstack, tc);
     }
     for (int s = 0; s < sc.nSpheres; ++s) {
@@ -391,13 +426,15 @@ __device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool br
 
 // Scene::occluded (scene.cpp:202-211): BoxMesh::occluded is always true (primitive.h:266-268)
 template <bool COUNT>
-__device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax, bool brute, int* sstack, TraceCounters& tc)
+__device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax, bool brute, int* sstack, TraceCounters& tc,
+                                       const float4* smallTris = nullptr)
 {
     if (sc.nBoxes > 0) return true;
     Hit h;
     h.t = tmax; h.prim = 0x7fffffff; h.u = h.v = 0.f;
     if (sc.nTris > 0) {
-        if (brute ? bruteTris<true>(sc, o, d, h, -1) : traverse<true, COUNT>(sc, o, d, h, -1, sstack, tc)) return true;
+        if (smallTris) { if (smallSceneTris<true>(smallTris, sc.nBruteTris, o, d, h, -1)) return true; }
+        else if (brute ? bruteTris<true>(sc, o, d, h, -1) : traverse<true, COUNT>(sc, o, d, h, -1, sstack, tc)) return true;
     }
     for (int s = 0; s < sc.nSpheres; ++s) {
         const float4 cr = __ldg(sc.spheres + 2 * s);
@@ -738,6 +775,13 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend_simple(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
+    __shared__ float4 s_tris[3 * kSmallSceneTris];
+    const float4* smallTris = nullptr;
+    if (brute == 2 && sc.nBruteTris <= kSmallSceneTris) { // small-scene mode: stage every triangle once per CTA
+        for (int k = threadIdx.x; k < 3 * sc.nBruteTris; k += blockDim.x) s_tris[k] = sc.tris_id[k];
+        __syncthreads();
+        smallTris = s_tris;
+    }
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     TraceCounters tc;
@@ -747,7 +791,7 @@ __global__ void __launch_bounds__(kBlock) k_extend_simple(DScene sc, DQueues q, 
         if (i < n) {
             const float4 r0 = q.q0[src][i], r1 = q.q1[src][i];
             Hit h;
-            closestHit<COUNT>(sc, xyz(r0), xyz(r1), brute != 0, h, s_stack + threadIdx.x, tc);
+            closestHit<COUNT>(sc, xyz(r0), xyz(r1), brute == 1, h, s_stack + threadIdx.x, tc, smallTris);
             q.hits[i] = make_float4(h.prim >= 0 ? h.t : FLT_MAX, h.u, h.v, __int_as_float(h.prim));
         }
     }
@@ -759,6 +803,13 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q, int bounce, int brute, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
+    __shared__ float4 s_tris[3 * kSmallSceneTris];
+    const float4* smallTris = nullptr;
+    if (brute == 2 && sc.nBruteTris <= kSmallSceneTris) {
+        for (int k = threadIdx.x; k < 3 * sc.nBruteTris; k += blockDim.x) s_tris[k] = sc.tris_id[k];
+        __syncthreads();
+        smallTris = s_tris;
+    }
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlShadow];
     TraceCounters tc;
@@ -767,7 +818,7 @@ __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q,
         const uint32_t i = base + laneId();
         if (i < n) {
             const float4 s0 = q.s0[i], s1 = q.s1[i];
-            const bool occ = anyHit<COUNT>(sc, xyz(s0), xyz(s1), s0.w, brute != 0, s_stack + threadIdx.x, tc);
+            const bool occ = anyHit<COUNT>(sc, xyz(s0), xyz(s1), s0.w, brute == 1, s_stack + threadIdx.x, tc, smallTris);
             if (!occ) {
                 const float4 c = q.s2[i];
                 float* r = reinterpret_cast<float*>(q.radiance + __float_as_int(s1.w));
@@ -1538,7 +1589,7 @@ inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam,
     if (count) k_primary<true><<<g1, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
     else k_primary<false><<<g0, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
 }
-inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, bool brute, bool count, unsigned long long* stats,
+inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
                          int thr, int spv)
 {
     static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
@@ -1554,7 +1605,7 @@ inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, in
     if (count) k_trace<false, true><<<g1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv);
     else k_trace<false, false><<<g0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv);
 }
-inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, bool brute, bool count, unsigned long long* stats,
+inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, int brute, bool count, unsigned long long* stats,
                           int thr, int spv)
 {
     static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;

@@ -289,11 +289,11 @@ def main():
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
     # aggregate ray counts over ranks
-    agg = np.zeros(8, dtype=np.float64)
+    agg = np.zeros(9, dtype=np.float64)
     for st in stats:
         if st:
             agg += np.array([st["closest_rays"], st["shadow_rays"], st["kernel_launches"], st["extend_ms"], st["shade_ms"],
-                             st["connect_ms"], st["extend_launches"], st["tracking_steps"]], dtype=np.float64)
+                             st["connect_ms"], st["extend_launches"], st["tracking_steps"], st["primary_hits"]], dtype=np.float64)
     if world > 1:
         t = torch.tensor(agg, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -331,18 +331,25 @@ def main():
         samples = W * H * spp_total * args.steps
         value = samples / (ms * 1e-3) / 1e6
         rays = agg_all[0] + agg_all[1]
-        # ---- roofline of the dominant kernel: k_extend (closest-hit BVH traversal), rank 0's launches ----
-        # achieved  = COMPULSORY HBM bytes of the launches / their CUDA-event time: every ray is read once (32 B: origin,
-        #             direction) and its hit written once (16 B), plus the BVH + triangle arrays once per launch. BVH nodes
-        #             and triangles re-fetched per ray are served by L1/L2, not HBM, so they are reported separately as
-        #             `fetch` = rays x (64 B x nodes visited + 48 B x triangles tested) / time  (SURVEY §8(d)'s B_ray).
+        # ---- roofline of the dominant stage: closest-hit traversal, rank 0's launches ----
+        # (k_primary = ray generation fused with the bounce-0 hit on shallow BVHs, k_extend_simple / k_trace<closest> after)
+        # achieved  = COMPULSORY HBM bytes of those launches / their CUDA-event time:
+        #               fused primary launch : 16 B radiance init per path + 64 B (48 B ray + 16 B hit) per primary HIT
+        #               every other launch   : 32 B ray read + 16 B hit write per ray
+        #               + the BVH and triangle arrays once per launch.
+        #             BVH nodes / triangles re-fetched per ray are served by L1/L2, not HBM; they are reported separately
+        #             as `fetch` = rays x (64 B x nodes visited + 48 B x triangles tested) / time  (SURVEY §8(d)'s B_ray).
         peak, peak_src = measured_peak_hbm()
         n_cl = max(cst["closest_rays"], 1)
         nodes_per_ray = cst["nodes_visited"] / n_cl
         tris_per_ray = cst["tris_tested"] / n_cl
         ext_ms, ext_launches, closest_r0 = agg[3], max(agg[6], 1), agg[0]
         bvh_bytes = 64.0 * info["n_bvh_nodes"] + 48.0 * info["n_triangles"]
-        hbm_bytes = closest_r0 * 48.0 + ext_launches * bvh_bytes
+        paths_r0 = float(W) * H * my_spp * args.steps
+        if agg[8] > 0:   # fused primary kernel in use
+            hbm_bytes = paths_r0 * 16.0 + agg[8] * 64.0 + (closest_r0 - paths_r0) * 48.0 + ext_launches * bvh_bytes
+        else:
+            hbm_bytes = closest_r0 * 48.0 + ext_launches * bvh_bytes
         fetch_bytes = closest_r0 * (64.0 * nodes_per_ray + 48.0 * tris_per_ray)
         achieved = hbm_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         traffic = None
@@ -352,10 +359,10 @@ def main():
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit SAH-BVH traversal)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "closest-hit stage (k_primary fused raygen+bounce 0, k_extend_simple / k_trace after)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": hbm_bytes / ext_launches,
-                    "bytes_per_ray_hbm": 48.0, "bvh_bytes": bvh_bytes,
+                    "bytes_per_ray_hbm": hbm_bytes / max(closest_r0, 1.0), "bvh_bytes": bvh_bytes,
                     "fetch": {"achieved": fetch_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0, "unit": "GB/s",
                               "level": "L1/L2 (BVH node + triangle fetches, 64 B and 48 B records)",
                               "bytes_per_ray": 64.0 * nodes_per_ray + 48.0 * tris_per_ray,

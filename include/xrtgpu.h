@@ -225,6 +225,7 @@ typedef struct xrtg_stats {
     float shade_ms;
     float other_ms;
     float h2d_ms, d2h_ms;
+    uint64_t primary_hits;   /* primary rays that hit something = entries of the compact bounce-0 queue */
 } xrtg_stats;
 
 /* Closest-hit record of the parity hooks. prim = global primitive id (-1 = miss). */

@@ -85,7 +85,7 @@ class Stats(C.Structure):
                 ("tracking_steps", C.c_uint64), ("kernel_launches", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shade_launches", C.c_uint64), ("connect_launches", C.c_uint64), ("render_ms", C.c_float),
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("primary_hits", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -640,6 +640,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         stats->nodes_visited_shadow = s->statsHost[kStatNodesAny];
         stats->tris_tested_shadow = s->statsHost[kStatTrisAny];
         stats->tracking_steps = s->statsHost[kStatSteps];
+        stats->primary_hits = s->statsHost[kStatPrimaryHits];
         stats->kernel_launches = launches;
         stats->extend_launches = nExtend; stats->shade_launches = nShade; stats->connect_launches = nConnect;
         CU(cudaEventElapsedTime(&stats->render_ms, s->ev[0], s->ev[1]));

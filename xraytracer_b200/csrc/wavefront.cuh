@@ -868,6 +868,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     __shared__ uint32_t s_scratch[kBlock / 32 + 1];
     const uint32_t n = w.nPaths;
     TraceCounters tc;
+    uint32_t nHits = 0;
     for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
         const uint32_t pid = tile * kBlock + threadIdx.x;
         bool hit = false;
@@ -895,6 +896,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
             q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
         }
         const uint32_t slot = blockAppend<kBlock / 32>(q.ctrl + kCtrlRays, hit, s_scratch);
+        nHits += hit ? 1u : 0u;
         if (hit) {
             q.q0[0][slot] = make_float4(o.x, o.y, o.z, 1.0f);
             q.q1[0][slot] = make_float4(d.x, d.y, d.z, 1.0f);
@@ -903,6 +905,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
+    statAdd(stats, kStatPrimaryHits, nHits);
     if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
 }
 

@@ -182,14 +182,29 @@ void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out)
 #pragma omp single nowait
     B.build(root, 0, n, 0);
 
-    // flatten: every inner build node becomes one BvhNode holding its two children's boxes
+    // flatten: every inner build node becomes one BvhNode holding its two children's boxes. Layout: the root at index 0,
+    // then SIBLING PAIRS at even indices (two 64-byte records = one 128-byte line: the far sibling popped from the stack
+    // later is usually still in L1), subtrees placed depth-first so a descent walks forward through memory.
     const int32_t nBuild = B.next.load();
     std::vector<int32_t> innerIndex(nBuild, -1);
     int32_t nInner = 0;
-    for (int32_t i = 0; i < nBuild; ++i) if (B.pool[i].left >= 0) innerIndex[i] = nInner++;
-    // keep the root first
-    if (B.pool[root].left >= 0 && innerIndex[root] != 0) {
-        for (int32_t i = 0; i < nBuild; ++i) if (innerIndex[i] == 0) { std::swap(innerIndex[i], innerIndex[root]); break; }
+    if (B.pool[root].left >= 0) {
+        innerIndex[root] = 0;
+        nInner = 2; // slot 1 pads the root to a full line
+        std::vector<int32_t> stack{root};
+        while (!stack.empty()) {
+            const int32_t bn = stack.back();
+            stack.pop_back();
+            const int32_t l = B.pool[bn].left, r = B.pool[bn].right;
+            const bool li = B.pool[l].left >= 0, ri = B.pool[r].left >= 0;
+            if (li || ri) {
+                if (li) innerIndex[l] = nInner;
+                if (ri) innerIndex[r] = nInner + (li ? 1 : 0);
+                nInner += 2;
+                if (ri) stack.push_back(r);
+                if (li) stack.push_back(l); // left subtree first
+            }
+        }
     }
     out.triOrder = B.order;
     const float rootArea = std::max(B.pool[root].box.area(), 1e-30f);
@@ -205,6 +220,7 @@ void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out)
         return;
     }
     out.nodes.resize(nInner);
+    for (auto& nd : out.nodes) { setEmpty(nd, 0); setEmpty(nd, 1); } // padding slots are never referenced
     for (int32_t i = 0; i < nBuild; ++i) {
         const BuildNode& bn = B.pool[i];
         depth = std::max(depth, bn.depth + 1);

@@ -540,9 +540,6 @@ __device__ __forceinline__ void addRadiance(const DQueues& q, uint32_t pid, V3 c
 
 constexpr int kSentinel = 0x7fffffff;
 constexpr uint32_t kFetchChunk = 64;  // queue entries a warp reserves per atomic (256 costs up to 16 % in tail imbalance)
-#ifndef XRT_REFILL_THRESHOLD
-#define XRT_REFILL_THRESHOLD 22
-#endif
 
 struct RayState {
     V3 o, d, idir, ood;

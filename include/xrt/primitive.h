@@ -113,7 +113,9 @@ private:
             const float theta = PI * i / num_theta_;
             for (int j = 0; j <= num_phi_; ++j) {
                 const float phi = 2 * PI * j / num_phi_;
-                const Vec3f n(float(std::sin(theta) * std::sin(phi)), float(std::cos(theta)), float(std::sin(theta) * std::cos(phi)));
+                // the reference's unqualified sin()/cos() resolve to the C double overloads: products are formed in double
+                const double st = std::sin(double(theta)), ct = std::cos(double(theta));
+                const Vec3f n(float(st * std::sin(double(phi))), float(ct), float(st * std::cos(double(phi))));
                 pos.push_back(center_ + radius_ * n);
                 nrm.push_back(n);
             }

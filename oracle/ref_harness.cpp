@@ -529,5 +529,22 @@ void xrtref_kat_hg_sample(float g, const float* wo, uint32_t seed, float* out4)
     out4[0] = wi[0]; out4[1] = wi[1]; out4[2] = wi[2]; out4[3] = f;
 }
 
+// SphereMesh::Triangulate (primitive.cpp:170-205): writes 2*nt*np triangles as 18 floats each (v0 v1 v2 n0 n1 n2);
+// returns the triangle count.
+int xrtref_kat_sphere_mesh(const float* center, float radius, int nt, int np, float* out, int cap)
+{
+    SphereMesh sm(v3(center), radius, nt, np, nullptr, nullptr);
+    int n = 0;
+    for (const auto& p : sm.m_primitives) {
+        if (n < cap) {
+            float* o = out + size_t(n) * 18;
+            for (int k = 0; k < 3; ++k)
+                for (int a = 0; a < 3; ++a) { o[3 * k + a] = p.vertices()[k][a]; o[9 + 3 * k + a] = p.normals()[k][a]; }
+        }
+        ++n;
+    }
+    return n;
+}
+
 } // extern "C"
 #pragma GCC visibility pop

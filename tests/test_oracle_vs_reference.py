@@ -58,3 +58,23 @@ def test_volume_cases_bit_exact_live():
             a, _, _ = api.ReferenceScene(desc).render(cam, 40, 40, 6, integ, 12)
             b, _, _ = api.OracleScene(desc).render(cam, 40, 40, 6, integ, 12)
             assert np.array_equal(bits(a), bits(b)), (name, integ)
+
+
+def test_sphere_mesh_tessellation_matches_reference_triangulate():
+    """The host API's SphereMesh (include/xrt/primitive.h) against the reference's SphereMesh::Triangulate
+    (primitive.cpp:170-205): same triangle count and order; positions/normals equal to float rounding (the reference
+    evaluates sin/cos in double through the C overloads, we do the same)."""
+    import ctypes as C
+    lib = capi.reference()
+    lib.xrtref_kat_sphere_mesh.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    nt, nph = 7, 9
+    want = np.zeros((2 * nt * nph, 18), np.float32)
+    n = lib.xrtref_kat_sphere_mesh((C.c_float * 3)(1.0, 2.0, 3.0), 2.5, nt, nph, want.ctypes.data, len(want))
+    assert n == 2 * nt * nph
+    s = scenes.HostScene()
+    s.add_sphere_mesh("sm", (1.0, 2.0, 3.0), 2.5, nt, nph, (1, 1, 1))
+    d = s.flatten().contents
+    got = np.array([list(d.triangles[i].v0) + list(d.triangles[i].v1) + list(d.triangles[i].v2) + list(d.triangles[i].n0)
+                    + list(d.triangles[i].n1) + list(d.triangles[i].n2) for i in range(d.n_triangles)], np.float32)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.abs(got - want).max()

@@ -546,5 +546,28 @@ int xrtref_kat_sphere_mesh(const float* center, float radius, int nt, int np, fl
     return n;
 }
 
+// Constructor arithmetic of the host-side classes the GPU path mirrors (light.cpp:6-14,49-57,84-90,115-134; camera.h:41-47):
+// kind 0 quad / 1 triangle: out9 = v0_ v1_ v2_ ; 2 sphere: out[0..2] = center_ ; 3 point: pos ; 4 distant: dir.
+void xrtref_kat_light_ctor(int kind, const float* a, const float* b, const float* c, const float* l2w16, float* out9)
+{
+    spdlog::set_level(spdlog::level::off);
+    Matrix44f m(l2w16[0], l2w16[1], l2w16[2], l2w16[3], l2w16[4], l2w16[5], l2w16[6], l2w16[7], l2w16[8], l2w16[9], l2w16[10],
+                l2w16[11], l2w16[12], l2w16[13], l2w16[14], l2w16[15]);
+    auto put = [&](int k, const Vec3f& v) { out9[3 * k] = v[0]; out9[3 * k + 1] = v[1]; out9[3 * k + 2] = v[2]; };
+    for (int k = 0; k < 9; ++k) out9[k] = 0.f;
+    if (kind == 0) { QuadLight L(v3(a), v3(b), v3(c), m, Vec3f(1.0f)); put(0, L.v0_); put(1, L.v1_); put(2, L.v2_); }
+    else if (kind == 1) { TriangleLight L(v3(a), v3(b), v3(c), m, Vec3f(1.0f)); put(0, L.v0_); put(1, L.v1_); put(2, L.v2_); }
+    else if (kind == 2) { SphereLight L(v3(a), 1.0f, m, Vec3f(1.0f)); put(0, L.center_); }
+    else if (kind == 3) { PointLight L(m, Vec3f(1.0f), 1.0f); put(0, L.pos); }
+    else { DistantLight L(m, Vec3f(1.0f), 1.0f); put(0, L.dir); }
+}
+
+float xrtref_kat_camera_scale(float fov)
+{
+    spdlog::set_level(spdlog::level::off);
+    PinholeCamera cam(1.0f, Matrix44f(), fov);
+    return cam.scale;
+}
+
 } // extern "C"
 #pragma GCC visibility pop

@@ -78,3 +78,41 @@ def test_sphere_mesh_tessellation_matches_reference_triangulate():
                     + list(d.triangles[i].n1) + list(d.triangles[i].n2) for i in range(d.n_triangles)], np.float32)
     assert got.shape == want.shape
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.abs(got - want).max()
+
+
+def test_host_constructors_match_reference():
+    """Light constructors push their geometry through lightToWorld (multVecMatrix / multDirMatrix) and the camera evaluates
+    tan(FOV/2) on the host; the flattened values must be bit-identical to what the reference's constructors compute."""
+    import ctypes as C
+    lib = capi.reference()
+    fp = C.POINTER(C.c_float)
+    lib.xrtref_kat_light_ctor.argtypes = [C.c_int, fp, fp, fp, fp, fp]
+    lib.xrtref_kat_camera_scale.restype = C.c_float
+    lib.xrtref_kat_camera_scale.argtypes = [C.c_float]
+    f3 = lambda v: (C.c_float * 3)(*v)
+    l2w = [0.95292, 0.289503, 0.0901785, 0, -0.0960954, 0.5704, -0.815727, 0, -0.287593, 0.768656, 0.571365, 0, 5.0, 2.5, -1.0, 1]
+    m16 = (C.c_float * 16)(*l2w)
+    a, b, c = (343.0, 548.0, 227.0), (343.0, 548.0, 332.0), (213.0, 548.0, 227.0)
+
+    def ref(kind):
+        out = (C.c_float * 9)()
+        lib.xrtref_kat_light_ctor(kind, f3(a), f3(b), f3(c), m16, out)
+        return np.array(out[:], np.float32)
+
+    s = scenes.HostScene()
+    s.add_quad_light("q", a, b, c, (1, 1, 1), l2w=l2w)
+    s.add_triangle_light("t", a, b, c, (1, 1, 1), l2w=l2w)
+    s.add_sphere_light("s", a, 1.0, (1, 1, 1), l2w=l2w)
+    s.add_point_light("p", l2w, (1, 1, 1), 1.0)
+    s.add_distant_light("d", l2w, (1, 1, 1), 1.0)
+    d = s.flatten().contents
+    bits = lambda x: np.asarray(x, np.float32).view(np.uint32)
+    for li, kind in ((0, 0), (1, 1)):
+        L = d.area_lights[li]
+        assert np.array_equal(bits(list(L.v0) + list(L.v1) + list(L.v2)), bits(ref(kind)))
+    assert np.array_equal(bits(list(d.area_lights[2].v0)), bits(ref(2)[:3]))
+    assert np.array_equal(bits(list(d.delta_lights[0].pos_or_dir)), bits(ref(3)[:3]))
+    assert np.array_equal(bits(list(d.delta_lights[1].pos_or_dir)), bits(ref(4)[:3]))
+    for fov in (60.0, 90.0, 36.86989764, 45.0, 20.0):
+        cam = scenes.make_camera(16, 9, fov=fov)
+        assert bits([cam.scale])[0] == bits([lib.xrtref_kat_camera_scale(fov)])[0], fov

@@ -27,6 +27,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <stdexcept>
 #include <memory>
 #include <queue>
 #include <random>
@@ -102,6 +103,7 @@ public:
     }
 
     float getMaxDensity() const override { return g.max_density; }
+    xrtg_grid desc() const { xrtg_grid d = g; d.data = data.data(); return d; }
 
 private:
     xrtg_grid g;
@@ -168,6 +170,181 @@ struct xrtref_scene {
     std::unordered_map<std::string, int> insertSeqByName;
     int nPrims = 0;
 };
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RefGpuRenderer — the binding of INTEGRATION.md, compiled against the reference's OWN headers: a third sibling of
+// NormalRenderer / ParallelRenderer (renderer.h:22-47) that flattens a reference `Scene` and renders it through the C ABI
+// of libxrtgpu.so. It stands in for the `gpu_renderer.cpp` a maintainer would add to the reference tree; where that file
+// would use the additive accessors, this test harness reads the private members directly (access opened above).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct RefFlat {
+    std::vector<xrtg_object> objects;
+    std::vector<std::string> names;
+    std::vector<xrtg_triangle> tris;
+    std::vector<xrtg_sphere> spheres;
+    std::vector<xrtg_box> boxes;
+    std::vector<xrtg_material> materials;
+    std::vector<xrtg_area_light> lights;
+    std::vector<xrtg_delta_light> dlights;
+    std::vector<xrtg_medium> media;
+    std::vector<xrtg_grid> grids;
+    xrtg_scene_desc desc{};
+};
+
+void put3(float* d, const Vec3f& v) { d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; }
+
+bool flattenReferenceScene(const Scene& scene, RefFlat& f, std::string& err)
+{
+    std::map<const Material*, int> matIdx;
+    std::map<const AreaLight*, int> lightIdx;
+    std::map<const Medium*, int> medIdx;
+    for (const auto& L : scene.m_areaLights) {
+        xrtg_area_light d{};
+        if (auto* q = dynamic_cast<const QuadLight*>(L.get())) { d.kind = XRTG_LIGHT_QUAD; put3(d.v0, q->v0_); put3(d.v1, q->v1_); put3(d.v2, q->v2_); }
+        else if (auto* t = dynamic_cast<const TriangleLight*>(L.get())) { d.kind = XRTG_LIGHT_TRIANGLE; put3(d.v0, t->v0_); put3(d.v1, t->v1_); put3(d.v2, t->v2_); }
+        else if (auto* sp = dynamic_cast<const SphereLight*>(L.get())) { d.kind = XRTG_LIGHT_SPHERE; put3(d.v0, sp->center_); d.radius = sp->radius_; }
+        else { err = "unknown AreaLight subclass"; return false; }
+        put3(d.Le, L->Le_);
+        lightIdx[L.get()] = int(f.lights.size());
+        f.lights.push_back(d);
+    }
+    for (const auto& L : scene.m_deltaLights) {
+        xrtg_delta_light d{};
+        if (auto* p = dynamic_cast<const PointLight*>(L.get())) { d.kind = XRTG_DLIGHT_POINT; put3(d.pos_or_dir, p->pos); }
+        else if (auto* dl = dynamic_cast<const DistantLight*>(L.get())) { d.kind = XRTG_DLIGHT_DISTANT; put3(d.pos_or_dir, dl->dir); }
+        else { err = "unknown DeltaLight subclass"; return false; }
+        put3(d.radiance, L->color * L->intensity);
+        f.dlights.push_back(d);
+    }
+    int seq = 0;
+    f.names.reserve(scene.m_objects.size());
+    for (const auto& [name, obj] : scene.m_objects) { // the order Scene::intersect walks (scene.cpp:193)
+        xrtg_object rec{};
+        rec.material = rec.area_light = rec.medium = -1;
+        rec.insert_seq = seq++;
+        if (auto* m = dynamic_cast<const Mesh*>(obj.get())) {
+            rec.kind = XRTG_OBJ_MESH; rec.first = int(f.tris.size()); rec.count = int(m->m_primitives.size());
+            for (const auto& p : m->m_primitives) {
+                xrtg_triangle t;
+                put3(t.v0, p.vertices()[0]); put3(t.v1, p.vertices()[1]); put3(t.v2, p.vertices()[2]);
+                put3(t.n0, p.normals()[0]); put3(t.n1, p.normals()[1]); put3(t.n2, p.normals()[2]);
+                f.tris.push_back(t);
+            }
+        }
+        else if (auto* sp = dynamic_cast<const Sphere*>(obj.get())) {
+            rec.kind = XRTG_OBJ_SPHERE; rec.first = int(f.spheres.size()); rec.count = 1;
+            xrtg_sphere d{};
+            put3(d.center, sp->m_center); d.radius = sp->m_raduis;
+            f.spheres.push_back(d);
+        }
+        else if (auto* bx = dynamic_cast<const BoxMesh*>(obj.get())) {
+            rec.kind = XRTG_OBJ_BOX; rec.first = int(f.boxes.size()); rec.count = 1;
+            xrtg_box d{};
+            put3(d.pmin, bx->box.pMin); put3(d.pmax, bx->box.pMax);
+            f.boxes.push_back(d);
+        }
+        else { err = "unknown Object subclass"; return false; }
+        if (const Material* mat = obj->m_material) {
+            auto it = matIdx.find(mat);
+            if (it == matIdx.end()) {
+                auto* lam = dynamic_cast<const Lambert*>(mat);
+                if (!lam) { err = "material without a GPU implementation"; return false; }
+                xrtg_material d{};
+                d.kind = XRTG_MAT_LAMBERT; put3(d.albedo, lam->m_albedo);
+                it = matIdx.emplace(mat, int(f.materials.size())).first;
+                f.materials.push_back(d);
+            }
+            rec.material = it->second;
+        }
+        if (obj->m_areaLight) rec.area_light = lightIdx.at(obj->m_areaLight);
+        if (const Medium* med = obj->m_medium) {
+            auto it = medIdx.find(med);
+            if (it == medIdx.end()) {
+                xrtg_medium d{};
+                d.grid = -1; d.density_mul = 1.0f;
+                d.g = static_cast<const HenyeyGreenstein*>(med->phaseFunction.get())->g;
+                if (auto* h = dynamic_cast<const HeterogeneousMedium*>(med)) {
+                    d.kind = XRTG_MEDIUM_HETEROGENEOUS;
+                    put3(d.sigma_a, h->absorptionColor); put3(d.sigma_s, h->scatteringColor); d.density_mul = h->densityMultiplier;
+                    auto* dg = dynamic_cast<const DenseGrid*>(h->densityGridPtr);
+                    if (!dg) { err = "density grid without a GPU implementation"; return false; }
+                    d.grid = int(f.grids.size());
+                    f.grids.push_back(dg->desc());
+                }
+                else if (auto* hm = dynamic_cast<const HomogeneousMedium*>(med)) {
+                    d.kind = dynamic_cast<const HomogeneousMediumMIS*>(med) ? XRTG_MEDIUM_HOMOGENEOUS_MIS
+                             : (dynamic_cast<const HomogeneousMediumAchromatic*>(med) ? XRTG_MEDIUM_HOMOGENEOUS_ACHROMATIC : XRTG_MEDIUM_HOMOGENEOUS_NOMIS);
+                    put3(d.sigma_a, hm->sigma_a); put3(d.sigma_s, hm->sigma_s);
+                }
+                else { err = "unknown Medium subclass"; return false; }
+                it = medIdx.emplace(med, int(f.media.size())).first;
+                f.media.push_back(d);
+            }
+            rec.medium = it->second;
+        }
+        f.names.push_back(name);
+        f.objects.push_back(rec);
+    }
+    for (size_t i = 0; i < f.objects.size(); ++i) f.objects[i].name = f.names[i].c_str();
+    xrtg_scene_desc& d = f.desc;
+    d.abi_version = XRTG_ABI_VERSION;
+    d.n_objects = int(f.objects.size()); d.objects = f.objects.data();
+    d.n_triangles = int(f.tris.size()); d.triangles = f.tris.data();
+    d.n_spheres = int(f.spheres.size()); d.spheres = f.spheres.data();
+    d.n_boxes = int(f.boxes.size()); d.boxes = f.boxes.data();
+    d.n_materials = int(f.materials.size()); d.materials = f.materials.data();
+    d.n_area_lights = int(f.lights.size()); d.area_lights = f.lights.data();
+    d.n_delta_lights = int(f.dlights.size()); d.delta_lights = f.dlights.data();
+    d.n_media = int(f.media.size()); d.media = f.media.data();
+    d.n_grids = int(f.grids.size()); d.grids = f.grids.data();
+    return true;
+}
+
+class RefGpuRenderer : public Renderer { // the reference's plug-in point, renderer.h:8-20
+public:
+    RefGpuRenderer(uint32_t spp, Camera* cam, Integrator* inte, uint32_t flags, uint32_t seed)
+        : Renderer(cam, inte), n_samples(spp), flags(flags), seed(seed) {}
+
+    void render(const Scene& scene, Sampler::SamplerType, Image& image) const override
+    {
+        RefFlat flat;
+        std::string err;
+        if (!flattenReferenceScene(scene, flat, err)) throw std::runtime_error("[RefGpuRenderer] " + err);
+        xrtg_scene* gs = nullptr;
+        if (xrtg_scene_create(&flat.desc, 0, &gs) != XRTG_OK) throw std::runtime_error(std::string("[RefGpuRenderer] ") + xrtg_last_error());
+        auto* pc = dynamic_cast<const PinholeCamera*>(camera);
+        if (!pc) { xrtg_scene_destroy(gs); throw std::runtime_error("[RefGpuRenderer] camera model without a GPU implementation"); }
+        xrtg_camera cam{};
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) cam.c2w[4 * r + c] = pc->camera2world[r][c];
+        cam.scale = pc->scale; cam.aspect = pc->aspect_ratio;
+        xrtg_render_params p{};
+        p.width = int(image.getWidth()); p.height = int(image.getHeight());
+        p.spp = p.spp_total = int(n_samples);
+        p.flags = flags; p.seed = seed; p.max_depth = 1;
+        if (dynamic_cast<const NormalIntegrator*>(integrator)) p.integrator = XRTG_INT_NORMAL;
+        else if (dynamic_cast<const FurnaceIntegrator*>(integrator)) p.integrator = XRTG_INT_FURNACE;
+        else if (dynamic_cast<const DirectIntegrator*>(integrator)) p.integrator = XRTG_INT_DIRECT;
+        else if (auto* i1 = dynamic_cast<const IndirectIntegrator*>(integrator)) { p.integrator = XRTG_INT_INDIRECT; p.max_depth = int(i1->m_maxDepth); }
+        else if (auto* i2 = dynamic_cast<const GIIntegrator*>(integrator)) { p.integrator = XRTG_INT_GI; p.max_depth = int(i2->m_maxDepth); }
+        else if (auto* i3 = dynamic_cast<const WhittedIntegrator*>(integrator)) { p.integrator = XRTG_INT_WHITTED; p.max_depth = int(i3->m_maxDepth); }
+        else if (auto* i4 = dynamic_cast<const VolumePathTracing*>(integrator)) { p.integrator = XRTG_INT_VOLUME; p.max_depth = int(i4->m_maxDepth); }
+        else if (auto* i5 = dynamic_cast<const VolumePathTracingNEE*>(integrator)) { p.integrator = XRTG_INT_VOLUME_NEE; p.max_depth = int(i5->m_maxDepth); }
+        else { xrtg_scene_destroy(gs); throw std::runtime_error("[RefGpuRenderer] integrator without a GPU implementation"); }
+        static_assert(sizeof(Vec3f) == 3 * sizeof(float), "Image::pixels must be tightly packed RGB");
+        const int rc = xrtg_render(gs, &cam, &p, &image.pixels[0][0], nullptr);
+        const std::string msg = rc == XRTG_OK ? "" : xrtg_last_error();
+        xrtg_scene_destroy(gs);
+        if (rc != XRTG_OK) throw std::runtime_error("[RefGpuRenderer] " + msg);
+    }
+
+private:
+    const uint32_t n_samples, flags, seed;
+};
+
+} // namespace
 
 static std::unique_ptr<AreaLight> makeAreaLight(const xrtg_area_light& L)
 {
@@ -388,6 +565,32 @@ int xrtref_render(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_param
                 o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
             }
     }
+    return 0;
+}
+
+// The same reference Scene / Camera / Integrator objects rendered through the GPU sibling renderer, called polymorphically
+// through the reference's `Renderer*` exactly as examples/cornellbox.cpp:61-63 would.
+int xrtref_render_gpu(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_params* p, float* rgb)
+{
+    spdlog::set_level(spdlog::level::off);
+    auto cam = makeCamera(c);
+    auto integ = makeIntegrator(p->integrator, p->max_depth);
+    if (!integ) { g_err = "unknown integrator"; return -1; }
+    Image image(p->width, p->height);
+    std::unique_ptr<Renderer> renderer = std::make_unique<RefGpuRenderer>(uint32_t(p->spp), cam.get(), integ.get(), p->flags, p->seed);
+    try {
+        renderer->render(s->scene, Sampler::SamplerType::Uniform, image);
+    }
+    catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+    for (int i = 0; i < p->height; ++i)
+        for (int j = 0; j < p->width; ++j) {
+            const Vec3f v = image.getPixel(i, j);
+            float* o = rgb + (size_t(i) * p->width + j) * 3;
+            o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        }
     return 0;
 }
 

@@ -193,6 +193,16 @@ class ReferenceScene(_CpuScene):
     def _lib():
         return capi.reference()
 
+    def render_gpu(self, cam, width, height, spp, integrator, max_depth=1, flags=0, seed=0):
+        """The SAME reference Scene object rendered by RefGpuRenderer (oracle/ref_harness.cpp): a `Renderer` subclass built
+        against the reference's own headers that calls libxrtgpu.so — the binding INTEGRATION.md describes."""
+        p = _params(width, height, spp, integrator, max_depth, flags, seed)
+        rgb = np.zeros((height, width, 3), dtype=np.float32)
+        rc = self.lib.xrtref_render_gpu(self.h, C.byref(cam), C.byref(p), rgb.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"xrtref_render_gpu failed: {self.lib.xrtref_last_error().decode()}")
+        return rgb
+
     def object_order(self):
         buf = (C.c_int32 * 4096)()
         n = self.lib.xrtref_object_order(self.h, buf, 4096)

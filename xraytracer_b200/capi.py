@@ -239,5 +239,6 @@ def reference():
         _type_oracle(lib, "xrtref_", False)
         lib.xrtref_object_order.argtypes = [VP, P(C.c_int32), C.c_int]
         lib.xrtref_render_pstl.argtypes = [VP, P(Camera), P(RenderParams), VP, P(C.c_double)]
+        lib.xrtref_render_gpu.argtypes = [VP, P(Camera), P(RenderParams), VP]
         lib._typed = True
     return lib

@@ -99,7 +99,7 @@ struct xrtg_scene {
     xrtg_scene_info info{};
     int maxShadowPerPath = 1;
     // workspace
-    DevBuf q0[2], q1[2], q2[2], hits, hitIdx, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
+    DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
     unsigned long long* statsHost = nullptr; // pinned
     uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
     cudaEvent_t ev[4] = {};
@@ -461,7 +461,6 @@ int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, int maxI
         if (int rc = s->q2[k].ensure(f4b * maxPaths)) return rc;
     }
     if (int rc = s->hits.ensure(f4b * maxPaths)) return rc;
-    if (int rc = s->hitIdx.ensure(sizeof(uint32_t) * size_t(maxPaths))) return rc;
     const size_t nShadow = size_t(maxPaths) * s->maxShadowPerPath;
     if (int rc = s->s0.ensure(f4b * nShadow)) return rc;
     if (int rc = s->s1.ensure(f4b * nShadow)) return rc;
@@ -486,7 +485,6 @@ DQueues makeQueues(xrtg_scene* s)
         q.q2[k] = static_cast<float4*>(s->q2[k].p);
     }
     q.hits = static_cast<float4*>(s->hits.p);
-    q.hitIdx = static_cast<uint32_t*>(s->hitIdx.p);
     q.s0 = static_cast<float4*>(s->s0.p);
     q.s1 = static_cast<float4*>(s->s1.p);
     q.s2 = static_cast<float4*>(s->s2.p);

@@ -72,13 +72,12 @@ struct DCamera {
 struct DQueues {
     float4 *q0[2], *q1[2], *q2[2]; // ping-pong ray queues
     float4* hits;                  // t,u,v | prim id, indexed like the ray queue being extended
-    uint32_t* hitIdx;              // compact list of ray-queue indices whose ray hit something (shade input)
     float4 *s0, *s1, *s2;          // shadow queue
     float4* radiance;              // per path id: rgb | unused
-    uint32_t* ctrl;                // per bounce b: ctrl[8b+0]=#rays  +1=#shadow  +2..+4 = work-fetch cursors  +5=#hits
+    uint32_t* ctrl;                // per bounce b: ctrl[8b+0]=#rays  +1=#shadow  +2..+4 = work-fetch cursors
 };
 
-enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4, kCtrlHits = 5 };
+enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
 
 // device-side statistics (uint64 each)
 enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatCount };

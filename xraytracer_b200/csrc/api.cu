@@ -93,7 +93,7 @@ struct xrtg_scene {
     int device = 0;
     cudaStream_t stream = nullptr; // uploads + host-buffer renders
     // scene arrays (pinned host copy + device copy)
-    Mirror nodes, tris, trisId, prims, spheres, boxes, lights, dlights, media, grids;
+    Mirror nodes, tris, trisId, ftris, ftrisId, prims, spheres, boxes, lights, dlights, media, grids;
     std::vector<std::unique_ptr<Mirror>> gridData;
     DScene ds{};
     xrtg_scene_info info{};
@@ -120,7 +120,7 @@ namespace {
 
 int uploadAll(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
     for (Mirror* m : all) {
         if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
@@ -213,11 +213,14 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     if (int rc = s->prims.alloc(sizeof(float4) * 4 * size_t(std::max(nPrims, 1)))) return rc;
     if (int rc = s->trisId.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
     if (int rc = s->tris.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = s->ftris.alloc(sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = s->ftrisId.alloc(sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
     if (int rc = s->spheres.alloc(sizeof(float4) * 2 * size_t(std::max(nSph, 1)))) return rc;
     if (int rc = s->boxes.alloc(sizeof(float4) * 2 * size_t(std::max(nBox, 1)))) return rc;
     std::memset(s->prims.h, 0, s->prims.bytes);
     float4* prims = static_cast<float4*>(s->prims.h);
     float4* trisId = static_cast<float4*>(s->trisId.h);
+    float4* ftrisId = static_cast<float4*>(s->ftrisId.h);
     float4* sph = static_cast<float4*>(s->spheres.h);
     float4* box = static_cast<float4*>(s->boxes.h);
     std::vector<float> buildTris(size_t(nMeshTris) * 9);
@@ -249,6 +252,23 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
                 trisId[3 * ti] = f4(t.v0, asF(id));
                 trisId[3 * ti + 1] = f4(e1, asF(int(o.area_light >= 0 ? 1 : 0)));
                 trisId[3 * ti + 2] = f4(e2, 0.f);
+                {
+                    // plane-equation record of the throughput instantiation (wavefront.cuh: triangleRecord), built in double:
+                    // N = e1 x e2, d = N.v0 ; u = n1.P + d1 with n1 = (e2 x N)/|N|^2 ; v = n2.P + d2 with n2 = (N x e1)/|N|^2
+                    const double E1[3] = {double(t.v1[0]) - t.v0[0], double(t.v1[1]) - t.v0[1], double(t.v1[2]) - t.v0[2]};
+                    const double E2[3] = {double(t.v2[0]) - t.v0[0], double(t.v2[1]) - t.v0[1], double(t.v2[2]) - t.v0[2]};
+                    const double N[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
+                    const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+                    const double n1[3] = {(E2[1] * N[2] - E2[2] * N[1]) / nn, (E2[2] * N[0] - E2[0] * N[2]) / nn, (E2[0] * N[1] - E2[1] * N[0]) / nn};
+                    const double n2[3] = {(N[1] * E1[2] - N[2] * E1[1]) / nn, (N[2] * E1[0] - N[0] * E1[2]) / nn, (N[0] * E1[1] - N[1] * E1[0]) / nn};
+                    const double dN = N[0] * t.v0[0] + N[1] * t.v0[1] + N[2] * t.v0[2];
+                    const double d1 = -(n1[0] * t.v0[0] + n1[1] * t.v0[1] + n1[2] * t.v0[2]);
+                    const double d2 = -(n2[0] * t.v0[0] + n2[1] * t.v0[1] + n2[2] * t.v0[2]);
+                    ftrisId[4 * ti] = make_float4(float(N[0]), float(N[1]), float(N[2]), float(dN));
+                    ftrisId[4 * ti + 1] = make_float4(float(n1[0]), float(n1[1]), float(n1[2]), float(d1));
+                    ftrisId[4 * ti + 2] = make_float4(float(n2[0]), float(n2[1]), float(n2[2]), float(d2));
+                    ftrisId[4 * ti + 3] = make_float4(asF(id), asF(int(o.area_light >= 0 ? 1 : 0)), 0.f, 0.f);
+                }
                 prims[4 * id] = f4(t.n0, ng[0]);
                 prims[4 * id + 1] = f4(t.n1, ng[1]);
                 prims[4 * id + 2] = f4(t.n2, ng[2]);
@@ -284,15 +304,18 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         // mirrored back into the pinned host copies (xrtg_scene_upload re-sends them)
         if (int rc = s->nodes.alloc(sizeof(BvhNode) * size_t(nMeshTris - 1))) return rc;
         CU(cudaMemcpyAsync(s->trisId.d, s->trisId.h, s->trisId.bytes, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->ftrisId.d, s->ftrisId.h, s->ftrisId.bytes, cudaMemcpyHostToDevice, s->stream));
         LbvhInfo li;
         CU(cudaStreamSynchronize(s->stream));
         Timer tbv;
         const cudaError_t e = buildLbvhDevice(static_cast<const float4*>(s->trisId.d), uint32_t(nMeshTris), static_cast<float4*>(s->tris.d),
-                                              static_cast<BvhNode*>(s->nodes.d), s->stream, &li);
+                                              static_cast<BvhNode*>(s->nodes.d), s->stream, &li, static_cast<const float4*>(s->ftrisId.d),
+                                              static_cast<float4*>(s->ftris.d));
         if (e != cudaSuccess) return fail(XRTG_ERR_CUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e));
         if (li.depth <= 60) { // deeper than the traversal stacks allow (pathological duplicates): fall back to the host SAH build
             CU(cudaMemcpyAsync(s->nodes.h, s->nodes.d, s->nodes.bytes, cudaMemcpyDeviceToHost, s->stream));
             CU(cudaMemcpyAsync(s->tris.h, s->tris.d, s->tris.bytes, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaMemcpyAsync(s->ftris.h, s->ftris.d, s->ftris.bytes, cudaMemcpyDeviceToHost, s->stream));
             CU(cudaStreamSynchronize(s->stream));
             bvh.depth = li.depth; bvh.pad = li.pad; bvh.sahCost = 0.f;
             bvh.nodes.resize(size_t(li.nNodes)); // size bookkeeping only
@@ -315,6 +338,9 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             tris[3 * k + 1] = trisId[3 * src + 1];
             tris[3 * k + 2] = trisId[3 * src + 2];
         }
+        float4* ftris = static_cast<float4*>(s->ftris.h);
+        for (size_t k = 0; k < bvh.triOrder.size(); ++k)
+            std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(bvh.triOrder[k]), 4 * sizeof(float4));
     }
     // ---- lights, media, grids ----
     if (int rc = s->lights.alloc(sizeof(DLight) * size_t(std::max(d->n_area_lights, 1)))) return rc;
@@ -382,6 +408,8 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     ds.nodes = static_cast<const float4*>(s->nodes.d);
     ds.tris = static_cast<const float4*>(s->tris.d);
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
+    ds.ftris = static_cast<const float4*>(s->ftris.d);
+    ds.ftris_id = static_cast<const float4*>(s->ftrisId.d);
     ds.prims = static_cast<const float4*>(s->prims.d);
     ds.spheres = static_cast<const float4*>(s->spheres.d);
     ds.boxes = static_cast<const float4*>(s->boxes.d);

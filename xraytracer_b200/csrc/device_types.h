@@ -48,6 +48,10 @@ struct DScene {
     const float4* nodes;   // 4 float4 per BVH node (bvh.h: BvhNode)
     const float4* tris;    // 3 float4 per triangle in LEAF order: v0|prim id, e1|flags(bit0 emitter), e2|0
     const float4* tris_id; // same triangles in PRIMITIVE-ID order (brute-force parity path), mesh triangles only
+    // throughput instantiation only: 4 float4 per triangle = plane-equation form (N|d, n1|d1, n2|d2, id|flags|0|0), see
+    // triangleRecord() in wavefront.cuh; leaf order / primitive-id order like tris / tris_id
+    const float4* ftris;
+    const float4* ftris_id;
     const float4* prims;   // 4 float4 per primitive id: shading record
                            //   tri:    n0|ng.x  n1|ng.y  n2|ng.z  albedo|meta
                            //   sphere: centre|radius  -  -  albedo|meta          box: -  -  -  0|meta

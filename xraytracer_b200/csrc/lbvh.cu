@@ -175,14 +175,13 @@ __global__ void k_emit(int n, const uint32_t* __restrict__ order, const float4* 
     out[i] = nd;
 }
 
-__global__ void k_gather_tris(const float4* __restrict__ trisId, const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ tris)
+__global__ void k_gather_tris(const float4* __restrict__ trisId, const uint32_t* __restrict__ order, uint32_t n, float4* __restrict__ tris,
+                              int f4PerTri)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t src = order[i];
-    tris[3 * size_t(i)] = trisId[3 * size_t(src)];
-    tris[3 * size_t(i) + 1] = trisId[3 * size_t(src) + 1];
-    tris[3 * size_t(i) + 2] = trisId[3 * size_t(src) + 2];
+    for (int k = 0; k < f4PerTri; ++k) tris[size_t(f4PerTri) * i + k] = trisId[size_t(f4PerTri) * src + k];
 }
 
 #define LB(call)                                       \
@@ -193,7 +192,8 @@ __global__ void k_gather_tris(const float4* __restrict__ trisId, const uint32_t*
 
 } // namespace
 
-cudaError_t buildLbvhDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeafOrder, BvhNode* dNodes, cudaStream_t st, LbvhInfo* info)
+cudaError_t buildLbvhDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeafOrder, BvhNode* dNodes, cudaStream_t st, LbvhInfo* info,
+                            const float4* dFastId, float4* dFastLeafOrder)
 {
     // n >= 2 (the caller handles 0 and 1 triangles with the host builder)
     void* bufs[16] = {};
@@ -236,7 +236,8 @@ cudaError_t buildLbvhDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeaf
     for (int a = 0; a < 6; ++a) mag = fmaxf(mag, fabsf(dec(hb[a])));
     const float pad = fmaxf(mag * (1.f / 32768.f), 1e-30f);
     k_emit<<<grid, kB, 0, st>>>(int(n), vals2, triLo, triHi, children, nodeLo, nodeHi, pad, dNodes);
-    k_gather_tris<<<grid, kB, 0, st>>>(dTrisId, vals2, n, dTrisLeafOrder);
+    k_gather_tris<<<grid, kB, 0, st>>>(dTrisId, vals2, n, dTrisLeafOrder, 3);
+    if (dFastId && dFastLeafOrder) k_gather_tris<<<grid, kB, 0, st>>>(dFastId, vals2, n, dFastLeafOrder, 4);
     int hdepth = 0;
     LB(cudaMemcpyAsync(&hdepth, depth, sizeof(int), cudaMemcpyDeviceToHost, st));
     LB(cudaStreamSynchronize(st));

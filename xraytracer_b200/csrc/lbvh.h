@@ -14,6 +14,8 @@ struct LbvhInfo {
 
 // dTrisId: n triangles (3 float4 each: v0|id, e1|flags, e2|0) in primitive-id order, resident on the device.
 // Writes n-1 BvhNode records (root = node 0) and the leaf-ordered triangle array. Requires n >= 2.
-cudaError_t buildLbvhDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeafOrder, BvhNode* dNodes, cudaStream_t st, LbvhInfo* info);
+// dFastId / dFastLeafOrder (optional): the 4-float4 plane-equation records, gathered into leaf order the same way.
+cudaError_t buildLbvhDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeafOrder, BvhNode* dNodes, cudaStream_t st, LbvhInfo* info,
+                            const float4* dFastId = nullptr, float4* dFastLeafOrder = nullptr);
 
 } // namespace xrt

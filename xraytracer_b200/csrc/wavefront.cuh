@@ -205,6 +205,57 @@ __device__ __forceinline__ bool rayTriangle(V3 orig, V3 dir, V3 v0, V3 e1, V3 e2
     return t > FLT_EPSILON;
 }
 
+struct Hit {
+    float t, u, v;
+    int prim;
+};
+
+// Closest-hit candidate rule that reproduces "first strictly smaller t in primitive order wins"
+// (scene.cpp:193-197, primitive.cpp:100) under an arbitrary visiting order: lower t, or equal t and lower id.
+__device__ __forceinline__ void consider(Hit& h, float t, float u, float v, int id)
+{
+    if (t < h.t || (t == h.t && id < h.prim)) { h.t = t; h.u = u; h.v = v; h.prim = id; }
+}
+
+// One triangle record against one ray. ANY=false: closest-hit candidate (ids > minId only) folded into `h`; ANY=true:
+// returns true if the triangle (not an emitter proxy) occludes the ray before h.t.
+//   exact instantiation : 3 float4 (v0|id, e1|flags, e2|0) and the reference's Moeller-Trumbore, bit for bit.
+//   fast instantiation  : 4 float4 in plane-equation form (Havel & Herout 2010): N = e1 x e2, d = N.v0 give t = (d - N.o)/(N.dir);
+//                         two affine functions of the hit point give the barycentrics, u = n1.P + d1, v = n2.P + d2 with
+//                         n1 = (e2 x N)/|N|^2, n2 = (N x e1)/|N|^2. ~25 instructions instead of ~42; the same acceptance rules
+//                         (|det| >= FLT_EPSILON with det = N.dir = -MT's det, u,v >= 0, u+v <= 1, t > FLT_EPSILON). It is an
+//                         independent Monte-Carlo path anyway; parity lives in the exact instantiation.
+constexpr int kTriF4 = kExact ? 3 : 4;
+__device__ __forceinline__ const float4* triArray(const DScene& sc, bool idOrder)
+{
+    if constexpr (kExact) return idOrder ? sc.tris_id : sc.tris;
+    else return idOrder ? sc.ftris_id : sc.ftris;
+}
+template <bool ANY, bool LDG>
+__device__ __forceinline__ bool triangleRecord(const float4* __restrict__ rec, V3 o, V3 d, Hit& h, int minId)
+{
+    const float4 q0 = LDG ? __ldg(rec) : rec[0], q1 = LDG ? __ldg(rec + 1) : rec[1], q2 = LDG ? __ldg(rec + 2) : rec[2];
+    if constexpr (kExact) {
+        const int id = __float_as_int(q0.w);
+        float t, u, v;
+        if (ANY) return (__float_as_int(q1.w) & 1) == 0 && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < h.t;
+        if (id > minId && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(h, t, u, v, id);
+        return false;
+    }
+    else {
+        const float det = dot(xyz(q0), d);
+        const float t = (q0.w - dot(o, xyz(q0))) * (1.0f / det);
+        const V3 P = o + t * d;
+        const float u = dot(P, xyz(q1)) + q1.w, v = dot(P, xyz(q2)) + q2.w;
+        const bool ok = !(fabsf(det) < FLT_EPSILON) && u >= 0.f && v >= 0.f && u + v <= 1.f && t > FLT_EPSILON;
+        if (!ok) return false;
+        const int4 m = LDG ? __ldg(reinterpret_cast<const int4*>(rec + 3)) : *reinterpret_cast<const int4*>(rec + 3);
+        if (ANY) return (m.y & 1) == 0 && t < h.t;
+        if (m.x > minId) consider(h, t, u, v, m.x);
+        return false;
+    }
+}
+
 // Sphere::doIntersect / solveQuadratic (primitive.h:133-177); the -0.5 literals and the unqualified sqrt() make
 // the root computation double precision in the reference.
 __device__ __forceinline__ bool sphereT(float4 cr, V3 orig, V3 dir, float& tNear)
@@ -247,18 +298,6 @@ __device__ __forceinline__ bool boxSlabs(V3 pmin, V3 pmax, V3 o, V3 d, float& t0
     return true;
 }
 
-struct Hit {
-    float t, u, v;
-    int prim;
-};
-
-// Closest-hit candidate rule that reproduces "first strictly smaller t in primitive order wins"
-// (scene.cpp:193-197, primitive.cpp:100) under an arbitrary visiting order: lower t, or equal t and lower id.
-__device__ __forceinline__ void consider(Hit& h, float t, float u, float v, int id)
-{
-    if (t < h.t || (t == h.t && id < h.prim)) { h.t = t; h.u = u; h.v = v; h.prim = id; }
-}
-
 struct TraceCounters {
     uint32_t nodes = 0, tris = 0;
 };
@@ -298,7 +337,7 @@ __device__ __forceinline__ bool traverse(const DScene& sc, V3 o, V3 d, Hit& h, i
     int sp = 0;
     int node = 0; // root
     const float4* __restrict__ nodes = sc.nodes;
-    const float4* __restrict__ tris = sc.tris;
+    const float4* __restrict__ tris = triArray(sc, false);
     while (true) {
         // ---- inner nodes ----
         const float4 n0 = __ldg(nodes + 4 * node), n1 = __ldg(nodes + 4 * node + 1), n2 = __ldg(nodes + 4 * node + 2);
@@ -322,14 +361,8 @@ __device__ __forceinline__ bool traverse(const DScene& sc, V3 o, V3 d, Hit& h, i
             if (!act) continue;
             if (k > 0) {
                 for (int i = 0; i < k; ++i) {
-                    const float4 q0 = __ldg(tris + 3 * (c + i)), q1 = __ldg(tris + 3 * (c + i) + 1), q2 = __ldg(tris + 3 * (c + i) + 2);
                     if (COUNT) tc.tris++;
-                    const int id = __float_as_int(q0.w);
-                    float t, u, v;
-                    if (ANY) {
-                        if ((__float_as_int(q1.w) & 1) == 0 && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < h.t) return true;
-                    }
-                    else if (id > minId && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(h, t, u, v, id);
+                    if (triangleRecord<ANY, true>(tris + kTriF4 * (c + i), o, d, h, minId)) return true;
                 }
             }
             else if (next < 0) next = c;
@@ -351,15 +384,9 @@ __device__ __forceinline__ bool traverse(const DScene& sc, V3 o, V3 d, Hit& h, i
 template <bool ANY>
 __device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, int minId)
 {
-    for (int i = 0; i < sc.nBruteTris; ++i) {
-        const float4 q0 = __ldg(sc.tris_id + 3 * i), q1 = __ldg(sc.tris_id + 3 * i + 1), q2 = __ldg(sc.tris_id + 3 * i + 2);
-        const int id = __float_as_int(q0.w);
-        float t, u, v;
-        if (ANY) {
-            if ((__float_as_int(q1.w) & 1) == 0 && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < h.t) return true;
-        }
-        else if (id > minId && rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(h, t, u, v, id);
-    }
+    const float4* __restrict__ tris = triArray(sc, true);
+    for (int i = 0; i < sc.nBruteTris; ++i)
+        if (triangleRecord<ANY, true>(tris + kTriF4 * i, o, d, h, minId)) return true;
     return false;
 }
 
@@ -374,23 +401,39 @@ template <bool ANY>
 __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, int n, V3 o, V3 d, Hit& h, int minId)
 {
     bool occluded = false;
+    if constexpr (kExact) {
 #pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-        const float4 q0 = st[3 * i], q1 = st[3 * i + 1], q2 = st[3 * i + 2];
-        const V3 v0 = xyz(q0), e1 = xyz(q1), e2 = xyz(q2);
-        const V3 pvec = cross(d, e2);
-        const float det = dot(e1, pvec);
-        const float invDet = 1 / det;
-        const V3 tvec = o - v0;
-        const float u = dot(tvec, pvec) * invDet;
-        const V3 qvec = cross(tvec, e1);
-        const float v = dot(d, qvec) * invDet;
-        const float t = dot(e2, qvec) * invDet;
-        const bool ok = !(fabsf(det) < FLT_EPSILON) && !(u < 0 || u > 1) && !(v < 0 || u + v > 1) && (t > FLT_EPSILON);
-        if (ANY) occluded = occluded || (ok && (__float_as_int(q1.w) & 1) == 0 && t < h.t);
-        else {
-            const int id = __float_as_int(q0.w);
-            if (ok && id > minId) consider(h, t, u, v, id);
+        for (int i = 0; i < n; ++i) {
+            const float4 q0 = st[3 * i], q1 = st[3 * i + 1], q2 = st[3 * i + 2];
+            const V3 v0 = xyz(q0), e1 = xyz(q1), e2 = xyz(q2);
+            const V3 pvec = cross(d, e2);
+            const float det = dot(e1, pvec);
+            const float invDet = 1 / det;
+            const V3 tvec = o - v0;
+            const float u = dot(tvec, pvec) * invDet;
+            const V3 qvec = cross(tvec, e1);
+            const float v = dot(d, qvec) * invDet;
+            const float t = dot(e2, qvec) * invDet;
+            const bool ok = !(fabsf(det) < FLT_EPSILON) && !(u < 0 || u > 1) && !(v < 0 || u + v > 1) && (t > FLT_EPSILON);
+            if (ANY) occluded = occluded || (ok && (__float_as_int(q1.w) & 1) == 0 && t < h.t);
+            else {
+                const int id = __float_as_int(q0.w);
+                if (ok && id > minId) consider(h, t, u, v, id);
+            }
+        }
+    }
+    else {
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) {
+            const float4 q0 = st[4 * i], q1 = st[4 * i + 1], q2 = st[4 * i + 2];
+            const int4 m = *reinterpret_cast<const int4*>(st + 4 * i + 3);
+            const float det = dot(xyz(q0), d);
+            const float t = (q0.w - dot(o, xyz(q0))) * (1.0f / det);
+            const V3 P = o + t * d;
+            const float u = dot(P, xyz(q1)) + q1.w, v = dot(P, xyz(q2)) + q2.w;
+            const bool ok = !(fabsf(det) < FLT_EPSILON) && u >= 0.f && v >= 0.f && u + v <= 1.f && t > FLT_EPSILON;
+            if (ANY) occluded = occluded || (ok && (m.y & 1) == 0 && t < h.t);
+            else if (ok && m.x > minId) consider(h, t, u, v, m.x);
         }
     }
     return occluded;
@@ -602,16 +645,10 @@ __device__ __forceinline__ bool traverseStep(const DScene& sc, RayState& r, int*
     if (r.node < 0) {
         const int code = ~r.node;
         const int first = code >> 2, cnt = (code & 3) + 1;
-        const float4* __restrict__ tris = sc.tris;
+        const float4* __restrict__ tris = triArray(sc, false);
         for (int i = 0; i < cnt; ++i) {
-            const float4 q0 = __ldg(tris + 3 * (first + i)), q1 = __ldg(tris + 3 * (first + i) + 1), q2 = __ldg(tris + 3 * (first + i) + 2);
             if (COUNT) tc.tris++;
-            const int id = __float_as_int(q0.w);
-            float t, u, v;
-            if (ANY) {
-                if ((__float_as_int(q1.w) & 1) == 0 && rayTriangle(r.o, r.d, xyz(q0), xyz(q1), xyz(q2), t, u, v) && t < r.h.t) return true;
-            }
-            else if (id > r.minId && rayTriangle(r.o, r.d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(r.h, t, u, v, id);
+            if (triangleRecord<ANY, true>(tris + kTriF4 * (first + i), r.o, r.d, r.h, r.minId)) return true;
         }
         r.node = stackPop(sstack, lstack, r.sp);
     }
@@ -772,10 +809,10 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend_simple(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
-    __shared__ float4 s_tris[3 * kSmallSceneTris];
+    __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
     const float4* smallTris = nullptr;
     if (brute == 2 && sc.nBruteTris <= kSmallSceneTris) { // small-scene mode: stage every triangle once per CTA
-        for (int k = threadIdx.x; k < 3 * sc.nBruteTris; k += blockDim.x) s_tris[k] = sc.tris_id[k];
+        for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = triArray(sc, true)[k];
         __syncthreads();
         smallTris = s_tris;
     }
@@ -800,10 +837,10 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q, int bounce, int brute, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
-    __shared__ float4 s_tris[3 * kSmallSceneTris];
+    __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
     const float4* smallTris = nullptr;
     if (brute == 2 && sc.nBruteTris <= kSmallSceneTris) {
-        for (int k = threadIdx.x; k < 3 * sc.nBruteTris; k += blockDim.x) s_tris[k] = sc.tris_id[k];
+        for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = triArray(sc, true)[k];
         __syncthreads();
         smallTris = s_tris;
     }

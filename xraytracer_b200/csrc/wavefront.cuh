@@ -4,13 +4,14 @@
 //   kernels_exact.cu  XRT_EXACT=1, compiled with -fmad=false : reproduces the reference's arithmetic (no FMA
 //                     contraction, IEEE div/sqrt, same operation order) and its per-pixel std::mt19937 sample
 //                     stream (renderer.cpp:35-36, sampler.h:48-49). One sample per pixel per wave.
-//   kernels_fast.cu   XRT_EXACT=0, FMA allowed : counter-based Philox4x32-7 keyed (seed,pixel)/(sample,block),
-//                     several samples per pixel per wave.
+//   kernels_fast.cu   XRT_EXACT=0, -use_fast_math : counter-based Philox4x32-7 keyed (seed,pixel)/(sample,block), several
+//                     samples per pixel per wave, plane-equation triangle records instead of Moeller-Trumbore.
 //
-// Pipeline per wave (all kernels are persistent: grid = k x 148 SMs, warps fetch 32 queue entries at a time
-// through an atomic cursor, queue sizes live in device memory so no host round trip is needed):
-//   raygen  -> [ extend (closest hit, SAH BVH) -> shade (Le, RR, NEE sample, BSDF sample; warp-ballot
-//   compaction into the next ray queue and the shadow queue) -> connect (any hit) ] x bounces -> accumulate
+// Pipeline per wave (queue sizes live in device memory, so a wave is enqueued without a host round trip):
+//   shallow BVH:  primary (raygen fused with the bounce-0 closest hit, compact hit-only queue)
+//   deep BVH:     raygen -> trace<closest> (resumable traversal with warp refill)
+//   then per bounce: shade (Le, RR, NEE sample of every light, BSDF sample; CTA-aggregated appends into the next ray queue
+//   and the shadow queue) -> connect (any hit) -> extend (closest hit of the next bounce) ... -> accumulate
 //
 // Reference citations (paths relative to /root/reference/Src) are on each device function.
 #pragma once
@@ -28,7 +29,7 @@ namespace xrt {
 namespace XRT_NS {
 
 constexpr bool kExact = (XRT_EXACT != 0);
-constexpr int kBlock = 128;          // threads per CTA for every kernel
+constexpr int kBlock = 128;          // threads per CTA of the traversal kernels (the surface shade kernel uses kShadeBlock)
 constexpr int kStackSmem = 24;       // traversal stack entries kept in shared memory per thread
 constexpr int kStackLocal = 40;      // overflow entries (local memory); builder depth limit is 56
 constexpr float kPI = 3.14159265359; // geometry.h:10
@@ -492,14 +493,6 @@ __device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax,
 // persistent-kernel helpers
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31u; }
-
-// warp grabs 32 consecutive work items
-__device__ __forceinline__ uint32_t fetch32(uint32_t* cursor)
-{
-    uint32_t base = 0;
-    if (laneId() == 0) base = atomicAdd(cursor, 32u);
-    return __shfl_sync(0xffffffffu, base, 0);
-}
 
 // warp-aggregated append: returns the slot for this lane if `want`, one atomic per warp
 __device__ __forceinline__ uint32_t warpAppend(uint32_t* counter, bool want)
@@ -1576,17 +1569,7 @@ __global__ void __launch_bounds__(kBlock) k_finalize(const float* __restrict__ a
 // ---------------------------------------------------------------------------------------------------------
 // host-side launchers (called from api.cpp through the table in kernels.h)
 // ---------------------------------------------------------------------------------------------------------
-struct LaunchCfg {
-    int sms = 0;
-    int persistentBlocks(const void* fn, int block)
-    {
-        int perSm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, block, 0);
-        if (perSm < 1) perSm = 1;
-        return sms * perSm;
-    }
-};
-
+// persistent grids: (resident CTAs per SM for this kernel) x (number of SMs) — 148 on B200
 inline int gridFor(const void* fn, int block = kBlock)
 {
     static thread_local int cachedDev = -1;
@@ -1597,9 +1580,9 @@ inline int gridFor(const void* fn, int block = kBlock)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cachedDev = dev;
     }
-    LaunchCfg c;
-    c.sms = sms;
-    return c.persistentBlocks(fn, block);
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, block, 0);
+    return sms * (perSm < 1 ? 1 : perSm);
 }
 
 inline void launchSeedMt(cudaStream_t st, const DWave& w)

@@ -287,6 +287,12 @@ int xrtg_trace_primary(xrtg_scene* scene, const xrtg_camera* cam, int width, int
 int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float* dir, const float* tmax,
                     int any_hit, uint32_t flags, xrtg_hit* out_hits);
 
+/* Host-only structural check of the SAH BVH builder (no CUDA device needed): builds the tree over n triangles (9 floats each:
+ * v0 v1 v2) and verifies that every triangle is referenced by exactly one leaf, that every child box (minus the conservative
+ * padding) contains its subtree, that leaves hold at most max_leaf triangles and that the depth fits the traversal stacks.
+ * Returns 0 if the tree is valid, a negative xrtg_status otherwise; the out parameters may be NULL. */
+int xrtg_bvh_selftest(const float* tris9, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost);
+
 /* Image post of the reference's Image class on the device (image.h:80-136): optional gammaCorrection — pow(x, 1/gamma) per
  * channel (image.h:80-90), gamma <= 0 skips it — followed by the 8-bit quantisation shared by writePPM and writeMat,
  * clamp(uint32(255*x), 0, 255), written RGB (PPM order, bgr = 0) or BGR (cv::Mat order, bgr = 1). rgb_host = W*H*3 floats,

@@ -118,7 +118,7 @@ BUILD_LBVH_GPU = 1
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_create2", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
-               "xrtg_trace_rays", "xrtg_image_to_u8"]
+               "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest"]
 
 GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
 HOST_LIB = PKG / "host" / "libxrthost.so"
@@ -159,6 +159,7 @@ def gpu():
     lib.xrtg_trace_primary.argtypes = [VP, P(Camera), C.c_int, C.c_int, C.c_int, VP, C.c_uint32, VP]
     lib.xrtg_trace_rays.argtypes = [VP, C.c_int64, VP, VP, VP, C.c_int, C.c_uint32, VP]
     lib.xrtg_image_to_u8.argtypes = [C.c_int, VP, C.c_int, C.c_int, C.c_float, C.c_int, VP]
+    lib.xrtg_bvh_selftest.argtypes = [VP, C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(C.c_float)]
     lib._typed = True
     return lib
 

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -326,7 +327,10 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     }
     if (!builtOnGpu) {
         Timer tbv;
-        buildBvh(buildTris.data(), uint32_t(nMeshTris), 4, bvh);
+        // at most 4 triangles per leaf (the leaf code of k_trace holds count-1 in 2 bits); XRT_MAX_LEAF overrides for experiments
+        const char* ml = std::getenv("XRT_MAX_LEAF");
+        const int maxLeaf = ml ? std::min(4, std::max(1, std::atoi(ml))) : 4;
+        buildBvh(buildTris.data(), uint32_t(nMeshTris), maxLeaf, bvh);
         s->info.bvh_build_ms = tbv.ms();
         s->info.bvh_builder = 0;
         if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
@@ -702,6 +706,65 @@ __global__ void k_image_to_u8(const float* __restrict__ rgb, unsigned char* __re
 }
 
 extern "C" {
+
+int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost)
+{
+    if (n < 0 || (n > 0 && !tri) || max_leaf < 1 || max_leaf > 4) return fail(XRTG_ERR_INVALID, "bad selftest arguments");
+    Bvh bvh;
+    buildBvh(tri, uint32_t(n), max_leaf, bvh);
+    if (n_nodes) *n_nodes = int(bvh.nodes.size());
+    if (depth) *depth = bvh.depth;
+    if (sah_cost) *sah_cost = bvh.sahCost;
+    if (n == 0) return 0;
+    if (bvh.triOrder.size() != size_t(n)) return fail(XRTG_ERR_INVALID, "selftest: triOrder has the wrong size");
+    if (bvh.depth > 60) return fail(XRTG_ERR_INVALID, "selftest: tree deeper than the traversal stacks");
+    std::vector<int> seen(size_t(n), 0);
+    struct Range { float lo[3], hi[3]; };
+    // recursive descent: returns the exact bounds of the subtree and checks them against the (padded) box stored in the parent
+    std::string err;
+    std::vector<std::pair<int, int>> stack; // (node, slot) handled iteratively through an explicit post-order
+    std::function<bool(int, int, Range&)> visit = [&](int child, int count, Range& out) -> bool {
+        for (int a = 0; a < 3; ++a) { out.lo[a] = FLT_MAX; out.hi[a] = -FLT_MAX; }
+        if (count > 0) { // leaf
+            if (count > max_leaf) { err = "selftest: leaf larger than max_leaf"; return false; }
+            for (int k = 0; k < count; ++k) {
+                const uint32_t t = bvh.triOrder[size_t(child) + k];
+                if (t >= uint32_t(n)) { err = "selftest: triangle index out of range"; return false; }
+                seen[t]++;
+                for (int v = 0; v < 3; ++v)
+                    for (int a = 0; a < 3; ++a) {
+                        out.lo[a] = std::min(out.lo[a], tri[9 * size_t(t) + 3 * v + a]);
+                        out.hi[a] = std::max(out.hi[a], tri[9 * size_t(t) + 3 * v + a]);
+                    }
+            }
+            return true;
+        }
+        if (child < 0 || size_t(child) >= bvh.nodes.size()) { err = "selftest: node index out of range"; return false; }
+        const BvhNode& nd = bvh.nodes[size_t(child)];
+        const int cs[2] = {nd.child0, nd.child1}, ks[2] = {nd.count0, nd.count1};
+        const float* los[2] = {nd.lo0, nd.lo1};
+        const float* his[2] = {nd.hi0, nd.hi1};
+        for (int s2 = 0; s2 < 2; ++s2) {
+            if (ks[s2] < 0) continue; // empty slot
+            Range r;
+            if (!visit(cs[s2], ks[s2], r)) return false;
+            for (int a = 0; a < 3; ++a) {
+                if (!(los[s2][a] <= r.lo[a] - 0.5f * bvh.pad) || !(his[s2][a] >= r.hi[a] + 0.5f * bvh.pad)) {
+                    err = "selftest: child box does not contain its subtree with the conservative padding";
+                    return false;
+                }
+                out.lo[a] = std::min(out.lo[a], r.lo[a]);
+                out.hi[a] = std::max(out.hi[a], r.hi[a]);
+            }
+        }
+        return true;
+    };
+    Range all;
+    if (!visit(0, 0, all)) return fail(XRTG_ERR_INVALID, err);
+    for (int t = 0; t < n; ++t)
+        if (seen[size_t(t)] != 1) return fail(XRTG_ERR_INVALID, "selftest: a triangle is referenced " + std::to_string(seen[size_t(t)]) + " times");
+    return 0;
+}
 
 int xrtg_image_to_u8(int device, const float* rgb_host, int width, int height, float gamma, int bgr, uint8_t* out_host)
 {

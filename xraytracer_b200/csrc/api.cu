@@ -621,11 +621,26 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         // Deep BVHs: separate raygen + the refillable traversal kernel, which is faster there even on primary rays.
         // No bounce at all (maxDepth 0): only the per-path radiance has to be cleared.
         const bool fusedPrimary = !deep && nIter > 0;
+        // Small scenes under the ray-tracing surface integrators: per bounce ONE kernel (k_bounce_small) instead of shade ->
+        // connect -> extend; see wavefront.cuh.
+        const bool fusedBounce = fusedPrimary && small && !brute && bruteSecondary && bruteShadow && envInt("XRT_FUSED_BOUNCE", 1) != 0 &&
+                                 (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
         if (nIter == 0) CU(cudaMemsetAsync(q.radiance, 0, sizeof(float4) * size_t(w.nPaths), st));
         else if (!fusedPrimary) { K.raygen(st, dc, q, w, nullptr); ++launches; }
         tm.end();
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
+            if (fusedBounce) { // small scene: primary, then one fused shade + connect + extend kernel per bounce
+                if (b == 0) {
+                    tm.begin(kStageExtend);
+                    K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
+                    tm.end();
+                }
+                tm.begin(kStageShade);
+                K.bounceSmall(st, s->ds, q, w, src, b, dstats); ++launches; ++nShade;
+                tm.end();
+                continue;
+            }
             tm.begin(kStageExtend);
             if (b == 0 && fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats);
             else K.extend(st, s->ds, q, src, b, brute ? 1 : ((bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? thrExt0 : thrExt, spv);

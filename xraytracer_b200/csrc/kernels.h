@@ -15,6 +15,8 @@ struct KernelTable {
     void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, int brute, bool count, unsigned long long* stats,
                     int refillThreshold, int stepsPerVote);
     void (*shadeSurface)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce);
+    // small scenes: shade + connect + extend of one bounce in one kernel (k_bounce_small)
+    void (*bounceSmall)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, unsigned long long* stats);
     void (*shadeVolume)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, bool brute, bool count,
                         unsigned long long* stats);
     void (*accumulate)(cudaStream_t, const DQueues&, const DWave&, float* accum, unsigned long long* stats);

@@ -443,7 +443,7 @@ __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, in
 // Scene::intersect (scene.cpp:190-200) for one ray: boxes first (the LAST box hit in object order overwrites
 // whatever came before it, primitive.h:259-261; objects after it win only with a strictly smaller t), then
 // triangles through the BVH, then analytic spheres. Box hits return t1 in h.u.
-template <bool COUNT>
+template <bool COUNT, bool SMALL = false>
 __device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool brute, Hit& h, int* sstack, TraceCounters& tc,
                                            const float4* smallTris = nullptr)
 {
@@ -455,7 +455,7 @@ __device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool br
         if (boxSlabs(xyz(bl), xyz(bh), o, d, t0, t1)) { h.t = t0; h.u = t1; h.v = 0.f; h.prim = __float_as_int(bl.w); minId = h.prim; }
     }
     if (sc.nTris > 0) {
-        if (smallTris) smallSceneTris<false>(smallTris, sc.nBruteTris, o, d, h, minId);
+        if (SMALL || smallTris) smallSceneTris<false>(smallTris, sc.nBruteTris, o, d, h, minId);
         else if (brute) bruteTris<false>(sc, o, d, h, minId);
         else traverse<false, COUNT>(sc, o, d, h, minId, sstack, tc);
     }
@@ -469,7 +469,7 @@ __device__ __forceinline__ void closestHit(const DScene& sc, V3 o, V3 d, bool br
 }
 
 // Scene::occluded (scene.cpp:202-211): BoxMesh::occluded is always true (primitive.h:266-268)
-template <bool COUNT>
+template <bool COUNT, bool SMALL = false>
 __device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax, bool brute, int* sstack, TraceCounters& tc,
                                        const float4* smallTris = nullptr)
 {
@@ -477,7 +477,7 @@ __device__ __forceinline__ bool anyHit(const DScene& sc, V3 o, V3 d, float tmax,
     Hit h;
     h.t = tmax; h.prim = 0x7fffffff; h.u = h.v = 0.f;
     if (sc.nTris > 0) {
-        if (smallTris) { if (smallSceneTris<true>(smallTris, sc.nBruteTris, o, d, h, -1)) return true; }
+        if (SMALL || smallTris) { if (smallSceneTris<true>(smallTris, sc.nBruteTris, o, d, h, -1)) return true; }
         else if (brute ? bruteTris<true>(sc, o, d, h, -1) : traverse<true, COUNT>(sc, o, d, h, -1, sstack, tc)) return true;
     }
     for (int s = 0; s < sc.nSpheres; ++s) {
@@ -1234,6 +1234,155 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Small scenes (<= kSmallSceneTris triangles — every scene the reference ships): ONE kernel per bounce that shades the hit,
+// traces the NEE shadow rays, samples the BSDF, traces the next closest hit and applies the NEXT depth's Russian roulette and
+// emitter test, all against the triangle list in shared memory. Only paths that go on to shade at depth+1 are appended
+// (ray + hit record, one atomic per CTA per 128 paths), so every lane that enters the kernel does useful work in every phase:
+// the shadow queue, the separate connect / extend launches, the hit-record round trip and the radiance atomics of the
+// three-kernel pipeline disappear (per path and bounce: 64 B in, <= 64 B out, one 16 B radiance read-modify-write).
+// The per-path draw order is the reference's: [RR] -> light samples -> BSDF sample (integrator.h:223-283); the RR draw of
+// depth+1 simply happens at the end of depth's kernel. Hit records are double-buffered (q.hits / q.s0) because CTAs append
+// to bounce b+1 while others still read bounce b.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4* hitBuffer(const DQueues& q, int bounce) { return (bounce & 1) ? q.s0 : q.hits; }
+
+__global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
+{
+    __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
+    __shared__ uint32_t s_scratch[kBlock / 32 + 1];
+    for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = triArray(sc, true)[k];
+    __syncthreads();
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    uint32_t* nextCount = ctrl + kCtrlStride + kCtrlRays;
+    const float4* __restrict__ hitsIn = hitBuffer(q, bounce);
+    float4* __restrict__ hitsOut = hitBuffer(q, bounce + 1);
+    // (ternaries instead of q.q0[src]: a dynamic index would force a local-memory copy of the kernel parameter)
+    const float4* __restrict__ in0 = src ? q.q0[1] : q.q0[0];
+    const float4* __restrict__ in1 = src ? q.q1[1] : q.q1[0];
+    const float4* __restrict__ in2 = src ? q.q2[1] : q.q2[0];
+    float4* __restrict__ out0 = src ? q.q0[0] : q.q0[1];
+    float4* __restrict__ out1 = src ? q.q1[0] : q.q1[1];
+    float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
+    const int kind = w.integrator;
+    uint32_t nClosest = 0, nShadow = 0;
+    TraceCounters tc;
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
+        const uint32_t i = tile * kBlock + threadIdx.x;
+        bool wantNext = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        Hit nh{FLT_MAX, 0.f, 0.f, -1};
+        uint32_t pid = 0, ctr = 0;
+        int depth = 0;
+        if (i < n) {
+            const float4 hv = hitsIn[i], r0 = in0[i], r1 = in1[i], r2 = in2[i];
+            const V3 o = xyz(r0), d = xyz(r1);
+            const V3 T = mk(r0.w, r1.w, r2.x);
+            pid = uint32_t(__float_as_int(r2.y));
+            depth = __float_as_int(r2.z);
+            float4 rad = q.radiance[pid];
+            bool radDirty = false;
+            auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; radDirty = true; };
+            const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+            Rng rng;
+            rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+            Surf s;
+            makeSurf(sc, o, d, h, s);
+            bool shadeLights = false, shadeDelta = false, bsdf = false;
+            if (kind == XRTG_INT_DIRECT) {
+                if (lightOf(s) >= 0) add(emitted(sc, s, d));
+                else shadeLights = true;
+            }
+            else if (kind == XRTG_INT_WHITTED) shadeDelta = hasMaterial(s);
+            else { // Indirect / GI. Entries of bounce > 0 already passed RR and the emitter test in the kernel that traced them.
+                bool alive = true;
+                if (bounce == 0 && lightOf(s) >= 0) { add(T * emitted(sc, s, d)); alive = false; }
+                shadeLights = alive && kind == XRTG_INT_GI;
+                bsdf = alive;
+            }
+            // ---- NEE over EVERY area light (integrator.h:95-108, :250-267), shadow ray traced inline ----
+            if (kind == XRTG_INT_DIRECT || kind == XRTG_INT_GI) {
+                for (int li = 0; li < sc.nLights; ++li) {
+                    bool want = false;
+                    V3 wi = mk(0.f), c = mk(0.f);
+                    float tmax = 0.f;
+                    if (shadeLights) {
+                        float pdf = 0.0f;
+                        const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                        if (pdf != 0) {
+                            const float cs = smax(0.0f, dot(s.ng, wi));
+                            const V3 fr = evalBxDF(s);
+                            c = T * (fr * Lr * cs / pdf);
+                            want = true;
+                        }
+                    }
+                    if (want) {
+                        const float bias = 0.01f;
+                        ++nShadow;
+                        if (!anyHit<false, true>(sc, s.pos + s.ng * bias, wi, tmax - bias, false, nullptr, tc, s_tris)) add(c);
+                    }
+                }
+            }
+            // ---- Whitted diffuse term over delta lights (integrator.h:328-343; light.cpp:120-142) ----
+            if (kind == XRTG_INT_WHITTED && shadeDelta) {
+                for (int li = 0; li < sc.nDelta; ++li) {
+                    const DDelta L = sc.dlights[li];
+                    V3 wi;
+                    float pdf, tmax;
+                    if (__float_as_int(L.p_kind.w) == XRTG_DLIGHT_POINT) {
+                        const V3 ld = xyz(L.p_kind) - s.pos;
+                        const float dist = length(ld);
+                        wi = ld / dist; pdf = dist * dist; tmax = dist;
+                    }
+                    else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
+                    const V3 c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
+                    ++nShadow;
+                    if (!anyHit<false, true>(sc, s.pos + s.ng * float(0.1), wi, tmax, false, nullptr, tc, s_tris)) add(c);
+                }
+            }
+            // ---- BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----
+            if (bsdf) {
+                float pdf = 1.0f;
+                V3 nextDir = mk(0.f);
+                const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+                const float cs = smax(.0f, dot(nextDir, s.ng));
+                nT = T * (fr * cs / pdf);
+                no = s.pos + s.ng * 0.01f;
+                nd = nextDir;
+                if (depth + 1 < w.maxDepth) {
+                    ++nClosest;
+                    closestHit<false, true>(sc, no, nd, false, nh, nullptr, tc, s_tris);
+                    if (nh.prim >= 0) {
+                        const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
+                        if (!(rng.next() >= p)) {
+                            nT = nT / mk(p);
+                            const uint32_t meta = __float_as_uint(__ldg(sc.prims + 4 * nh.prim + 3).w);
+                            if (((meta >> kMetaLightShift) & 0xfffu) == 0) wantNext = true;
+                            else if (kind == XRTG_INT_INDIRECT) { // Le at any depth (integrator.h:150-160); GI only at depth 0
+                                Surf s2;
+                                makeSurf(sc, no, nd, nh, s2);
+                                add(nT * emitted(sc, s2, nd));
+                            }
+                        }
+                    }
+                }
+            }
+            ctr = rng.close();
+            if (radDirty) q.radiance[pid] = rad;
+        }
+        const uint32_t slot = blockAppend<kBlock / 32>(nextCount, wantNext, s_scratch);
+        if (wantNext) {
+            out0[slot] = make_float4(no.x, no.y, no.z, nT.x);
+            out1[slot] = make_float4(nd.x, nd.y, nd.z, nT.y);
+            out2[slot] = make_float4(nT.z, __int_as_float(int(pid)), __int_as_float(depth + 1), __int_as_float(int(ctr)));
+            hitsOut[slot] = make_float4(nh.t, nh.u, nh.v, __int_as_float(nh.prim));
+        }
+    }
+    statAdd(stats, kStatClosest, nClosest);
+    statAdd(stats, kStatShadow, nShadow);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // participating media (medium.h, medium.cpp) — used by the volume shade kernel
 // ---------------------------------------------------------------------------------------------------------
 
@@ -1646,6 +1795,12 @@ inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues&
     static thread_local int grid = 0;
     if (!grid) grid = gridFor((const void*)k_shade_surface, kShadeBlock);
     k_shade_surface<<<grid, kShadeBlock, 0, st>>>(sc, q, w, src, bounce);
+}
+inline void launchBounceSmall(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, unsigned long long* stats)
+{
+    static thread_local int grid = 0;
+    if (!grid) grid = gridFor((const void*)k_bounce_small);
+    k_bounce_small<<<grid, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
 }
 inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, bool brute, bool count,
                               unsigned long long* stats)

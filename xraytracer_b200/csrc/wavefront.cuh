@@ -245,10 +245,11 @@ __device__ __forceinline__ bool triangleRecord(const float4* __restrict__ rec, V
     }
     else {
         const float det = dot(xyz(q0), d);
-        const float t = (q0.w - dot(o, xyz(q0))) * (1.0f / det);
+        const float t = fmaf(-o.x, q0.x, fmaf(-o.y, q0.y, fmaf(-o.z, q0.z, q0.w))) * (1.0f / det);
         const V3 P = o + t * d;
-        const float u = dot(P, xyz(q1)) + q1.w, v = dot(P, xyz(q2)) + q2.w;
-        const bool ok = !(fabsf(det) < FLT_EPSILON) && u >= 0.f && v >= 0.f && u + v <= 1.f && t > FLT_EPSILON;
+        const float u = fmaf(P.x, q1.x, fmaf(P.y, q1.y, fmaf(P.z, q1.z, q1.w)));
+        const float v = fmaf(P.x, q2.x, fmaf(P.y, q2.y, fmaf(P.z, q2.z, q2.w)));
+        const bool ok = fminf(fminf(u, v), 1.f - (u + v)) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON;
         if (!ok) return false;
         const int4 m = LDG ? __ldg(reinterpret_cast<const int4*>(rec + 3)) : *reinterpret_cast<const int4*>(rec + 3);
         if (ANY) return (m.y & 1) == 0 && t < h.t;
@@ -398,7 +399,7 @@ __device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, 
 // rayTriangle(), the rejections of primitive.cpp:153-167 folded into one predicate (a NaN anywhere ends in `t > eps`
 // being false, exactly like the reference's early returns).
 constexpr int kSmallSceneTris = 64;
-template <bool ANY>
+template <bool ANY, bool OCCLUDERS_ONLY = false>
 __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, int n, V3 o, V3 d, Hit& h, int minId)
 {
     bool occluded = false;
@@ -424,17 +425,63 @@ __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, in
         }
     }
     else {
+        // Plane-equation records (see triangleRecord). fma chains seeded with the plane offsets: 18 FP ops per triangle; the three
+        // barycentric conditions collapse into one FMNMX3. The list is in primitive-id order, so for the closest hit "strictly
+        // smaller t wins" IS the reference's first-wins rule (scene.cpp:193-197) — only (t, index) are carried through the loop and
+        // u, v, id are re-derived for the winner. Any-hit keeps the minimum valid t (branch-free) and compares once at the end.
+        if (ANY) {
+            float tmin = FLT_MAX;
 #pragma unroll 2
-        for (int i = 0; i < n; ++i) {
-            const float4 q0 = st[4 * i], q1 = st[4 * i + 1], q2 = st[4 * i + 2];
-            const int4 m = *reinterpret_cast<const int4*>(st + 4 * i + 3);
-            const float det = dot(xyz(q0), d);
-            const float t = (q0.w - dot(o, xyz(q0))) * (1.0f / det);
-            const V3 P = o + t * d;
-            const float u = dot(P, xyz(q1)) + q1.w, v = dot(P, xyz(q2)) + q2.w;
-            const bool ok = !(fabsf(det) < FLT_EPSILON) && u >= 0.f && v >= 0.f && u + v <= 1.f && t > FLT_EPSILON;
-            if (ANY) occluded = occluded || (ok && (m.y & 1) == 0 && t < h.t);
-            else if (ok && m.x > minId) consider(h, t, u, v, m.x);
+            for (int i = 0; i < n; ++i) {
+                const float4 q0 = st[4 * i], q1 = st[4 * i + 1], q2 = st[4 * i + 2];
+                const float det = dot(xyz(q0), d);
+                const float t = fmaf(-o.x, q0.x, fmaf(-o.y, q0.y, fmaf(-o.z, q0.z, q0.w))) * (1.0f / det);
+                const V3 P = o + t * d;
+                const float u = fmaf(P.x, q1.x, fmaf(P.y, q1.y, fmaf(P.z, q1.z, q1.w)));
+                const float v = fmaf(P.x, q2.x, fmaf(P.y, q2.y, fmaf(P.z, q2.z, q2.w)));
+                bool ok = fminf(fminf(u, v), 1.f - (u + v)) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON;
+                if (!OCCLUDERS_ONLY) ok = ok && (__float_as_int(st[4 * i + 3].y) & 1) == 0;
+                tmin = fminf(tmin, ok ? t : FLT_MAX);
+            }
+            occluded = tmin < h.t;
+        }
+        else {
+            float best = h.t;
+            int bi = -1;
+            if (minId < 0) {
+#pragma unroll 2
+                for (int i = 0; i < n; ++i) {
+                    const float4 q0 = st[4 * i], q1 = st[4 * i + 1], q2 = st[4 * i + 2];
+                    const float det = dot(xyz(q0), d);
+                    const float t = fmaf(-o.x, q0.x, fmaf(-o.y, q0.y, fmaf(-o.z, q0.z, q0.w))) * (1.0f / det);
+                    const V3 P = o + t * d;
+                    const float u = fmaf(P.x, q1.x, fmaf(P.y, q1.y, fmaf(P.z, q1.z, q1.w)));
+                    const float v = fmaf(P.x, q2.x, fmaf(P.y, q2.y, fmaf(P.z, q2.z, q2.w)));
+                    const bool ok = fminf(fminf(u, v), 1.f - (u + v)) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < best;
+                    if (ok) { best = t; bi = i; }
+                }
+            }
+            else { // a BoxMesh hit came first: only primitives after it in object order may replace it (primitive.h:259-261)
+                for (int i = 0; i < n; ++i) {
+                    const float4 q0 = st[4 * i], q1 = st[4 * i + 1], q2 = st[4 * i + 2];
+                    const int id = __float_as_int(st[4 * i + 3].x);
+                    const float det = dot(xyz(q0), d);
+                    const float t = fmaf(-o.x, q0.x, fmaf(-o.y, q0.y, fmaf(-o.z, q0.z, q0.w))) * (1.0f / det);
+                    const V3 P = o + t * d;
+                    const float u = fmaf(P.x, q1.x, fmaf(P.y, q1.y, fmaf(P.z, q1.z, q1.w)));
+                    const float v = fmaf(P.x, q2.x, fmaf(P.y, q2.y, fmaf(P.z, q2.z, q2.w)));
+                    const bool ok = fminf(fminf(u, v), 1.f - (u + v)) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < best;
+                    if (ok && id > minId) { best = t; bi = i; }
+                }
+            }
+            if (bi >= 0) {
+                const float4 q1 = st[4 * bi + 1], q2 = st[4 * bi + 2];
+                const V3 P = o + best * d;
+                h.t = best;
+                h.u = fmaf(P.x, q1.x, fmaf(P.y, q1.y, fmaf(P.z, q1.z, q1.w)));
+                h.v = fmaf(P.x, q2.x, fmaf(P.y, q2.y, fmaf(P.z, q2.z, q2.w)));
+                h.prim = __float_as_int(st[4 * bi + 3].x);
+            }
         }
     }
     return occluded;
@@ -1244,14 +1291,55 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
 // depth+1 simply happens at the end of depth's kernel. Hit records are double-buffered (q.hits / q.s0) because CTAs append
 // to bounce b+1 while others still read bounce b.
 // ---------------------------------------------------------------------------------------------------------
+// Stages the scene's triangle list (primitive-id order) in shared memory; the throughput instantiation also builds the list of
+// OCCLUDERS (everything that is not an emitter proxy, scene.cpp:206) so the shadow loop carries no per-triangle flag test.
+__device__ __forceinline__ void stageSmallScene(const DScene& sc, float4* s_tris, float4* s_occ, int* s_nOcc)
+{
+    const float4* __restrict__ src = triArray(sc, true);
+    for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = src[k];
+    if constexpr (kExact) { if (threadIdx.x == 0) *s_nOcc = sc.nBruteTris; }
+    else if (threadIdx.x < 32) { // warp 0: order-preserving compaction, 32 triangles per round
+        int nOcc = 0;
+        for (int base = 0; base < sc.nBruteTris; base += 32) {
+            const int i = base + int(threadIdx.x);
+            const bool keep = i < sc.nBruteTris && (__float_as_int(src[4 * i + 3].y) & 1) == 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int slot = nOcc + __popc(m & ((1u << threadIdx.x) - 1u));
+                for (int k = 0; k < 4; ++k) s_occ[4 * slot + k] = src[4 * i + k];
+            }
+            nOcc += __popc(m);
+        }
+        if (threadIdx.x == 0) *s_nOcc = nOcc;
+    }
+    __syncthreads();
+}
+// Scene::occluded (scene.cpp:202-211) on a staged small scene
+__device__ __forceinline__ bool anyHitSmall(const DScene& sc, V3 o, V3 d, float tmax, const float4* occTris, int nOcc)
+{
+    if (sc.nBoxes > 0) return true; // BoxMesh::occluded is always true (primitive.h:266-268)
+    Hit h;
+    h.t = tmax; h.prim = 0x7fffffff; h.u = h.v = 0.f;
+    if (smallSceneTris<true, !kExact>(occTris, nOcc, o, d, h, -1)) return true;
+    for (int s = 0; s < sc.nSpheres; ++s) {
+        const float4 cr = __ldg(sc.spheres + 2 * s);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * s + 1));
+        float t;
+        if (meta.y == 0 && sphereT(cr, o, d, t) && t < tmax) return true;
+    }
+    return false;
+}
 __device__ __forceinline__ float4* hitBuffer(const DQueues& q, int bounce) { return (bounce & 1) ? q.s0 : q.hits; }
 
 __global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
 {
     __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
+    __shared__ float4 s_occ[kExact ? 1 : kTriF4 * kSmallSceneTris];
     __shared__ uint32_t s_scratch[kBlock / 32 + 1];
-    for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = triArray(sc, true)[k];
-    __syncthreads();
+    __shared__ int s_nOcc;
+    stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
+    const float4* occTris = kExact ? s_tris : s_occ;
+    const int nOcc = s_nOcc;
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     uint32_t* nextCount = ctrl + kCtrlStride + kCtrlRays;
@@ -1319,7 +1407,7 @@ __global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, D
                     if (want) {
                         const float bias = 0.01f;
                         ++nShadow;
-                        if (!anyHit<false, true>(sc, s.pos + s.ng * bias, wi, tmax - bias, false, nullptr, tc, s_tris)) add(c);
+                        if (!anyHitSmall(sc, s.pos + s.ng * bias, wi, tmax - bias, occTris, nOcc)) add(c);
                     }
                 }
             }
@@ -1337,7 +1425,7 @@ __global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, D
                     else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
                     const V3 c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
                     ++nShadow;
-                    if (!anyHit<false, true>(sc, s.pos + s.ng * float(0.1), wi, tmax, false, nullptr, tc, s_tris)) add(c);
+                    if (!anyHitSmall(sc, s.pos + s.ng * float(0.1), wi, tmax, occTris, nOcc)) add(c);
                 }
             }
             // ---- BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----

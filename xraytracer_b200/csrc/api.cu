@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <xrtgpu.h>
 #include "bvh.h"
+#include "small_scene.h"
 #include "device_types.h"
 #include "kernels.h"
 #include "lbvh.h"
@@ -94,7 +95,7 @@ struct xrtg_scene {
     int device = 0;
     cudaStream_t stream = nullptr; // uploads + host-buffer renders
     // scene arrays (pinned host copy + device copy)
-    Mirror nodes, tris, trisId, ftris, ftrisId, prims, spheres, boxes, lights, dlights, media, grids;
+    Mirror nodes, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
     std::vector<std::unique_ptr<Mirror>> gridData;
     DScene ds{};
     xrtg_scene_info info{};
@@ -121,7 +122,7 @@ namespace {
 
 int uploadAll(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
     for (Mirror* m : all) {
         if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
@@ -346,6 +347,16 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         for (size_t k = 0; k < bvh.triOrder.size(); ++k)
             std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(bvh.triOrder[k]), 4 * sizeof(float4));
     }
+    // ---- small scenes: plane-grouped triangle block for k_bounce_small (small_scene.h) ----
+    int smallBlockF4 = 0;
+    if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
+        std::vector<float> block;
+        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, nullptr)) {
+            if (int rc = s->smallBlock.alloc(block.size() * sizeof(float))) return rc;
+            std::memcpy(s->smallBlock.h, block.data(), s->smallBlock.bytes);
+            smallBlockF4 = int(block.size() / 4);
+        }
+    }
     // ---- lights, media, grids ----
     if (int rc = s->lights.alloc(sizeof(DLight) * size_t(std::max(d->n_area_lights, 1)))) return rc;
     DLight* L = static_cast<DLight*>(s->lights.h);
@@ -414,6 +425,8 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
     ds.ftris = static_cast<const float4*>(s->ftris.d);
     ds.ftris_id = static_cast<const float4*>(s->ftrisId.d);
+    ds.smallBlock = static_cast<const float4*>(s->smallBlock.d);
+    ds.smallBlockF4 = smallBlockF4;
     ds.prims = static_cast<const float4*>(s->prims.d);
     ds.spheres = static_cast<const float4*>(s->spheres.d);
     ds.boxes = static_cast<const float4*>(s->boxes.d);
@@ -583,6 +596,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     DWave w{};
     w.width = p->width; w.height = p->height; w.nPixels = nPixels;
     w.integrator = integ; w.maxDepth = p->max_depth; w.seed = p->seed;
+    w.flags = 0;
     w.mt = static_cast<uint32_t*>(s->mt.p);
     w.mti = static_cast<uint32_t*>(s->mti.p);
 

@@ -52,6 +52,8 @@ struct DScene {
     // triangleRecord() in wavefront.cuh; leaf order / primitive-id order like tris / tris_id
     const float4* ftris;
     const float4* ftris_id;
+    const float4* smallBlock; // plane-paired triangles of a small scene (small_scene.h) or nullptr
+    int smallBlockF4;         // its size in float4 (0 = not available)
     const float4* prims;   // 4 float4 per primitive id: shading record
                            //   tri:    n0|ng.x  n1|ng.y  n2|ng.z  albedo|meta
                            //   sphere: centre|radius  -  -  albedo|meta          box: -  -  -  0|meta
@@ -94,6 +96,7 @@ struct DWave {
     uint32_t samplesThisWave;
     int integrator, maxDepth;
     uint32_t seed;
+    uint32_t flags;         // development switches (none at present)
     // exact mode: per-pixel mt19937 state, word-major [624][nPixels], and the per-pixel cursor
     uint32_t* mt;
     uint32_t* mti;

@@ -1,0 +1,31 @@
+// small_scene.h — plane-grouped triangle block for scenes of at most 64 triangles (host side, see small_scene.cpp).
+//
+// Coplanar triangles (the two halves of every OBJ quad, the Cornell floor with both block footprints) are tested in PAIRS that
+// share ONE ray/plane intersection; each triangle then costs only its two barycentric plane equations. The block is copied
+// verbatim into shared memory by k_bounce_small (wavefront.cuh) — layout in float4 units:
+//   [0]            int4 (offAll, offOcc, totalF4, 0)
+//   section:       int4 (nRecords, 0, offRecords, offIds)          offsets from the start of the block
+//                  5 float4 per record:  N.xyz | d ,  n1.xyz | d1 , n2.xyz | d2  (triangle A) ,  n1 | d1 , n2 | d2  (triangle B)
+//                                        an unpaired triangle gets a B that no point is inside of (0 | -1 , 0 | -1)
+//                  2 ints per record:    primitive ids of A and B (-1 for padding)
+// Records of one plane are consecutive, carry bit-identical plane words and are in primitive-id order, so "strictly smaller t
+// wins" between records and "A before B" inside one reproduce the reference's first-wins rule for coplanar duplicates.
+// `All` holds every mesh triangle (closest hit), `Occ` only the triangles that are not emitter proxies (Scene::occluded skips
+// those, scene.cpp:206).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace xrt {
+
+constexpr int kSmallBlockMaxF4 = 704; // shared-memory budget of the kernel (11 KB)
+
+struct SmallBlockInfo {
+    int nRecordsAll = 0, nRecordsOcc = 0, nPlanesAll = 0;
+};
+
+// ftrisId: 4 floats x 4 per triangle (N|d, n1|d1, n2|d2, id|flags) in primitive-id order. Returns false (block left empty) when
+// grouping does not pay (fewer than 4 triangles saved) or the block would not fit.
+bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info);
+
+} // namespace xrt

@@ -17,6 +17,7 @@
 #pragma once
 #include <cfloat>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "device_types.h"
 #include <xrtgpu.h>
@@ -399,6 +400,7 @@ __device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, 
 // rayTriangle(), the rejections of primitive.cpp:153-167 folded into one predicate (a NaN anywhere ends in `t > eps`
 // being false, exactly like the reference's early returns).
 constexpr int kSmallSceneTris = 64;
+constexpr int kSmallBlockF4 = 704; // = kSmallBlockMaxF4 (small_scene.h)
 template <bool ANY, bool OCCLUDERS_ONLY = false>
 __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, int n, V3 o, V3 d, Hit& h, int minId)
 {
@@ -1331,15 +1333,131 @@ __device__ __forceinline__ bool anyHitSmall(const DScene& sc, V3 o, V3 d, float 
 }
 __device__ __forceinline__ float4* hitBuffer(const DQueues& q, int bounce) { return (bounce & 1) ? q.s0 : q.hits; }
 
-__global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
+// Plane-paired small scene (small_scene.h), throughput instantiation: one record = one supporting plane + two triangles in it;
+// one ray/plane intersection and two barycentric plane equations per triangle. Branch-free per lane.
+struct SmallSection {
+    const float4* recs; // 5 per record: N|d , A: n1|d1 , n2|d2 , B: n1|d1 , n2|d2
+    const int* ids;     // 2 per record
+    int nRecords;
+};
+__device__ __forceinline__ SmallSection smallSection(const float4* blk, int off)
 {
-    __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
-    __shared__ float4 s_occ[kExact ? 1 : kTriF4 * kSmallSceneTris];
+    const int4 h = *reinterpret_cast<const int4*>(blk + off);
+    return SmallSection{blk + h.z, reinterpret_cast<const int*>(blk + h.w), h.x};
+}
+__device__ __forceinline__ float insideness(const float4 a, const float4 b, V3 P)
+{
+    const float u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
+    const float v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
+    return fminf(fminf(u, v), 1.f - (u + v)); // >= 0 <=> u >= 0, v >= 0, u + v <= 1
+}
+// Any hit with eps < t < tmax among the occluders; lanes without a shadow ray pass tmax < 0. Must be called by all 32 lanes of
+// a converged warp: a plane that no lane can hit (behind every ray or beyond every tmax — the floor and the ceiling for every
+// shadow ray towards the Cornell light) is skipped with one vote.
+__device__ __forceinline__ bool groupedAnyHit(const SmallSection& S, V3 o, V3 d, float tmax)
+{
+    float acc = -1.f;
+    for (int r = 0; r < S.nRecords; ++r) {
+        const float4* rec = S.recs + 5 * r;
+        const float4 pl = rec[0];
+        const float det = dot(xyz(pl), d);
+        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
+        const bool vt = !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < tmax;
+        if (!__any_sync(0xffffffffu, vt)) continue;
+        const V3 P = o + t * d;
+        const float m = fmaxf(insideness(rec[1], rec[2], P), insideness(rec[3], rec[4], P));
+        acc = fmaxf(acc, vt ? m : -1.f);
+    }
+    return acc >= 0.f;
+}
+// Closest hit: strictly smaller t wins between records, A before B inside one (scene.cpp:193-197); lanes without a ray pass
+// want = false.
+__device__ __forceinline__ void groupedClosest(const SmallSection& S, V3 o, V3 d, bool want, Hit& h)
+{
+    float best = want ? FLT_MAX : -1.f;
+    int bi = -1;
+#pragma unroll 2
+    for (int r = 0; r < S.nRecords; ++r) {
+        const float4* rec = S.recs + 5 * r;
+        const float4 pl = rec[0];
+        const float det = dot(xyz(pl), d);
+        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
+        const V3 P = o + t * d;
+        const float m0 = insideness(rec[1], rec[2], P), m1 = insideness(rec[3], rec[4], P);
+        const bool take = fmaxf(m0, m1) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < best;
+        best = take ? t : best;
+        bi = take ? (m0 >= 0.f ? 2 * r : 2 * r + 1) : bi;
+    }
+    if (bi >= 0) {
+        const float4* rec = S.recs + 5 * (bi >> 1) + 1 + 2 * (bi & 1);
+        const float4 a = rec[0], b = rec[1];
+        const V3 P = o + best * d;
+        h.t = best;
+        h.u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
+        h.v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
+        h.prim = S.ids[bi];
+    }
+}
+
+// GROUPED: the scene carries a plane-paired block (throughput instantiation, no BoxMesh); otherwise the per-triangle lists.
+template <bool GROUPED>
+__global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
+{
+    constexpr int kListF4 = GROUPED ? 1 : kTriF4 * kSmallSceneTris;
+    __shared__ float4 s_tris[kListF4];
+    __shared__ float4 s_occ[(kExact || GROUPED) ? 1 : kTriF4 * kSmallSceneTris];
+    __shared__ float4 s_block[GROUPED ? kSmallBlockF4 : 1];
     __shared__ uint32_t s_scratch[kBlock / 32 + 1];
     __shared__ int s_nOcc;
-    stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
-    const float4* occTris = kExact ? s_tris : s_occ;
-    const int nOcc = s_nOcc;
+    SmallSection secAll{}, secOcc{};
+    const float4* occTris = nullptr;
+    int nOcc = 0;
+    if constexpr (GROUPED) {
+        for (int k = threadIdx.x; k < sc.smallBlockF4; k += blockDim.x) s_block[k] = sc.smallBlock[k];
+        __syncthreads();
+        const int4 hd = *reinterpret_cast<const int4*>(s_block);
+        secAll = smallSection(s_block, hd.x);
+        secOcc = smallSection(s_block, hd.y);
+    }
+    else {
+        stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
+        occTris = kExact ? s_tris : s_occ;
+        nOcc = s_nOcc;
+    }
+    // Scene::occluded / Scene::intersect on the staged scene. GROUPED: executed by the whole (converged) warp.
+    auto occluded = [&](bool want, V3 o, V3 d, float tmax) -> bool {
+        if constexpr (GROUPED) {
+            bool occ = groupedAnyHit(secOcc, o, d, want ? tmax : -1.f);
+            if (want && !occ)
+                for (int k = 0; k < sc.nSpheres; ++k) {
+                    const float4 cr = __ldg(sc.spheres + 2 * k);
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1));
+                    float t;
+                    if (meta.y == 0 && sphereT(cr, o, d, t) && t < tmax) { occ = true; break; }
+                }
+            return occ;
+        }
+        else return want && anyHitSmall(sc, o, d, tmax, occTris, nOcc);
+    };
+    auto closest = [&](bool want, V3 o, V3 d, Hit& h) {
+        if constexpr (GROUPED) {
+            h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
+            groupedClosest(secAll, o, d, want, h);
+            if (want)
+                for (int k = 0; k < sc.nSpheres; ++k) {
+                    const float4 cr = __ldg(sc.spheres + 2 * k);
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1));
+                    float t;
+                    if (sphereT(cr, o, d, t)) consider(h, t, 0.f, 0.f, meta.x);
+                }
+            if (h.prim == 0x7fffffff) h.prim = -1;
+        }
+        else if (want) {
+            TraceCounters tc;
+            closestHit<false, true>(sc, o, d, false, h, nullptr, tc, s_tris);
+        }
+    };
+
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     uint32_t* nextCount = ctrl + kCtrlStride + kCtrlRays;
@@ -1354,29 +1472,30 @@ __global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, D
     float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
     const int kind = w.integrator;
     uint32_t nClosest = 0, nShadow = 0;
-    TraceCounters tc;
     for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
         const uint32_t i = tile * kBlock + threadIdx.x;
-        bool wantNext = false;
-        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
-        Hit nh{FLT_MAX, 0.f, 0.f, -1};
+        const bool live = i < n;
+        // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
+        V3 d = mk(0.f), T = mk(0.f);
         uint32_t pid = 0, ctr = 0;
         int depth = 0;
-        if (i < n) {
+        float4 rad = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool radDirty = false;
+        auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; radDirty = true; };
+        Rng rng;
+        Surf s = {};
+        bool shadeLights = false, shadeDelta = false, bsdf = false;
+        if (live) {
             const float4 hv = hitsIn[i], r0 = in0[i], r1 = in1[i], r2 = in2[i];
-            const V3 o = xyz(r0), d = xyz(r1);
-            const V3 T = mk(r0.w, r1.w, r2.x);
+            const V3 o = xyz(r0);
+            d = xyz(r1);
+            T = mk(r0.w, r1.w, r2.x);
             pid = uint32_t(__float_as_int(r2.y));
             depth = __float_as_int(r2.z);
-            float4 rad = q.radiance[pid];
-            bool radDirty = false;
-            auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; radDirty = true; };
+            rad = q.radiance[pid];
             const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
-            Rng rng;
             rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
-            Surf s;
             makeSurf(sc, o, d, h, s);
-            bool shadeLights = false, shadeDelta = false, bsdf = false;
             if (kind == XRTG_INT_DIRECT) {
                 if (lightOf(s) >= 0) add(emitted(sc, s, d));
                 else shadeLights = true;
@@ -1388,73 +1507,80 @@ __global__ void __launch_bounds__(kBlock) k_bounce_small(DScene sc, DQueues q, D
                 shadeLights = alive && kind == XRTG_INT_GI;
                 bsdf = alive;
             }
-            // ---- NEE over EVERY area light (integrator.h:95-108, :250-267), shadow ray traced inline ----
-            if (kind == XRTG_INT_DIRECT || kind == XRTG_INT_GI) {
-                for (int li = 0; li < sc.nLights; ++li) {
-                    bool want = false;
-                    V3 wi = mk(0.f), c = mk(0.f);
-                    float tmax = 0.f;
-                    if (shadeLights) {
-                        float pdf = 0.0f;
-                        const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
-                        if (pdf != 0) {
-                            const float cs = smax(0.0f, dot(s.ng, wi));
-                            const V3 fr = evalBxDF(s);
-                            c = T * (fr * Lr * cs / pdf);
-                            want = true;
-                        }
-                    }
-                    if (want) {
-                        const float bias = 0.01f;
+        }
+        // ---- phase 2: NEE over EVERY area light (integrator.h:95-108, :250-267), shadow ray traced inline ----
+        if (kind == XRTG_INT_DIRECT || kind == XRTG_INT_GI) {
+            for (int li = 0; li < sc.nLights; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeLights) {
+                    float pdf = 0.0f;
+                    const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                    if (pdf != 0) {
+                        const float cs = smax(0.0f, dot(s.ng, wi));
+                        const V3 fr = evalBxDF(s);
+                        c = T * (fr * Lr * cs / pdf);
+                        want = true;
                         ++nShadow;
-                        if (!anyHitSmall(sc, s.pos + s.ng * bias, wi, tmax - bias, occTris, nOcc)) add(c);
                     }
                 }
+                const float bias = 0.01f;
+                if (!occluded(want, s.pos + s.ng * bias, wi, tmax - bias) && want) add(c);
             }
-            // ---- Whitted diffuse term over delta lights (integrator.h:328-343; light.cpp:120-142) ----
-            if (kind == XRTG_INT_WHITTED && shadeDelta) {
-                for (int li = 0; li < sc.nDelta; ++li) {
+        }
+        // ---- Whitted diffuse term over delta lights (integrator.h:328-343; light.cpp:120-142) ----
+        if (kind == XRTG_INT_WHITTED) {
+            for (int li = 0; li < sc.nDelta; ++li) {
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeDelta) {
                     const DDelta L = sc.dlights[li];
-                    V3 wi;
-                    float pdf, tmax;
+                    float pdf;
                     if (__float_as_int(L.p_kind.w) == XRTG_DLIGHT_POINT) {
                         const V3 ld = xyz(L.p_kind) - s.pos;
                         const float dist = length(ld);
                         wi = ld / dist; pdf = dist * dist; tmax = dist;
                     }
                     else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
-                    const V3 c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
+                    c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
                     ++nShadow;
-                    if (!anyHitSmall(sc, s.pos + s.ng * float(0.1), wi, tmax, occTris, nOcc)) add(c);
                 }
+                if (!occluded(shadeDelta, s.pos + s.ng * float(0.1), wi, tmax) && shadeDelta) add(c);
             }
-            // ---- BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----
-            if (bsdf) {
-                float pdf = 1.0f;
-                V3 nextDir = mk(0.f);
-                const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
-                const float cs = smax(.0f, dot(nextDir, s.ng));
-                nT = T * (fr * cs / pdf);
-                no = s.pos + s.ng * 0.01f;
-                nd = nextDir;
-                if (depth + 1 < w.maxDepth) {
-                    ++nClosest;
-                    closestHit<false, true>(sc, no, nd, false, nh, nullptr, tc, s_tris);
-                    if (nh.prim >= 0) {
-                        const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
-                        if (!(rng.next() >= p)) {
-                            nT = nT / mk(p);
-                            const uint32_t meta = __float_as_uint(__ldg(sc.prims + 4 * nh.prim + 3).w);
-                            if (((meta >> kMetaLightShift) & 0xfffu) == 0) wantNext = true;
-                            else if (kind == XRTG_INT_INDIRECT) { // Le at any depth (integrator.h:150-160); GI only at depth 0
-                                Surf s2;
-                                makeSurf(sc, no, nd, nh, s2);
-                                add(nT * emitted(sc, s2, nd));
-                            }
-                        }
+        }
+        // ---- phase 3: BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----
+        bool wantNext = false, trace = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        Hit nh{FLT_MAX, 0.f, 0.f, -1};
+        if (bsdf) {
+            float pdf = 1.0f;
+            V3 nextDir = mk(0.f);
+            const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+            const float cs = smax(.0f, dot(nextDir, s.ng));
+            nT = T * (fr * cs / pdf);
+            no = s.pos + s.ng * 0.01f;
+            nd = nextDir;
+            trace = depth + 1 < w.maxDepth;
+        }
+        if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) closest(trace, no, nd, nh);
+        if (trace) {
+            ++nClosest;
+            if (nh.prim >= 0) {
+                const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
+                if (!(rng.next() >= p)) {
+                    nT = nT / mk(p);
+                    const uint32_t meta = __float_as_uint(__ldg(sc.prims + 4 * nh.prim + 3).w);
+                    if (((meta >> kMetaLightShift) & 0xfffu) == 0) wantNext = true;
+                    else if (kind == XRTG_INT_INDIRECT) { // Le at any depth (integrator.h:150-160); GI only at depth 0
+                        Surf s2;
+                        makeSurf(sc, no, nd, nh, s2);
+                        add(nT * emitted(sc, s2, nd));
                     }
                 }
             }
+        }
+        if (live) {
             ctr = rng.close();
             if (radDirty) q.radiance[pid] = rad;
         }
@@ -1886,9 +2012,11 @@ inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues&
 }
 inline void launchBounceSmall(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, unsigned long long* stats)
 {
-    static thread_local int grid = 0;
-    if (!grid) grid = gridFor((const void*)k_bounce_small);
-    k_bounce_small<<<grid, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
+    static thread_local int g0 = 0, g1 = 0;
+    if (!g0) { g0 = gridFor((const void*)k_bounce_small<false>); g1 = gridFor((const void*)k_bounce_small<true>); }
+    const bool grouped = !kExact && sc.smallBlockF4 > 0 && sc.nBoxes == 0;
+    if (grouped) k_bounce_small<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
+    else k_bounce_small<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
 }
 inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, bool brute, bool count,
                               unsigned long long* stats)

@@ -289,11 +289,12 @@ def main():
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
     # aggregate ray counts over ranks
-    agg = np.zeros(9, dtype=np.float64)
+    agg = np.zeros(11, dtype=np.float64)
     for st in stats:
         if st:
             agg += np.array([st["closest_rays"], st["shadow_rays"], st["kernel_launches"], st["extend_ms"], st["shade_ms"],
-                             st["connect_ms"], st["extend_launches"], st["tracking_steps"], st["primary_hits"]], dtype=np.float64)
+                             st["connect_ms"], st["extend_launches"], st["tracking_steps"], st["primary_hits"],
+                             st["bounce_entries"], st["bounce_launches"]], dtype=np.float64)
     if world > 1:
         t = torch.tensor(agg, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -331,14 +332,6 @@ def main():
         samples = W * H * spp_total * args.steps
         value = samples / (ms * 1e-3) / 1e6
         rays = agg_all[0] + agg_all[1]
-        # ---- roofline of the dominant stage: closest-hit traversal, rank 0's launches ----
-        # (k_primary = ray generation fused with the bounce-0 hit on shallow BVHs, k_extend_simple / k_trace<closest> after)
-        # achieved  = COMPULSORY HBM bytes of those launches / their CUDA-event time:
-        #               fused primary launch : 16 B radiance init per path + 64 B (48 B ray + 16 B hit) per primary HIT
-        #               every other launch   : 32 B ray read + 16 B hit write per ray
-        #               + the BVH and triangle arrays once per launch.
-        #             BVH nodes / triangles re-fetched per ray are served by L1/L2, not HBM; they are reported separately
-        #             as `fetch` = rays x (64 B x nodes visited + 48 B x triangles tested) / time  (SURVEY §8(d)'s B_ray).
         peak, peak_src = measured_peak_hbm()
         n_cl = max(cst["closest_rays"], 1)
         nodes_per_ray = cst["nodes_visited"] / n_cl
@@ -346,30 +339,63 @@ def main():
         ext_ms, ext_launches, closest_r0 = agg[3], max(agg[6], 1), agg[0]
         bvh_bytes = 64.0 * info["n_bvh_nodes"] + 48.0 * info["n_triangles"]
         paths_r0 = float(W) * H * my_spp * args.steps
-        if agg[8] > 0:   # fused primary kernel in use
-            hbm_bytes = paths_r0 * 16.0 + agg[8] * 64.0 + (closest_r0 - paths_r0) * 48.0 + ext_launches * bvh_bytes
-        else:
-            hbm_bytes = closest_r0 * 48.0 + ext_launches * bvh_bytes
-        fetch_bytes = closest_r0 * (64.0 * nodes_per_ray + 48.0 * tris_per_ray)
-        achieved = hbm_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
         traffic = None
-        tp = ROOT / "profiles" / f"extend_traffic_{args.workload}.json"
+        # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, summarised by scripts/summarize_profiles.py)
+        tp = ROOT / "profiles" / (f"bounce_traffic_{args.workload}.json" if agg[9] > 0 else f"extend_traffic_{args.workload}.json")
         if tp.exists():
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "closest-hit stage (k_primary fused raygen+bounce 0, k_extend_simple / k_trace after)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": hbm_bytes / ext_launches,
-                    "bytes_per_ray_hbm": hbm_bytes / max(closest_r0, 1.0), "bvh_bytes": bvh_bytes,
-                    "fetch": {"achieved": fetch_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0, "unit": "GB/s",
-                              "level": "L1/L2 (BVH node + triangle fetches, 64 B and 48 B records)",
-                              "bytes_per_ray": 64.0 * nodes_per_ray + 48.0 * tris_per_ray,
-                              "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray},
-                    "launches": int(ext_launches), "avg_launch_ms": ext_ms / ext_launches,
-                    "share_of_step": {"extend": agg[3] / ms, "shade": agg[4] / ms, "connect": agg[5] / ms},
-                    "note": "node/triangle counters from an instrumented run (XRTG_FLAG_COUNTERS) of the same kernels on the same scene"}
+        share = {"extend": agg[3] / ms, "shade": agg[4] / ms, "connect": agg[5] / ms}
+        if agg[9] > 0:
+            # ---- small scene: the dominant kernel is k_bounce_small (shade + shadow rays + next closest hit + next RR fused) ----
+            # achieved = COMPULSORY HBM bytes of its launches / their CUDA-event time, rank 0:
+            #   per queue entry  : 64 B in (48 B ray/throughput/path word + 16 B hit record) + 16 B radiance read + 16 B radiance write
+            #   per survivor     : 64 B out (ray + hit record of the next bounce); survivors = entries of bounce >= 1 = entries - primary hits
+            # The triangles are read from shared memory (plane-paired block staged once per CTA), reported as `fetch`.
+            entries, launches_b, b_ms = agg[9], max(agg[10], 1), agg[4]
+            hbm_bytes = entries * 96.0 + (entries - agg[8]) * 64.0
+            achieved = hbm_bytes / (b_ms * 1e-3) / 1e9 if b_ms > 0 else 0.0
+            traced = (closest_r0 - paths_r0)      # closest-hit rays traced inside the bounce kernels
+            smem_bytes = 80.0 * (traced * info["small_records_all"] + agg[1] * info["small_records_occ"]) if info["small_records_all"] else \
+                64.0 * info["n_triangles"] * (traced + agg[1])
+            roofline = {"bound": "hbm", "kernel": "k_bounce_small (per bounce: shade + NEE shadow rays + next closest hit + next Russian roulette, fused)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": hbm_bytes / launches_b,
+                        "bytes_per_entry_hbm": hbm_bytes / max(entries, 1.0), "entries_per_launch": entries / launches_b,
+                        "fetch": {"achieved": smem_bytes / (b_ms * 1e-3) / 1e9 if b_ms > 0 else 0.0, "unit": "GB/s",
+                                  "level": "shared memory (every ray reads the whole plane-paired triangle block, 80 B per record; upper bound: "
+                                           "shadow rays skip planes no lane of the warp can reach)",
+                                  "records_closest": info["small_records_all"], "records_occluders": info["small_records_occ"]},
+                        "launches": int(launches_b), "avg_launch_ms": b_ms / launches_b, "share_of_step": share,
+                        "note": "instruction-issue bound (ncu: ~65 % issue-active at 31 of 32 lanes), not memory bound: a 36-triangle scene cannot "
+                                "saturate HBM; the fraction says how far the queue traffic is from the HBM roof"}
+        else:
+            # ---- deep BVH: roofline of the dominant stage, closest-hit traversal, rank 0's launches ----
+            # (k_primary = ray generation fused with the bounce-0 hit on shallow BVHs, k_extend_simple / k_trace<closest> after)
+            # achieved  = COMPULSORY HBM bytes of those launches / their CUDA-event time:
+            #               fused primary launch : 16 B radiance init per path + 64 B (48 B ray + 16 B hit) per primary HIT
+            #               every other launch   : 32 B ray read + 16 B hit write per ray
+            #               + the BVH and triangle arrays once per launch.
+            #             BVH nodes / triangles re-fetched per ray are served by L1/L2, not HBM; they are reported separately
+            #             as `fetch` = rays x (64 B x nodes visited + 48 B x triangles tested) / time  (SURVEY §8(d)'s B_ray).
+            if agg[8] > 0:   # fused primary kernel in use
+                hbm_bytes = paths_r0 * 16.0 + agg[8] * 64.0 + (closest_r0 - paths_r0) * 48.0 + ext_launches * bvh_bytes
+            else:
+                hbm_bytes = closest_r0 * 48.0 + ext_launches * bvh_bytes
+            fetch_bytes = closest_r0 * (64.0 * nodes_per_ray + 48.0 * tris_per_ray)
+            achieved = hbm_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": "closest-hit stage (k_primary fused raygen+bounce 0, k_extend_simple / k_trace after)", "achieved": achieved, "peak": peak,
+                        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": hbm_bytes / ext_launches,
+                        "bytes_per_ray_hbm": hbm_bytes / max(closest_r0, 1.0), "bvh_bytes": bvh_bytes,
+                        "fetch": {"achieved": fetch_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0, "unit": "GB/s",
+                                  "level": "L1/L2 (BVH node + triangle fetches, 64 B and 48 B records)",
+                                  "bytes_per_ray": 64.0 * nodes_per_ray + 48.0 * tris_per_ray,
+                                  "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray},
+                        "launches": int(ext_launches), "avg_launch_ms": ext_ms / ext_launches, "share_of_step": share,
+                        "note": "node/triangle counters from an instrumented run (XRTG_FLAG_COUNTERS) of the same kernels on the same scene"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             _, cpu = cpu_baseline(desc, cam, wl, integ_id)

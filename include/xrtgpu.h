@@ -226,6 +226,8 @@ typedef struct xrtg_stats {
     float other_ms;
     float h2d_ms, d2h_ms;
     uint64_t primary_hits;   /* primary rays that hit something = entries of the compact bounce-0 queue */
+    uint64_t bounce_entries; /* queue entries consumed by the fused per-bounce kernel of small scenes (0 = three-kernel pipeline) */
+    uint64_t bounce_launches;/* launches of that kernel (counted in shade_launches as well) */
 } xrtg_stats;
 
 /* Closest-hit record of the parity hooks. prim = global primitive id (-1 = miss). */
@@ -244,6 +246,8 @@ typedef struct xrtg_scene_info {
     uint64_t upload_bytes; /* bytes copied H2D by an upload    */
     float bvh_build_ms;    /* the BVH builder alone (host SAH, or the GPU LBVH kernels incl. their sort) */
     int32_t bvh_builder;   /* 0 = host binned SAH, 1 = GPU linear BVH                                    */
+    int32_t small_records_all, small_records_occ; /* plane-paired triangle records (80 B each) of a small scene's closest-hit /
+                                                     occluder sections; 0 = no block (per-triangle lists or BVH only)  */
 } xrtg_scene_info;
 
 int xrtg_abi_version(void);
@@ -292,6 +296,14 @@ int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float*
  * padding) contains its subtree, that leaves hold at most max_leaf triangles and that the depth fits the traversal stacks.
  * Returns 0 if the tree is valid, a negative xrtg_status otherwise; the out parameters may be NULL. */
 int xrtg_bvh_selftest(const float* tris9, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost);
+
+/* Host-only check of the plane-paired triangle block that scenes of at most 64 triangles are traced from (no CUDA device
+ * needed): builds the block over n triangles (9 floats each; emitter_flags[i] & 1 marks emitter proxies, may be NULL) and
+ * verifies that every triangle sits in exactly one record of the closest-hit section, every non-emitter in exactly one
+ * record of the occluder section, and that each record's plane and barycentric equations reproduce the triangle it came from.
+ * Returns 0 for a valid block, 1 if the scene has too few coplanar pairs for a block to pay (none is built, the per-triangle
+ * lists are used), a negative xrtg_status on an inconsistent block. Out parameters may be NULL. */
+int xrtg_small_scene_selftest(const float* tris9, const int* emitter_flags, int n, int* n_records_all, int* n_records_occ, int* n_planes);
 
 /* Image post of the reference's Image class on the device (image.h:80-136): optional gammaCorrection — pow(x, 1/gamma) per
  * channel (image.h:80-90), gamma <= 0 skips it — followed by the 8-bit quantisation shared by writePPM and writeMat,

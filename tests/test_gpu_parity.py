@@ -283,6 +283,37 @@ def test_fast_mode_is_deterministic_and_seed_dependent(gpu_cornell):
     assert not np.array_equal(bits(a), bits(c))
 
 
+# ---- small scenes: the fused per-bounce kernel against the three-kernel pipeline ----------------------------------------------
+
+@pytest.mark.parametrize("light,integ,depth,exact", [
+    ("quad", capi.INT_GI, 3, False), ("sphere", capi.INT_GI, 4, False), ("triangle", capi.INT_DIRECT, 1, False),
+    ("quad", capi.INT_INDIRECT, 3, False), ("quad", capi.INT_GI, 3, True), ("quad", capi.INT_INDIRECT, 2, True)])
+def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, depth, exact, monkeypatch):
+    """k_bounce_small (shade + shadow rays + next closest hit + next RR in one kernel, plane-paired triangle records in the
+    throughput build) draws the same numbers per path as shade -> connect -> extend, so with the same seed both pipelines
+    render the same paths: ray counts agree and the images differ only where a hit point moved by an ulp across an edge."""
+    require_gpu()
+    desc = scenes.cornell_box(light).flatten()
+    gpu = api.GpuScene(desc, 0)
+    W, H, spp = 160, 90, 16 if not exact else 2
+    cam = scenes.make_camera(W, H)
+    flags = capi.FLAG_EXACT if exact else 0
+    monkeypatch.setenv("XRT_FUSED_BOUNCE", "1")
+    a, sa = gpu.render(cam, W, H, spp, integ, depth, seed=11, flags=flags)
+    monkeypatch.setenv("XRT_FUSED_BOUNCE", "0")
+    b, sb = gpu.render(cam, W, H, spp, integ, depth, seed=11, flags=flags)
+    assert sa["kernel_launches"] < sb["kernel_launches"]
+    if exact:   # same arithmetic, same order: identical counts, images equal to the last bits of the radiance sums
+        assert sa["closest_rays"] == sb["closest_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
+        assert close_image(a, b)
+    else:
+        assert abs(sa["closest_rays"] - sb["closest_rays"]) <= 1e-4 * sb["closest_rays"]
+        assert abs(sa["shadow_rays"] - sb["shadow_rays"]) <= 1e-4 * sb["shadow_rays"]
+        assert abs(float(a.mean()) - float(b.mean())) <= 2e-4 * float(b.mean())
+        differing = np.abs(a - b).max(axis=-1) > 1e-3 * (1.0 + np.abs(b).max(axis=-1))
+        assert differing.mean() < 0.01
+
+
 # ---- the spp split used across GPUs -----------------------------------------------------------------------------------
 
 def test_sample_offset_split_equals_single_render(gpu_cornell):

@@ -1,0 +1,62 @@
+"""Scenes of at most 64 triangles are traced from a plane-paired triangle block (xraytracer_b200/csrc/small_scene.cpp): coplanar
+triangles share one ray/plane intersection. The block builder is host code; xrtg_small_scene_selftest checks a block against
+the triangles it came from without a CUDA device."""
+import ctypes as C
+
+import numpy as np
+
+from xraytracer_b200 import capi
+
+
+def selftest(tris9, flags=None):
+    tris9 = np.ascontiguousarray(tris9, dtype=np.float32).reshape(-1, 9)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.int32)
+    ra, ro, pl = C.c_int(), C.c_int(), C.c_int()
+    lib = capi.gpu()
+    rc = lib.xrtg_small_scene_selftest(tris9.ctypes.data if len(tris9) else None, None if fl is None else fl.ctypes.data, len(tris9),
+                                       C.byref(ra), C.byref(ro), C.byref(pl))
+    assert rc >= 0, lib.xrtg_last_error().decode()
+    return rc, ra.value, ro.value, pl.value
+
+
+def quad(p, e1, e2):
+    p, e1, e2 = (np.asarray(x, np.float32) for x in (p, e1, e2))
+    return [np.concatenate([p, p + e1, p + e1 + e2]), np.concatenate([p, p + e1 + e2, p + e2])]
+
+
+def test_cornell_box_pairs_every_quad(cornell):
+    _, desc = cornell
+    d = desc.contents
+    tris = np.array([list(d.triangles[i].v0) + list(d.triangles[i].v1) + list(d.triangles[i].v2) for i in range(d.n_triangles)], np.float32)
+    flags = np.zeros(d.n_triangles, np.int32)
+    for k in range(d.n_objects):
+        o = d.objects[k]
+        if o.kind == 0 and o.area_light >= 0:
+            flags[o.first:o.first + o.count] = 1
+    rc, n_all, n_occ, n_planes = selftest(tris, flags)
+    assert rc == 0
+    # 36 triangles: 17 planar quads pair up; the left wall of the Cornell data (552.8 0 0 / 549.6 0 559.2 / 556 548.8 559.2 /
+    # 556 548.8 0) is NOT planar, so its two triangles stay single
+    assert n_all == 19
+    assert n_occ == n_all - 1                                 # the light's proxy quad is not an occluder
+    assert n_planes == n_all - 2                              # floor and both block footprints share the y = 0 plane
+
+
+def test_triangle_soup_is_not_paired():
+    rng = np.random.default_rng(3)
+    assert selftest(rng.uniform(-1, 1, (40, 9)))[0] == 1      # no coplanar partners: the per-triangle lists stay in use
+
+
+def test_odd_groups_are_padded_and_degenerates_tolerated():
+    tris = quad((0, 0, 0), (1, 0, 0), (0, 1, 0)) + quad((0, 0, 1), (1, 0, 0), (0, 1, 0)) + quad((0, 0, 2), (2, 0, 0), (0, 2, 0))
+    tris += [np.array([2, 0, 0, 3, 0, 0, 3, 1, 0], np.float32)]            # third triangle of the z = 0 plane -> odd group
+    tris += quad((5, 0, 0), (0, 1, 0), (0, 0, 1)) + quad((6, 0, 0), (0, 1, 0), (0, 0, 1))
+    tris += [np.zeros(9, np.float32)]                                        # zero-area triangle: its own record, never hit
+    rc, n_all, n_occ, n_planes = selftest(np.array(tris))
+    assert rc == 0 and n_all == 7 and n_planes == 6 and n_occ == n_all
+
+
+def test_sizes_outside_the_small_scene_range():
+    big = np.tile(np.array(quad((0, 0, 0), (1, 0, 0), (0, 1, 0))), (33, 1))   # 66 triangles: not a small scene
+    assert selftest(big)[0] == 1
+    assert selftest(np.zeros((0, 9), np.float32))[0] == 1

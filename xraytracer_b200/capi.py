@@ -85,7 +85,8 @@ class Stats(C.Structure):
                 ("tracking_steps", C.c_uint64), ("kernel_launches", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("shade_launches", C.c_uint64), ("connect_launches", C.c_uint64), ("render_ms", C.c_float),
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("primary_hits", C.c_uint64)]
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("primary_hits", C.c_uint64),
+                ("bounce_entries", C.c_uint64), ("bounce_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -99,7 +100,8 @@ class SceneInfo(C.Structure):
     _fields_ = [("n_prims", C.c_int32), ("n_triangles", C.c_int32), ("n_bvh_nodes", C.c_int32),
                 ("bvh_depth", C.c_int32), ("bvh_sah_cost", C.c_float), ("build_ms", C.c_float),
                 ("upload_ms", C.c_float), ("device_bytes", C.c_uint64), ("upload_bytes", C.c_uint64),
-                ("bvh_build_ms", C.c_float), ("bvh_builder", C.c_int32)]
+                ("bvh_build_ms", C.c_float), ("bvh_builder", C.c_int32),
+                ("small_records_all", C.c_int32), ("small_records_occ", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -118,7 +120,7 @@ BUILD_LBVH_GPU = 1
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_create2", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
-               "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest"]
+               "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest", "xrtg_small_scene_selftest"]
 
 GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
 HOST_LIB = PKG / "host" / "libxrthost.so"
@@ -160,6 +162,7 @@ def gpu():
     lib.xrtg_trace_rays.argtypes = [VP, C.c_int64, VP, VP, VP, C.c_int, C.c_uint32, VP]
     lib.xrtg_image_to_u8.argtypes = [C.c_int, VP, C.c_int, C.c_int, C.c_float, C.c_int, VP]
     lib.xrtg_bvh_selftest.argtypes = [VP, C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(C.c_float)]
+    lib.xrtg_small_scene_selftest.argtypes = [VP, VP, C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]
     lib._typed = True
     return lib
 

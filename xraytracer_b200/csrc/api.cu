@@ -254,23 +254,8 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
                 trisId[3 * ti] = f4(t.v0, asF(id));
                 trisId[3 * ti + 1] = f4(e1, asF(int(o.area_light >= 0 ? 1 : 0)));
                 trisId[3 * ti + 2] = f4(e2, 0.f);
-                {
-                    // plane-equation record of the throughput instantiation (wavefront.cuh: triangleRecord), built in double:
-                    // N = e1 x e2, d = N.v0 ; u = n1.P + d1 with n1 = (e2 x N)/|N|^2 ; v = n2.P + d2 with n2 = (N x e1)/|N|^2
-                    const double E1[3] = {double(t.v1[0]) - t.v0[0], double(t.v1[1]) - t.v0[1], double(t.v1[2]) - t.v0[2]};
-                    const double E2[3] = {double(t.v2[0]) - t.v0[0], double(t.v2[1]) - t.v0[1], double(t.v2[2]) - t.v0[2]};
-                    const double N[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
-                    const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
-                    const double n1[3] = {(E2[1] * N[2] - E2[2] * N[1]) / nn, (E2[2] * N[0] - E2[0] * N[2]) / nn, (E2[0] * N[1] - E2[1] * N[0]) / nn};
-                    const double n2[3] = {(N[1] * E1[2] - N[2] * E1[1]) / nn, (N[2] * E1[0] - N[0] * E1[2]) / nn, (N[0] * E1[1] - N[1] * E1[0]) / nn};
-                    const double dN = N[0] * t.v0[0] + N[1] * t.v0[1] + N[2] * t.v0[2];
-                    const double d1 = -(n1[0] * t.v0[0] + n1[1] * t.v0[1] + n1[2] * t.v0[2]);
-                    const double d2 = -(n2[0] * t.v0[0] + n2[1] * t.v0[1] + n2[2] * t.v0[2]);
-                    ftrisId[4 * ti] = make_float4(float(N[0]), float(N[1]), float(N[2]), float(dN));
-                    ftrisId[4 * ti + 1] = make_float4(float(n1[0]), float(n1[1]), float(n1[2]), float(d1));
-                    ftrisId[4 * ti + 2] = make_float4(float(n2[0]), float(n2[1]), float(n2[2]), float(d2));
-                    ftrisId[4 * ti + 3] = make_float4(asF(id), asF(int(o.area_light >= 0 ? 1 : 0)), 0.f, 0.f);
-                }
+                // plane-equation record of the throughput instantiation (wavefront.cuh: triangleRecord), built in double
+                makePlaneRecord(t.v0, t.v1, t.v2, id, o.area_light >= 0 ? 1 : 0, reinterpret_cast<float*>(ftrisId + 4 * ti));
                 prims[4 * id] = f4(t.n0, ng[0]);
                 prims[4 * id + 1] = f4(t.n1, ng[1]);
                 prims[4 * id + 2] = f4(t.n2, ng[2]);
@@ -351,7 +336,10 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     int smallBlockF4 = 0;
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
         std::vector<float> block;
-        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, nullptr)) {
+        SmallBlockInfo sbi;
+        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi)) {
+            s->info.small_records_all = sbi.nRecordsAll;
+            s->info.small_records_occ = sbi.nRecordsOcc;
             if (int rc = s->smallBlock.alloc(block.size() * sizeof(float))) return rc;
             std::memcpy(s->smallBlock.h, block.data(), s->smallBlock.bytes);
             smallBlockF4 = int(block.size() / 4);
@@ -618,7 +606,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     const bool small = !deep && s->ds.nBruteTris > 0 && s->ds.nBruteTris <= 64;
     const bool bruteSecondary = envInt("XRT_BRUTE_SECONDARY", small ? 1 : 0) != 0, bruteShadow = envInt("XRT_BRUTE_SHADOW", small ? 1 : 0) != 0;
     const bool dump = std::getenv("XRT_STAGE_DUMP") != nullptr;
-    uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0;
+    uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0, nBounce = 0;
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
     CU(cudaMemsetAsync(dstats, 0, sizeof(unsigned long long) * kStatCount, st));
@@ -651,7 +639,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                     tm.end();
                 }
                 tm.begin(kStageShade);
-                K.bounceSmall(st, s->ds, q, w, src, b, dstats); ++launches; ++nShade;
+                K.bounceSmall(st, s->ds, q, w, src, b, dstats); ++launches; ++nShade; ++nBounce;
                 tm.end();
                 continue;
             }
@@ -700,6 +688,8 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         stats->tris_tested_shadow = s->statsHost[kStatTrisAny];
         stats->tracking_steps = s->statsHost[kStatSteps];
         stats->primary_hits = s->statsHost[kStatPrimaryHits];
+        stats->bounce_entries = s->statsHost[kStatBounceEntries];
+        stats->bounce_launches = nBounce;
         stats->kernel_launches = launches;
         stats->extend_launches = nExtend; stats->shade_launches = nShade; stats->connect_launches = nConnect;
         CU(cudaEventElapsedTime(&stats->render_ms, s->ev[0], s->ev[1]));
@@ -735,6 +725,18 @@ __global__ void k_image_to_u8(const float* __restrict__ rgb, unsigned char* __re
 }
 
 extern "C" {
+
+int xrtg_small_scene_selftest(const float* tris9, const int* emitter_flags, int n, int* n_records_all, int* n_records_occ, int* n_planes)
+{
+    if (n < 0 || (n > 0 && !tris9)) return fail(XRTG_ERR_INVALID, "bad triangle array");
+    SmallBlockInfo bi;
+    const int rc = smallBlockSelftest(tris9, emitter_flags, n, &bi);
+    if (n_records_all) *n_records_all = bi.nRecordsAll;
+    if (n_records_occ) *n_records_occ = bi.nRecordsOcc;
+    if (n_planes) *n_planes = bi.nPlanesAll;
+    if (rc < 0) return fail(XRTG_ERR_INVALID, "small-scene block is inconsistent with its triangles");
+    return rc;
+}
 
 int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost)
 {

@@ -86,7 +86,7 @@ struct DQueues {
 enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
 
 // device-side statistics (uint64 each)
-enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatCount };
+enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatCount };
 
 struct DWave {
     int width, height;

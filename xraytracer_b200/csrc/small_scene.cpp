@@ -1,5 +1,6 @@
 // small_scene.cpp — groups the triangles of a small scene by supporting plane (see small_scene.h).
 #include "small_scene.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -84,6 +85,74 @@ size_t emitSection(const float* rec, const std::vector<int>& tris, const std::ve
 }
 
 } // namespace
+
+void makePlaneRecord(const float v0[3], const float v1[3], const float v2[3], int id, int flags, float rec[16])
+{
+    const double E1[3] = {double(v1[0]) - v0[0], double(v1[1]) - v0[1], double(v1[2]) - v0[2]};
+    const double E2[3] = {double(v2[0]) - v0[0], double(v2[1]) - v0[1], double(v2[2]) - v0[2]};
+    const double N[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
+    const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+    const double n1[3] = {(E2[1] * N[2] - E2[2] * N[1]) / nn, (E2[2] * N[0] - E2[0] * N[2]) / nn, (E2[0] * N[1] - E2[1] * N[0]) / nn};
+    const double n2[3] = {(N[1] * E1[2] - N[2] * E1[1]) / nn, (N[2] * E1[0] - N[0] * E1[2]) / nn, (N[0] * E1[1] - N[1] * E1[0]) / nn};
+    const double dN = N[0] * v0[0] + N[1] * v0[1] + N[2] * v0[2];
+    const double d1 = -(n1[0] * v0[0] + n1[1] * v0[1] + n1[2] * v0[2]);
+    const double d2 = -(n2[0] * v0[0] + n2[1] * v0[1] + n2[2] * v0[2]);
+    const float out[16] = {float(N[0]),  float(N[1]),  float(N[2]),  float(dN), float(n1[0]), float(n1[1]), float(n1[2]), float(d1),
+                           float(n2[0]), float(n2[1]), float(n2[2]), float(d2), asFloat(id),  asFloat(flags), 0.f,        0.f};
+    std::memcpy(rec, out, sizeof(out));
+}
+
+// Checks a block against the triangles it was built from: every triangle exactly once in `All`, every non-emitter exactly once
+// in `Occ`, padding slots reject every point, each triangle's centroid lies on its record's plane and inside its own barycentric
+// equations, records of one plane carry identical plane words. Returns 0 (valid block), 1 (valid, but pairing does not pay so
+// no block is emitted) or -1 (inconsistent).
+int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, SmallBlockInfo* info)
+{
+    std::vector<float> recs(size_t(std::max(n, 1)) * 16);
+    for (int t = 0; t < n; ++t)
+        makePlaneRecord(tris9 + 9 * size_t(t), tris9 + 9 * size_t(t) + 3, tris9 + 9 * size_t(t) + 6, t, emitterFlags ? emitterFlags[t] : 0, &recs[16 * size_t(t)]);
+    std::vector<float> block;
+    SmallBlockInfo bi;
+    const bool ok = buildSmallBlock(recs.data(), n, block, &bi);
+    if (info) *info = bi;
+    if (!ok) return 1;
+    auto asInt = [](float f) { int i; std::memcpy(&i, &f, 4); return i; };
+    const int total = asInt(block[2]);
+    if (size_t(total) * 4 != block.size() || total > kSmallBlockMaxF4) return -1;
+    for (int sec = 0; sec < 2; ++sec) {
+        const int off = asInt(block[size_t(sec)]);
+        const int nRec = asInt(block[4 * size_t(off)]), offRecs = asInt(block[4 * size_t(off) + 2]), offIds = asInt(block[4 * size_t(off) + 3]);
+        std::vector<int> seen(size_t(n), 0);
+        for (int r = 0; r < nRec; ++r) {
+            const float* R = &block[4 * (size_t(offRecs) + 5 * size_t(r))];
+            for (int k = 0; k < 2; ++k) {
+                const int id = asInt(block[4 * size_t(offIds) + 2 * size_t(r) + size_t(k)]);
+                const float* a = R + 4 + 8 * k;
+                if (id < 0) { // padding: n1 = n2 = 0, d1 = d2 = -1
+                    if (k == 0 || a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != -1.f || a[7] != -1.f) return -1;
+                    continue;
+                }
+                if (id >= n || seen[size_t(id)]++) return -1;
+                if (sec == 1 && emitterFlags && (emitterFlags[id] & 1)) return -1;
+                const float* v = tris9 + 9 * size_t(id);
+                const double c[3] = {(double(v[0]) + v[3] + v[6]) / 3, (double(v[1]) + v[4] + v[7]) / 3, (double(v[2]) + v[5] + v[8]) / 3};
+                const double nlen = std::sqrt(double(R[0]) * R[0] + double(R[1]) * R[1] + double(R[2]) * R[2]);
+                if (!(nlen > 0.0) || !std::isfinite(nlen)) continue; // degenerate triangle: its record rejects every ray
+                const double dist = (R[0] * c[0] + R[1] * c[1] + R[2] * c[2] - R[3]) / nlen; // centroid to the record's plane
+                double scale = 1.0;
+                for (int q = 0; q < 3; ++q) scale = std::fmax(scale, std::fabs(c[q]));
+                if (!(std::fabs(dist) <= 1e-4 * scale)) return -1;
+                const double u = a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3], w = a[4] * c[0] + a[5] * c[1] + a[6] * c[2] + a[7];
+                if (!(std::fabs(u - 1.0 / 3) < 1e-3 && std::fabs(w - 1.0 / 3) < 1e-3)) return -1;
+            }
+        }
+        for (int t = 0; t < n; ++t) {
+            const bool expect = sec == 0 || !(emitterFlags && (emitterFlags[t] & 1));
+            if (seen[size_t(t)] != (expect ? 1 : 0)) return -1;
+        }
+    }
+    return 0;
+}
 
 bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info)
 {

@@ -24,6 +24,14 @@ struct SmallBlockInfo {
     int nRecordsAll = 0, nRecordsOcc = 0, nPlanesAll = 0;
 };
 
+// Plane-equation record of one triangle (16 floats: N|d, n1|d1, n2|d2, id|flags|0|0 — the last two as int bits), computed in
+// double: N = e1 x e2, d = N.v0 give t = (d - N.o)/(N.dir); u = n1.P + d1 with n1 = (e2 x N)/|N|^2, v = n2.P + d2 with
+// n2 = (N x e1)/|N|^2 (Havel & Herout 2010). flags bit 0 = emitter proxy.
+void makePlaneRecord(const float v0[3], const float v1[3], const float v2[3], int id, int flags, float rec[16]);
+
+// Host-only consistency check of buildSmallBlock (no CUDA device needed), see xrtg_small_scene_selftest in xrtgpu.h.
+int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, SmallBlockInfo* info);
+
 // ftrisId: 4 floats x 4 per triangle (N|d, n1|d1, n2|d2, id|flags) in primitive-id order. Returns false (block left empty) when
 // grouping does not pay (fewer than 4 triangles saved) or the block would not fit.
 bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info);

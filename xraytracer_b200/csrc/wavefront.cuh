@@ -1594,6 +1594,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     }
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatShadow, nShadow);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatBounceEntries, (unsigned long long)n);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -625,6 +625,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         const bool fusedPrimary = !deep && nIter > 0;
         // Small scenes under the ray-tracing surface integrators: per bounce ONE kernel (k_bounce_small) instead of shade ->
         // connect -> extend; see wavefront.cuh.
+        const bool volumePaths = fusedPrimary && volume && envInt("XRT_VOLUME_PATHS", 1) != 0;
         const bool fusedBounce = fusedPrimary && small && !brute && bruteSecondary && bruteShadow && envInt("XRT_FUSED_BOUNCE", 1) != 0 &&
                                  (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
         if (nIter == 0) CU(cudaMemsetAsync(q.radiance, 0, sizeof(float4) * size_t(w.nPaths), st));
@@ -632,6 +633,15 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         tm.end();
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
+            if (volumePaths) { // volume integrators on a shallow BVH: primary, then every path to completion in one launch
+                tm.begin(kStageExtend);
+                K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
+                tm.end();
+                tm.begin(kStageShade);
+                K.volumePaths(st, s->ds, q, w, brute, nIter, count, dstats); ++launches; ++nShade;
+                tm.end();
+                break;
+            }
             if (fusedBounce) { // small scene: primary, then one fused shade + connect + extend kernel per bounce
                 if (b == 0) {
                     tm.begin(kStageExtend);

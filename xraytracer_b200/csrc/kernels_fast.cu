@@ -9,7 +9,7 @@ namespace xrt {
 const KernelTable& fastKernels()
 {
     using namespace fast;
-    static const KernelTable t = {launchSeedMt, launchRaygen, launchPrimary, launchExtend, launchConnect, launchShadeSurface, launchBounceSmall, launchShadeVolume,
+    static const KernelTable t = {launchSeedMt, launchRaygen, launchPrimary, launchExtend, launchConnect, launchShadeSurface, launchBounceSmall, launchShadeVolume, launchVolumePaths,
                                   launchAccumulate, launchFinalize, launchTraceRays, launchGenJitter};
     return t;
 }

@@ -1799,8 +1799,78 @@ __device__ __forceinline__ V3 transmittance(const DScene& sc, const DMedium& m, 
     return tr;
 }
 
-// VolumePathTracing (integrator.h:409-473) and VolumePathTracingNEE (integrator.h:489-631): one loop iteration
-// of the reference per wavefront bounce; the tracking loop runs inside the thread.
+// VolumePathTracing (integrator.h:409-473) and VolumePathTracingNEE (integrator.h:489-631): ONE iteration of the reference's
+// loop for one path whose ray (o, d) has the closest hit h — Russian roulette, emitter, medium sampling (the tracking loop runs
+// inside the thread), NEE through the medium. Returns true if the path continues with ray (no, nd), throughput nT and `depth`
+// updated; at most one radiance contribution per iteration (hasContrib / contrib).
+template <bool COUNT>
+__device__ __forceinline__ bool volumeIteration(const DScene& sc, const DWave& w, bool nee, bool brute, V3 o, V3 d, V3 T, const Hit& h, int& depth,
+                                                Rng& rng, int* sstack, TraceCounters& tc, uint32_t& steps, uint32_t& extraClosest, V3& no, V3& nd,
+                                                V3& nT, bool& hasContrib, V3& contrib)
+{
+    hasContrib = false;
+    if (h.prim < 0) return false; // a miss adds throughput*background*(depth!=0) = 0
+    Surf s;
+    makeSurf(sc, o, d, h, s);
+    if (depth > 0) {
+        const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
+        if (rng.next() >= p) return false;
+        T = T / mk(p);
+    }
+    if (lightOf(s) >= 0) {
+        if (!nee || depth == 0) { contrib = T * emitted(sc, s, d); hasContrib = true; }
+        return false;
+    }
+    const int mi = mediumOf(s);
+    if (mi < 0) {
+        // A plain surface: the reference never advances here (infinite loop).
+        // The sample is poisoned so that it is DROPPED and counted, like the oracle port does.
+        contrib = mk(__int_as_float(0x7fc00000)); hasContrib = true;
+        return false;
+    }
+    const DMedium m = sc.media[mi];
+    V3 pos, dir, tm;
+    bool scattered;
+    if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) scattered = sampleHeterogeneous(sc, m, o, d, T, h.t, s.t1, rng, pos, dir, tm, steps);
+    else scattered = sampleHomogeneous(m, o, d, T, h.t, s.t1, rng, pos, dir, tm);
+    if (nee && scattered) {
+        // sampleDirectionToLight (integrator.h:583-602), Scene::sampleAreaLight (scene.cpp:182-188)
+        unsigned int li = (unsigned int)(float(sc.nLights) * rng.next());
+        if (li == (unsigned int)sc.nLights) li--;
+        const float choose = 1.0f / float(sc.nLights);
+        V3 dl = mk(0.f);
+        float dist, lp = 0.0f;
+        const V3 Le = sampleLight(sc.lights[li], pos, dl, lp, dist, rng);
+        const float pdf_dir = choose * lp;
+        if (pdf_dir > 0.0f) {
+            // isVisible (integrator.h:604-631): ONE closest-hit query, dist_to_light ignored
+            V3 trn = mk(1.0f);
+            bool visible = true;
+            Hit sh;
+            closestHit<COUNT>(sc, pos, dl, brute, sh, sstack, tc);
+            ++extraClosest;
+            if (sh.prim >= 0) {
+                Surf ss;
+                makeSurf(sc, pos, dl, sh, ss);
+                if (hasMaterial(ss)) visible = false;
+                else if (mediumOf(ss) >= 0)
+                    trn = trn * transmittance(sc, sc.media[mediumOf(ss)], pos + sh.t * dl, pos + ss.t1 * dl, rng, steps);
+            }
+            if (visible) {
+                const V3 f = mk(hgEval(m.g, d, dl));
+                const V3 Ls = trn * f * Le / pdf_dir;
+                contrib = T * tm * Ls; hasContrib = true;
+            }
+        }
+    }
+    nT = T * tm;
+    no = pos; nd = dir;
+    if (scattered) depth++;
+    return depth < w.maxDepth;
+}
+
+// Wavefront form: one iteration per launch, continuing paths appended to the next ray queue (deep BVHs: the closest hits of the
+// next iteration go through the refillable traversal kernel).
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, DWave w, int src, int bounce, int brute, unsigned long long* stats)
 {
@@ -1822,81 +1892,67 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
         int depth = 0;
         if (i < n) {
             const float4 r0 = q.q0[src][i], r1 = q.q1[src][i], r2 = q.q2[src][i], hv = q.hits[i];
-            const V3 o = xyz(r0), d = xyz(r1);
-            V3 T = mk(r0.w, r1.w, r2.x);
             pid = uint32_t(__float_as_int(r2.y));
             depth = __float_as_int(r2.z);
-            Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+            const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
             Rng rng;
             rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
-            if (h.prim >= 0) { // a miss adds throughput*background*(depth!=0) = 0
-                Surf s;
-                makeSurf(sc, o, d, h, s);
-                bool alive = true;
-                if (depth > 0) {
-                    const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
-                    if (rng.next() >= p) alive = false;
-                    else T = T / mk(p);
-                }
-                if (alive && lightOf(s) >= 0) {
-                    if (!nee || depth == 0) addRadiance(q, pid, T * emitted(sc, s, d));
-                    alive = false;
-                }
-                if (alive) {
-                    const int mi = mediumOf(s);
-                    if (mi >= 0) {
-                        const DMedium m = sc.media[mi];
-                        V3 pos, dir, tm;
-                        bool scattered;
-                        if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) scattered = sampleHeterogeneous(sc, m, o, d, T, h.t, s.t1, rng, pos, dir, tm, steps);
-                        else scattered = sampleHomogeneous(m, o, d, T, h.t, s.t1, rng, pos, dir, tm);
-                        if (nee && scattered) {
-                            // sampleDirectionToLight (integrator.h:583-602), Scene::sampleAreaLight (scene.cpp:182-188)
-                            unsigned int li = (unsigned int)(float(sc.nLights) * rng.next());
-                            if (li == (unsigned int)sc.nLights) li--;
-                            const float choose = 1.0f / float(sc.nLights);
-                            V3 dl = mk(0.f);
-                            float dist, lp = 0.0f;
-                            const V3 Le = sampleLight(sc.lights[li], pos, dl, lp, dist, rng);
-                            const float pdf_dir = choose * lp;
-                            if (pdf_dir > 0.0f) {
-                                // isVisible (integrator.h:604-631): ONE closest-hit query, dist_to_light ignored
-                                V3 trn = mk(1.0f);
-                                bool visible = true;
-                                Hit sh;
-                                closestHit<COUNT>(sc, pos, dl, brute != 0, sh, s_stack + threadIdx.x, tc);
-                                ++extraClosest;
-                                if (sh.prim >= 0) {
-                                    Surf ss;
-                                    makeSurf(sc, pos, dl, sh, ss);
-                                    if (hasMaterial(ss)) visible = false;
-                                    else if (mediumOf(ss) >= 0)
-                                        trn = trn * transmittance(sc, sc.media[mediumOf(ss)], pos + sh.t * dl, pos + ss.t1 * dl, rng, steps);
-                                }
-                                if (visible) {
-                                    const V3 f = mk(hgEval(m.g, d, dl));
-                                    const V3 Ls = trn * f * Le / pdf_dir;
-                                    addRadiance(q, pid, T * tm * Ls);
-                                }
-                            }
-                        }
-                        nT = T * tm;
-                        no = pos; nd = dir;
-                        if (scattered) depth++;
-                        wantRay = depth < w.maxDepth;
-                    }
-                    else {
-                        // A plain surface: the reference never advances here (infinite loop).
-                        // The sample is poisoned so that it is DROPPED and counted, like the oracle port does.
-                        addRadiance(q, pid, mk(__int_as_float(0x7fc00000)));
-                    }
-                }
-            }
+            bool hasContrib;
+            V3 contrib;
+            wantRay = volumeIteration<COUNT>(sc, w, nee, brute != 0, xyz(r0), xyz(r1), mk(r0.w, r1.w, r2.x), h, depth, rng, s_stack + threadIdx.x, tc,
+                                             steps, extraClosest, no, nd, nT, hasContrib, contrib);
+            if (hasContrib) addRadiance(q, pid, contrib);
             ctr = rng.close();
         }
         pushRayWarp(so, wantRay, no, nd, nT, pid, depth, ctr);
     }
     if (extraClosest) atomicAdd(stats + kStatClosest, (unsigned long long)extraClosest);
+    statAdd(stats, kStatSteps, steps);
+    if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
+}
+
+// Shallow BVHs (every volume scene of the reference: a box or a sphere, a light, a few walls): after the primary hit a path
+// only ever produces ONE next ray, and only ~14 % of the 1080p paths enter the medium at all, so the wavefront form degenerates
+// into dozens of launches over a few ten thousand rays each plus a host poll per iteration (workload c5: 105 launches per wave,
+// 10.5 M closest hits of which 8.3 M are primary). Here one thread runs its path to completion: iteration, inline closest hit,
+// iteration, ... — the same draws in the same order. One launch per wave, no host round trip.
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, unsigned long long* stats)
+{
+    __shared__ int s_stack[kStackSmem * kBlock];
+    uint32_t* ctrl = q.ctrl;
+    const uint32_t n = ctrl[kCtrlRays];
+    const bool nee = (w.integrator == XRTG_INT_VOLUME_NEE);
+    uint32_t steps = 0, nClosest = 0;
+    TraceCounters tc;
+    uint32_t resNext = 0, resEnd = 0, base;
+    while (warpNextBatch<32>(ctrl + kCtrlFetchShade, n, resNext, resEnd, base)) {
+        const uint32_t i = base + laneId();
+        if (i >= n) continue;
+        const float4 r0 = q.q0[0][i], r1 = q.q1[0][i], r2 = q.q2[0][i], hv = q.hits[i];
+        const uint32_t pid = uint32_t(__float_as_int(r2.y));
+        int depth = __float_as_int(r2.z);
+        V3 o = xyz(r0), d = xyz(r1), T = mk(r0.w, r1.w, r2.x);
+        Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+        Rng rng;
+        rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+        float4 rad = q.radiance[pid];
+        bool dirty = false;
+        for (int it = 0; it < maxIter; ++it) {
+            V3 no, nd, nT, contrib;
+            bool hasContrib;
+            const bool cont = volumeIteration<COUNT>(sc, w, nee, brute != 0, o, d, T, h, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd, nT,
+                                                     hasContrib, contrib);
+            if (hasContrib) { rad.x += contrib.x; rad.y += contrib.y; rad.z += contrib.z; dirty = true; }
+            if (!cont || it + 1 == maxIter) break;
+            o = no; d = nd; T = nT;
+            closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+            ++nClosest;
+        }
+        rng.close();
+        if (dirty) q.radiance[pid] = rad;
+    }
+    statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatSteps, steps);
     if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
 }
@@ -2026,6 +2082,20 @@ inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& 
     if (!g0) { g0 = gridFor((const void*)k_shade_volume<false>); g1 = gridFor((const void*)k_shade_volume<true>); }
     if (count) k_shade_volume<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
     else k_shade_volume<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
+}
+inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, bool count,
+                              unsigned long long* stats)
+{
+    static thread_local int g0 = 0, g1 = 0, g2 = 0, sel = 0;
+    if (!g0) {
+        g0 = gridFor((const void*)k_volume_paths<false, 4>); g1 = gridFor((const void*)k_volume_paths<true, 4>);
+        g2 = gridFor((const void*)k_volume_paths<false, 5>);
+        const char* e = std::getenv("XRT_VOLUME_MINB");
+        sel = e ? std::atoi(e) : 5;
+    }
+    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
+    else if (sel == 5) k_volume_paths<false, 5><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
+    else k_volume_paths<false, 4><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
 }
 inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
 {

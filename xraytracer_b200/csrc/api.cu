@@ -424,6 +424,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     ds.grids = static_cast<const DGrid*>(s->grids.d);
     ds.nTris = nMeshTris; ds.nBruteTris = nMeshTris; ds.nSpheres = nSph; ds.nBoxes = nBox;
     ds.nLights = d->n_area_lights; ds.nDelta = d->n_delta_lights; ds.nPrims = nPrims;
+    ds.nMedia = d->n_media; ds.nGrids = d->n_grids;
     s->maxShadowPerPath = std::max(1, std::max(d->n_area_lights, d->n_delta_lights));
 
     s->info.n_prims = nPrims;
@@ -638,7 +639,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
                 tm.end();
                 tm.begin(kStageShade);
-                K.volumePaths(st, s->ds, q, w, brute, nIter, count, dstats); ++launches; ++nShade;
+                K.volumePaths(st, s->ds, q, w, brute, nIter, envInt("XRT_THR_VOL", 20), count, dstats); ++launches; ++nShade;
                 tm.end();
                 break;
             }

@@ -63,7 +63,7 @@ struct DScene {
     const DDelta* dlights;
     const DMedium* media;
     const DGrid* grids;
-    int nTris, nSpheres, nBoxes, nLights, nDelta, nPrims, nBruteTris;
+    int nTris, nSpheres, nBoxes, nLights, nDelta, nPrims, nBruteTris, nMedia, nGrids;
 };
 
 struct DCamera {

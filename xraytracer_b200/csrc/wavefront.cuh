@@ -1614,10 +1614,19 @@ __device__ __forceinline__ float gridDensity(const DGrid& g, V3 p)
     const float bx = floorf(fx), by = floorf(fy), bz = floorf(fz);
     const float wx = fx - bx, wy = fy - by, wz = fz - bz;
     const int x = int(bx), y = int(by), z = int(bz);
-    const float v000 = gridVoxel(g, x, y, z), v001 = gridVoxel(g, x, y, z + 1);
-    const float v010 = gridVoxel(g, x, y + 1, z), v011 = gridVoxel(g, x, y + 1, z + 1);
-    const float v100 = gridVoxel(g, x + 1, y, z), v101 = gridVoxel(g, x + 1, y, z + 1);
-    const float v110 = gridVoxel(g, x + 1, y + 1, z), v111 = gridVoxel(g, x + 1, y + 1, z + 1);
+    float v000, v001, v010, v011, v100, v101, v110, v111;
+    if (x >= 0 && y >= 0 && z >= 0 && x + 1 < g.nx && y + 1 < g.ny && z + 1 < g.nz) { // interior cell: one address, eight fixed offsets
+        const float* __restrict__ c = g.data + (size_t(z) * g.ny + y) * g.nx + x;
+        const size_t sy = size_t(g.nx), sz = size_t(g.nx) * g.ny;
+        v000 = __ldg(c); v100 = __ldg(c + 1); v010 = __ldg(c + sy); v110 = __ldg(c + sy + 1);
+        v001 = __ldg(c + sz); v101 = __ldg(c + sz + 1); v011 = __ldg(c + sz + sy); v111 = __ldg(c + sz + sy + 1);
+    }
+    else {
+        v000 = gridVoxel(g, x, y, z); v001 = gridVoxel(g, x, y, z + 1);
+        v010 = gridVoxel(g, x, y + 1, z); v011 = gridVoxel(g, x, y + 1, z + 1);
+        v100 = gridVoxel(g, x + 1, y, z); v101 = gridVoxel(g, x + 1, y, z + 1);
+        v110 = gridVoxel(g, x + 1, y + 1, z); v111 = gridVoxel(g, x + 1, y + 1, z + 1);
+    }
     const float c00 = v000 + (v001 - v000) * wz;
     const float c01 = v010 + (v011 - v010) * wz;
     const float c10 = v100 + (v101 - v100) * wz;
@@ -1729,53 +1738,65 @@ __device__ __forceinline__ bool sampleHomogeneous(const DMedium& m, V3 o, V3 d, 
     return true;
 }
 
-// HeterogeneousMedium::sampleMedium — spectral delta tracking (medium.cpp:45-133)
-__device__ __forceinline__ bool sampleHeterogeneous(const DScene& sc, const DMedium& m, V3 o, V3 d, V3 rayT, float tEntry, float t1, Rng& rng,
-                                                    V3& pos, V3& dir, V3& thr, uint32_t& steps)
+// HeterogeneousMedium::sampleMedium — spectral delta tracking (medium.cpp:45-133), as a resumable loop: trackBegin() = the
+// set-up before the loop (:52-60), trackStep() = one iteration (:62-132), returning true when the walk ended (scatter or exit).
+struct TrackState {
+    float t, t1, density; // density = multiplier * grid density at the current position (sigma_a of the next wavelength pick)
+    V3 tt;                // throughput accumulated by the walk
+};
+struct TrackResult {
+    V3 pos, dir, thr;
+    bool scattered;
+};
+__device__ __forceinline__ void trackBegin(const DMedium& m, const DGrid& g, V3 o, V3 d, float tEntry, float t1, TrackState& ts)
 {
-    const DGrid g = sc.grids[m.grid];
+    ts.tt = mk(1.f);
+    ts.t = tEntry;
+    ts.t1 = t1;
+    ts.density = m.densityMul * gridDensity(g, o + tEntry * d);
+}
+__device__ __forceinline__ bool trackStep(const DMedium& m, const DGrid& g, V3 o, V3 d, V3 rayT, TrackState& ts, Rng& rng, TrackResult& r, uint32_t& steps)
+{
     const V3 absC = v3(m.sigma_a), scatC = v3(m.sigma_s);
-    V3 tt = mk(1.f);
-    float t = tEntry;
-    float density = m.densityMul * gridDensity(g, o + t * d);
-    V3 sigma_a = absC * density;
     const V3 maj = mk(m.majorant);
-    while (true) {
-        ++steps;
-        V3 pmf;
-        const uint32_t ch = sampleWavelength(rayT * tt, (maj - sigma_a) * m.invMajorant, rng, pmf);
-        const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
-        t += sd;
-        if (t > t1 - kRayEps) {
-            pos = o + (t1 + kRayEps) * d; dir = d;
-            const float rest = sd - (t - (t1 - kRayEps));
-            const V3 tr = analyticTr(rest, maj);
-            const V3 pdf = pmf * tr;
-            tt = tt * (tr / (pdf.x + pdf.y + pdf.z));
-            thr = anyNan(tt) ? mk(0.f) : tt;
-            return false;
-        }
-        density = m.densityMul * gridDensity(g, o + t * d);
-        const V3 sigma_s = scatC * density;
-        sigma_a = absC * density;
-        const V3 sigma_n = maj - sigma_a - sigma_s;
-        const V3 P_s = sigma_s / (sigma_s + sigma_n);
-        const V3 P_n = sigma_n / (sigma_s + sigma_n);
-        if (rng.next() < comp(P_s, ch)) {
-            pos = o + t * d;
-            hgSample(m.g, d, rng, dir);
-            const V3 tr = analyticTr(sd, maj);
-            const V3 pdf_distance = m.majorant * tr;
-            const V3 pdf = pmf * pdf_distance * P_s;
-            tt = tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
-            thr = anyNan(tt) ? mk(0.f) : tt;
-            return true;
-        }
+    V3 sigma_a = absC * ts.density;
+    ++steps;
+    V3 pmf;
+    const uint32_t ch = sampleWavelength(rayT * ts.tt, (maj - sigma_a) * m.invMajorant, rng, pmf);
+    const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
+    ts.t += sd;
+    if (ts.t > ts.t1 - kRayEps) {
+        r.pos = o + (ts.t1 + kRayEps) * d; r.dir = d;
+        const float rest = sd - (ts.t - (ts.t1 - kRayEps));
+        const V3 tr = analyticTr(rest, maj);
+        const V3 pdf = pmf * tr;
+        ts.tt = ts.tt * (tr / (pdf.x + pdf.y + pdf.z));
+        r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;
+        r.scattered = false;
+        return true;
+    }
+    ts.density = m.densityMul * gridDensity(g, o + ts.t * d);
+    const V3 sigma_s = scatC * ts.density;
+    sigma_a = absC * ts.density;
+    const V3 sigma_n = maj - sigma_a - sigma_s;
+    const V3 P_s = sigma_s / (sigma_s + sigma_n);
+    const V3 P_n = sigma_n / (sigma_s + sigma_n);
+    if (rng.next() < comp(P_s, ch)) {
+        r.pos = o + ts.t * d;
+        hgSample(m.g, d, rng, r.dir);
         const V3 tr = analyticTr(sd, maj);
         const V3 pdf_distance = m.majorant * tr;
-        const V3 pdf = pmf * pdf_distance * P_n;
-        tt = tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+        const V3 pdf = pmf * pdf_distance * P_s;
+        ts.tt = ts.tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
+        r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;
+        r.scattered = true;
+        return true;
     }
+    const V3 tr = analyticTr(sd, maj);
+    const V3 pdf_distance = m.majorant * tr;
+    const V3 pdf = pmf * pdf_distance * P_n;
+    ts.tt = ts.tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+    return false;
 }
 
 // Medium::transmittance: analytic (medium.h:134-139) or ratio tracking (medium.h:360-386)
@@ -1799,73 +1820,85 @@ __device__ __forceinline__ V3 transmittance(const DScene& sc, const DMedium& m, 
     return tr;
 }
 
-// VolumePathTracing (integrator.h:409-473) and VolumePathTracingNEE (integrator.h:489-631): ONE iteration of the reference's
-// loop for one path whose ray (o, d) has the closest hit h — Russian roulette, emitter, medium sampling (the tracking loop runs
-// inside the thread), NEE through the medium. Returns true if the path continues with ray (no, nd), throughput nT and `depth`
-// updated; at most one radiance contribution per iteration (hasContrib / contrib).
-template <bool COUNT>
-__device__ __forceinline__ bool volumeIteration(const DScene& sc, const DWave& w, bool nee, bool brute, V3 o, V3 d, V3 T, const Hit& h, int& depth,
-                                                Rng& rng, int* sstack, TraceCounters& tc, uint32_t& steps, uint32_t& extraClosest, V3& no, V3& nd,
-                                                V3& nT, bool& hasContrib, V3& contrib)
+// VolumePathTracing (integrator.h:409-473) and VolumePathTracingNEE (integrator.h:489-631): ONE iteration of the reference's loop
+// for one path whose ray (o, d) has the closest hit h, in three pieces so that the tracking walk in the middle can be driven
+// either inline (wavefront kernel) or one step at a time by a whole warp (path kernel):
+//   volumePre  : Russian roulette, emitter test, medium lookup. Returns kVolEnd (path over; at most one contribution),
+//                kVolTrack (heterogeneous medium: walk initialised in ts) or kVolSampled (homogeneous medium: r is final).
+//   trackStep  : see above.
+//   volumePost : NEE through the medium (VolumePathTracingNEE), next ray. Returns true if the path continues.
+enum { kVolEnd = 0, kVolTrack = 1, kVolSampled = 2 };
+__device__ __forceinline__ int volumePre(const DScene& sc, const DMedium* media, const DGrid* grids, bool nee, V3 o, V3 d, V3& T, const Hit& h, int depth,
+                                         Rng& rng, int& mi, TrackState& ts, TrackResult& r, bool& hasContrib, V3& contrib)
 {
     hasContrib = false;
-    if (h.prim < 0) return false; // a miss adds throughput*background*(depth!=0) = 0
+    if (h.prim < 0) return kVolEnd; // a miss adds throughput*background*(depth!=0) = 0
     Surf s;
     makeSurf(sc, o, d, h, s);
     if (depth > 0) {
         const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
-        if (rng.next() >= p) return false;
+        if (rng.next() >= p) return kVolEnd;
         T = T / mk(p);
     }
     if (lightOf(s) >= 0) {
         if (!nee || depth == 0) { contrib = T * emitted(sc, s, d); hasContrib = true; }
-        return false;
+        return kVolEnd;
     }
-    const int mi = mediumOf(s);
+    mi = mediumOf(s);
     if (mi < 0) {
         // A plain surface: the reference never advances here (infinite loop).
         // The sample is poisoned so that it is DROPPED and counted, like the oracle port does.
         contrib = mk(__int_as_float(0x7fc00000)); hasContrib = true;
-        return false;
+        return kVolEnd;
     }
-    const DMedium m = sc.media[mi];
-    V3 pos, dir, tm;
-    bool scattered;
-    if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) scattered = sampleHeterogeneous(sc, m, o, d, T, h.t, s.t1, rng, pos, dir, tm, steps);
-    else scattered = sampleHomogeneous(m, o, d, T, h.t, s.t1, rng, pos, dir, tm);
-    if (nee && scattered) {
+    const DMedium& m = media[mi];
+    if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) {
+        trackBegin(m, grids[m.grid], o, d, h.t, s.t1, ts);
+        return kVolTrack;
+    }
+    r.scattered = sampleHomogeneous(m, o, d, T, h.t, s.t1, rng, r.pos, r.dir, r.thr);
+    return kVolSampled;
+}
+template <bool COUNT>
+__device__ __forceinline__ bool volumePost(const DScene& sc, const DWave& w, const DMedium* media, bool nee, bool brute, V3 d, V3 T, int mi,
+                                           const TrackResult& r, int& depth, Rng& rng, int* sstack, TraceCounters& tc, uint32_t& steps,
+                                           uint32_t& extraClosest, V3& no, V3& nd, V3& nT, bool& hasContrib, V3& contrib)
+{
+    hasContrib = false;
+    const DMedium& m = media[mi];
+    if (nee && r.scattered) {
         // sampleDirectionToLight (integrator.h:583-602), Scene::sampleAreaLight (scene.cpp:182-188)
         unsigned int li = (unsigned int)(float(sc.nLights) * rng.next());
         if (li == (unsigned int)sc.nLights) li--;
         const float choose = 1.0f / float(sc.nLights);
         V3 dl = mk(0.f);
         float dist, lp = 0.0f;
-        const V3 Le = sampleLight(sc.lights[li], pos, dl, lp, dist, rng);
+        const V3 Le = sampleLight(sc.lights[li], r.pos, dl, lp, dist, rng);
         const float pdf_dir = choose * lp;
         if (pdf_dir > 0.0f) {
             // isVisible (integrator.h:604-631): ONE closest-hit query, dist_to_light ignored
             V3 trn = mk(1.0f);
             bool visible = true;
             Hit sh;
-            closestHit<COUNT>(sc, pos, dl, brute, sh, sstack, tc);
+            closestHit<COUNT>(sc, r.pos, dl, brute, sh, sstack, tc);
             ++extraClosest;
             if (sh.prim >= 0) {
                 Surf ss;
-                makeSurf(sc, pos, dl, sh, ss);
+                makeSurf(sc, r.pos, dl, sh, ss);
                 if (hasMaterial(ss)) visible = false;
                 else if (mediumOf(ss) >= 0)
-                    trn = trn * transmittance(sc, sc.media[mediumOf(ss)], pos + sh.t * dl, pos + ss.t1 * dl, rng, steps);
+                    trn = trn * transmittance(sc, media[mediumOf(ss)], r.pos + sh.t * dl, r.pos + ss.t1 * dl, rng, steps);
             }
             if (visible) {
                 const V3 f = mk(hgEval(m.g, d, dl));
                 const V3 Ls = trn * f * Le / pdf_dir;
-                contrib = T * tm * Ls; hasContrib = true;
+                contrib = T * r.thr * Ls; hasContrib = true;
             }
         }
     }
-    nT = T * tm;
-    no = pos; nd = dir;
-    if (scattered) depth++;
+    nT = T * r.thr;
+    no = r.pos; nd = r.dir;
+    if (r.scattered) depth++;
     return depth < w.maxDepth;
 }
 
@@ -1895,13 +1928,27 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
             pid = uint32_t(__float_as_int(r2.y));
             depth = __float_as_int(r2.z);
             const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+            const V3 o = xyz(r0), d = xyz(r1);
+            V3 T = mk(r0.w, r1.w, r2.x);
             Rng rng;
             rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
             bool hasContrib;
             V3 contrib;
-            wantRay = volumeIteration<COUNT>(sc, w, nee, brute != 0, xyz(r0), xyz(r1), mk(r0.w, r1.w, r2.x), h, depth, rng, s_stack + threadIdx.x, tc,
-                                             steps, extraClosest, no, nd, nT, hasContrib, contrib);
+            int mi = -1;
+            TrackState ts;
+            TrackResult r;
+            const int what = volumePre(sc, sc.media, sc.grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
             if (hasContrib) addRadiance(q, pid, contrib);
+            if (what != kVolEnd) {
+                if (what == kVolTrack) {
+                    const DMedium m = sc.media[mi];
+                    const DGrid g = sc.grids[m.grid];
+                    while (!trackStep(m, g, o, d, T, ts, rng, r, steps)) {}
+                }
+                wantRay = volumePost<COUNT>(sc, w, sc.media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, extraClosest, no, nd,
+                                            nT, hasContrib, contrib);
+                if (hasContrib) addRadiance(q, pid, contrib);
+            }
             ctr = rng.close();
         }
         pushRayWarp(so, wantRay, no, nd, nT, pid, depth, ctr);
@@ -1914,43 +1961,119 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
 // Shallow BVHs (every volume scene of the reference: a box or a sphere, a light, a few walls): after the primary hit a path
 // only ever produces ONE next ray, and only ~14 % of the 1080p paths enter the medium at all, so the wavefront form degenerates
 // into dozens of launches over a few ten thousand rays each plus a host poll per iteration (workload c5: 105 launches per wave,
-// 10.5 M closest hits of which 8.3 M are primary). Here one thread runs its path to completion: iteration, inline closest hit,
-// iteration, ... — the same draws in the same order. One launch per wave, no host round trip.
+// 10.5 M closest hits of which 8.3 M are primary). Here every lane owns one path at a time and runs it to completion — the same
+// draws in the same order — and the warp is a small state machine around the one hot loop, the delta-tracking walk:
+//   kLanePre   : the lane has a ray + hit: volumePre(), then kLaneTrack, kLanePost or finished
+//   kLaneTrack : trackStep() executed in lockstep by every tracking lane, kTrackSteps steps per vote, while at least
+//                `threshold` lanes are still walking (walk lengths differ by orders of magnitude: run per thread the loop
+//                keeps 7.6 of 32 lanes busy, ncu profiles/r01_notes.md)
+//   kLanePost  : volumePost(), inline closest hit of the next ray, back to kLanePre or finished
+//   kLaneIdle  : refilled from the compact bounce-0 queue (one atomic per 32 entries per warp)
+// One launch per wave, no host round trip.
+enum { kLaneIdle = 0, kLanePre, kLaneTrack, kLanePost };
+constexpr int kTrackSteps = 4;
+constexpr int kMediaSmem = 4;
 template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, unsigned long long* stats)
+__global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, int threshold, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
+    __shared__ DMedium s_media[kMediaSmem];
+    __shared__ DGrid s_grids[kMediaSmem];
+    const bool staged = sc.nMedia <= kMediaSmem && sc.nGrids <= kMediaSmem;
+    if (staged) {
+        if (int(threadIdx.x) < sc.nMedia) s_media[threadIdx.x] = sc.media[threadIdx.x];
+        if (int(threadIdx.x) < sc.nGrids) s_grids[threadIdx.x] = sc.grids[threadIdx.x];
+        __syncthreads();
+    }
+    const DMedium* media = staged ? s_media : sc.media;
+    const DGrid* grids = staged ? s_grids : sc.grids;
     uint32_t* ctrl = q.ctrl;
     const uint32_t n = ctrl[kCtrlRays];
     const bool nee = (w.integrator == XRTG_INT_VOLUME_NEE);
+    const uint32_t lane = laneId();
     uint32_t steps = 0, nClosest = 0;
     TraceCounters tc;
-    uint32_t resNext = 0, resEnd = 0, base;
-    while (warpNextBatch<32>(ctrl + kCtrlFetchShade, n, resNext, resEnd, base)) {
-        const uint32_t i = base + laneId();
-        if (i >= n) continue;
-        const float4 r0 = q.q0[0][i], r1 = q.q1[0][i], r2 = q.q2[0][i], hv = q.hits[i];
-        const uint32_t pid = uint32_t(__float_as_int(r2.y));
-        int depth = __float_as_int(r2.z);
-        V3 o = xyz(r0), d = xyz(r1), T = mk(r0.w, r1.w, r2.x);
-        Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
-        Rng rng;
-        rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
-        float4 rad = q.radiance[pid];
-        bool dirty = false;
-        for (int it = 0; it < maxIter; ++it) {
-            V3 no, nd, nT, contrib;
-            bool hasContrib;
-            const bool cont = volumeIteration<COUNT>(sc, w, nee, brute != 0, o, d, T, h, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd, nT,
-                                                     hasContrib, contrib);
-            if (hasContrib) { rad.x += contrib.x; rad.y += contrib.y; rad.z += contrib.z; dirty = true; }
-            if (!cont || it + 1 == maxIter) break;
-            o = no; d = nd; T = nT;
-            closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
-            ++nClosest;
-        }
+    // per-lane path state
+    int state = kLaneIdle, depth = 0, it = 0, mi = -1;
+    uint32_t pid = 0;
+    V3 o = mk(0.f), d = mk(0.f), T = mk(0.f);
+    Hit h{FLT_MAX, 0.f, 0.f, -1};
+    Rng rng;
+    TrackState ts;
+    TrackResult r;
+    float4 rad = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool dirty = false, exhausted = false;
+    uint32_t resNext = 0, resEnd = 0;
+    auto finish = [&]() { // the lane's path is over
         rng.close();
         if (dirty) q.radiance[pid] = rad;
+        state = kLaneIdle;
+    };
+    auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; dirty = true; };
+    while (true) {
+        // ---- refill idle lanes from the warp's reservation of 32 consecutive queue entries ----
+        const uint32_t need = __ballot_sync(0xffffffffu, state == kLaneIdle);
+        if (need != 0 && !exhausted) {
+            const uint32_t nNeed = __popc(need), rank = __popc(need & ((1u << lane) - 1u)), left = resEnd - resNext;
+            uint32_t nb = 0;
+            if (nNeed > left) {
+                if (lane == 0) nb = atomicAdd(ctrl + kCtrlFetchShade, 32u);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb >= n) exhausted = true;
+            }
+            const uint32_t i = rank < left ? resNext + rank : nb + (rank - left);
+            if (nNeed > left) { resNext = nb + (nNeed - left); resEnd = nb + 32u; }
+            else resNext += nNeed;
+            if (state == kLaneIdle && i < n) {
+                const float4 r0 = q.q0[0][i], r1 = q.q1[0][i], r2 = q.q2[0][i], hv = q.hits[i];
+                pid = uint32_t(__float_as_int(r2.y));
+                depth = __float_as_int(r2.z);
+                o = xyz(r0); d = xyz(r1); T = mk(r0.w, r1.w, r2.x);
+                h = Hit{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+                rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+                rad = q.radiance[pid];
+                dirty = false;
+                it = 0;
+                state = kLanePre;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, state != kLaneIdle) == 0) break;
+        // ---- lanes between walks: epilogue of the last walk, closest hit of the next ray, prologue of the next walk ----
+        if (state == kLanePost) {
+            V3 no, nd, nT, contrib;
+            bool hasContrib;
+            const bool cont = volumePost<COUNT>(sc, w, media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd,
+                                                nT, hasContrib, contrib);
+            if (hasContrib) add(contrib);
+            if (!cont || ++it == maxIter) finish();
+            else {
+                o = no; d = nd; T = nT;
+                closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+                ++nClosest;
+                state = kLanePre;
+            }
+        }
+        if (state == kLanePre) {
+            V3 contrib;
+            bool hasContrib;
+            const int what = volumePre(sc, media, grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
+            if (hasContrib) add(contrib);
+            if (what == kVolEnd) finish();
+            else state = what == kVolTrack ? kLaneTrack : kLanePost;
+        }
+        // ---- the walk: every tracking lane takes kTrackSteps steps per vote ----
+        const uint32_t pending = __ballot_sync(0xffffffffu, state == kLanePre || state == kLanePost || (state == kLaneIdle && !exhausted));
+        const uint32_t thr = pending ? uint32_t(threshold) : 1u;
+        uint32_t busy = __popc(__ballot_sync(0xffffffffu, state == kLaneTrack));
+        while (busy >= thr && busy > 0) {
+#pragma unroll 1
+            for (int k = 0; k < kTrackSteps; ++k)
+                if (state == kLaneTrack) {
+                    const DMedium& m = media[mi];
+                    if (trackStep(m, grids[m.grid], o, d, T, ts, rng, r, steps)) state = kLanePost;
+                }
+            busy = __popc(__ballot_sync(0xffffffffu, state == kLaneTrack));
+        }
     }
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatSteps, steps);
@@ -2083,19 +2206,19 @@ inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& 
     if (count) k_shade_volume<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
     else k_shade_volume<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
 }
-inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, bool count,
+inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, int threshold, bool count,
                               unsigned long long* stats)
 {
     static thread_local int g0 = 0, g1 = 0, g2 = 0, sel = 0;
     if (!g0) {
-        g0 = gridFor((const void*)k_volume_paths<false, 4>); g1 = gridFor((const void*)k_volume_paths<true, 4>);
-        g2 = gridFor((const void*)k_volume_paths<false, 5>);
+        g0 = gridFor((const void*)k_volume_paths<false, 5>); g1 = gridFor((const void*)k_volume_paths<true, 4>);
+        g2 = gridFor((const void*)k_volume_paths<false, 4>);
         const char* e = std::getenv("XRT_VOLUME_MINB");
-        sel = e ? std::atoi(e) : 5;
+        sel = e ? std::atoi(e) : 4;
     }
-    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
-    else if (sel == 5) k_volume_paths<false, 5><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
-    else k_volume_paths<false, 4><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, stats);
+    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
+    else if (sel == 4) k_volume_paths<false, 4><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
+    else k_volume_paths<false, 5><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
 }
 inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
 {

@@ -639,7 +639,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
                 tm.end();
                 tm.begin(kStageShade);
-                K.volumePaths(st, s->ds, q, w, brute, nIter, envInt("XRT_THR_VOL", 20), count, dstats); ++launches; ++nShade;
+                K.volumePaths(st, s->ds, q, w, brute, nIter, envInt("XRT_THR_VOL", 16), envInt("XRT_SPV_VOL", 2), count, dstats); ++launches; ++nShade;
                 tm.end();
                 break;
             }

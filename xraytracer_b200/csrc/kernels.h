@@ -20,7 +20,7 @@ struct KernelTable {
     void (*shadeVolume)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, bool brute, bool count,
                         unsigned long long* stats);
     // shallow BVHs: every volume path run to completion in one launch (k_volume_paths)
-    void (*volumePaths)(cudaStream_t, const DScene&, const DQueues&, const DWave&, bool brute, int maxIter, int refillThreshold, bool count,
+    void (*volumePaths)(cudaStream_t, const DScene&, const DQueues&, const DWave&, bool brute, int maxIter, int refillThreshold, int stepsPerVote, bool count,
                         unsigned long long* stats);
     void (*accumulate)(cudaStream_t, const DQueues&, const DWave&, float* accum, unsigned long long* stats);
     void (*finalize)(cudaStream_t, const float* accum, float* out, size_t n, float divisor);

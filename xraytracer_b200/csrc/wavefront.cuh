@@ -114,6 +114,12 @@ struct Rng {
         if constexpr (kExact) { mti[pix] = idx; return 0; }
         else return ctr;
     }
+    // Throughput instantiation: skip to the start of the next 4-draw block, so that lanes walking in lockstep (trackStep) all
+    // compute their Philox block in the same instruction instead of one quarter of the lanes at a time. No-op for mt19937.
+    __device__ __forceinline__ void alignBlock()
+    {
+        if constexpr (!kExact) ctr = (ctr + 3u) & ~3u;
+    }
     __device__ __forceinline__ void philox(uint32_t block)
     {
         uint32_t c0 = sample, c1 = block, c2 = 0x243F6A88u, c3 = 0x85A308D3u, a = k0, b = k1;
@@ -1761,6 +1767,7 @@ __device__ __forceinline__ bool trackStep(const DMedium& m, const DGrid& g, V3 o
     const V3 maj = mk(m.majorant);
     V3 sigma_a = absC * ts.density;
     ++steps;
+    rng.alignBlock(); // the three draws of one step come from one Philox block
     V3 pmf;
     const uint32_t ch = sampleWavelength(rayT * ts.tt, (maj - sigma_a) * m.invMajorant, rng, pmf);
     const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
@@ -1964,17 +1971,16 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
 // 10.5 M closest hits of which 8.3 M are primary). Here every lane owns one path at a time and runs it to completion — the same
 // draws in the same order — and the warp is a small state machine around the one hot loop, the delta-tracking walk:
 //   kLanePre   : the lane has a ray + hit: volumePre(), then kLaneTrack, kLanePost or finished
-//   kLaneTrack : trackStep() executed in lockstep by every tracking lane, kTrackSteps steps per vote, while at least
+//   kLaneTrack : trackStep() executed in lockstep by every tracking lane, stepsPerVote steps per vote, while at least
 //                `threshold` lanes are still walking (walk lengths differ by orders of magnitude: run per thread the loop
 //                keeps 7.6 of 32 lanes busy, ncu profiles/r01_notes.md)
 //   kLanePost  : volumePost(), inline closest hit of the next ray, back to kLanePre or finished
 //   kLaneIdle  : refilled from the compact bounce-0 queue (one atomic per 32 entries per warp)
 // One launch per wave, no host round trip.
 enum { kLaneIdle = 0, kLanePre, kLaneTrack, kLanePost };
-constexpr int kTrackSteps = 4;
 constexpr int kMediaSmem = 4;
 template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, int threshold, unsigned long long* stats)
+__global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, int threshold, int stepsPerVote, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
     __shared__ DMedium s_media[kMediaSmem];
@@ -2067,7 +2073,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
         uint32_t busy = __popc(__ballot_sync(0xffffffffu, state == kLaneTrack));
         while (busy >= thr && busy > 0) {
 #pragma unroll 1
-            for (int k = 0; k < kTrackSteps; ++k)
+            for (int k = 0; k < stepsPerVote; ++k)
                 if (state == kLaneTrack) {
                     const DMedium& m = media[mi];
                     if (trackStep(m, grids[m.grid], o, d, T, ts, rng, r, steps)) state = kLanePost;
@@ -2206,7 +2212,7 @@ inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& 
     if (count) k_shade_volume<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
     else k_shade_volume<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
 }
-inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, int threshold, bool count,
+inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, int threshold, int stepsPerVote, bool count,
                               unsigned long long* stats)
 {
     static thread_local int g0 = 0, g1 = 0, g2 = 0, sel = 0;
@@ -2216,9 +2222,9 @@ inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& 
         const char* e = std::getenv("XRT_VOLUME_MINB");
         sel = e ? std::atoi(e) : 4;
     }
-    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
-    else if (sel == 4) k_volume_paths<false, 4><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
-    else k_volume_paths<false, 5><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stats);
+    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    else if (sel == 4) k_volume_paths<false, 4><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    else k_volume_paths<false, 5><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
 }
 inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
 {

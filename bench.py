@@ -289,12 +289,12 @@ def main():
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
     # aggregate ray counts over ranks
-    agg = np.zeros(11, dtype=np.float64)
+    agg = np.zeros(12, dtype=np.float64)
     for st in stats:
         if st:
             agg += np.array([st["closest_rays"], st["shadow_rays"], st["kernel_launches"], st["extend_ms"], st["shade_ms"],
                              st["connect_ms"], st["extend_launches"], st["tracking_steps"], st["primary_hits"],
-                             st["bounce_entries"], st["bounce_launches"]], dtype=np.float64)
+                             st["bounce_entries"], st["bounce_launches"], st["shade_launches"]], dtype=np.float64)
     if world > 1:
         t = torch.tensor(agg, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -341,7 +341,9 @@ def main():
         paths_r0 = float(W) * H * my_spp * args.steps
         traffic = None
         # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, summarised by scripts/summarize_profiles.py)
-        tp = ROOT / "profiles" / (f"bounce_traffic_{args.workload}.json" if agg[9] > 0 else f"extend_traffic_{args.workload}.json")
+        is_volume = wl["integrator"].startswith("volume")
+        tp = ROOT / "profiles" / (f"bounce_traffic_{args.workload}.json" if agg[9] > 0 else
+                                  (f"volume_traffic_{args.workload}.json" if is_volume else f"extend_traffic_{args.workload}.json"))
         if tp.exists():
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
@@ -371,6 +373,21 @@ def main():
                         "launches": int(launches_b), "avg_launch_ms": b_ms / launches_b, "share_of_step": share,
                         "note": "instruction-issue bound (ncu: ~65 % issue-active at 31 of 32 lanes), not memory bound: a 36-triangle scene cannot "
                                 "saturate HBM; the fraction says how far the queue traffic is from the HBM roof"}
+        elif wl["integrator"].startswith("volume") and agg[7] > 0 and agg[4] > agg[3]:
+            # ---- volume workloads: the dominant kernel is the path kernel k_volume_paths (delta tracking, run to completion) ----
+            # achieved = algorithmic bytes / CUDA-event time of its launches, rank 0: SURVEY §8(d)'s 8 voxels x 4 B = 32 B per tracking
+            # step + per path that enters it 64 B in (ray + hit record) and a 16 B radiance read-modify-write. The voxel gathers of
+            # a 64 MiB grid are served by L2 (ncu: ~80 % L2 hit rate), so DRAM traffic is far below this figure.
+            v_ms, v_launches = agg[4], max(agg[11], 1)
+            hbm_bytes = agg[7] * 32.0 + agg[8] * 96.0
+            achieved = hbm_bytes / (v_ms * 1e-3) / 1e9 if v_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": "k_volume_paths (volume paths run to completion: lockstep delta-tracking walk + inline closest hits)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": hbm_bytes / v_launches, "tracking_steps_per_launch": agg[7] / v_launches,
+                        "tracking_steps_per_s": agg[7] / (v_ms * 1e-3) if v_ms > 0 else 0.0, "paths_per_launch": agg[8] / v_launches,
+                        "launches": int(v_launches), "avg_launch_ms": v_ms / v_launches, "share_of_step": share,
+                        "note": "instruction-issue bound on the tracking step (3 draws, log, 3 exp, 8 voxel gathers + trilinear weights per "
+                                "step); the gathers hit L2, so the HBM fraction only says how far the walk is from the memory roof"}
         else:
             # ---- deep BVH: roofline of the dominant stage, closest-hit traversal, rank 0's launches ----
             # (k_primary = ray generation fused with the bounce-0 hit on shallow BVHs, k_extend_simple / k_trace<closest> after)

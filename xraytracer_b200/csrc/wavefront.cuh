@@ -1749,11 +1749,14 @@ __device__ __forceinline__ bool sampleHomogeneous(const DMedium& m, V3 o, V3 d, 
 struct TrackState {
     float t, t1, density; // density = multiplier * grid density at the current position (sigma_a of the next wavelength pick)
     V3 tt;                // throughput accumulated by the walk
+    float sd;             // last sampled distance and wavelength pmf: what trackFinish() needs from the final step
+    V3 pmf;
 };
 struct TrackResult {
     V3 pos, dir, thr;
     bool scattered;
 };
+enum { kTrackContinue = 0, kTrackExit = 1, kTrackScatter = 2 };
 __device__ __forceinline__ void trackBegin(const DMedium& m, const DGrid& g, V3 o, V3 d, float tEntry, float t1, TrackState& ts)
 {
     ts.tt = mk(1.f);
@@ -1761,49 +1764,59 @@ __device__ __forceinline__ void trackBegin(const DMedium& m, const DGrid& g, V3 
     ts.t1 = t1;
     ts.density = m.densityMul * gridDensity(g, o + tEntry * d);
 }
-__device__ __forceinline__ bool trackStep(const DMedium& m, const DGrid& g, V3 o, V3 d, V3 rayT, TrackState& ts, Rng& rng, TrackResult& r, uint32_t& steps)
+// One iteration of the loop up to the decision (medium.cpp:62-72, :84-99): null collisions update the throughput and continue;
+// leaving the medium or a real scattering event only RECORD the step (ts.sd, ts.pmf) — the few lanes that end their walk in a
+// given step would otherwise run the long exit / scatter epilogues at 2-3 of 32 lanes inside the lockstep loop.
+__device__ __forceinline__ int trackStep(const DMedium& m, const DGrid& g, V3 o, V3 d, V3 rayT, TrackState& ts, Rng& rng, uint32_t& steps)
 {
     const V3 absC = v3(m.sigma_a), scatC = v3(m.sigma_s);
     const V3 maj = mk(m.majorant);
     V3 sigma_a = absC * ts.density;
     ++steps;
     rng.alignBlock(); // the three draws of one step come from one Philox block
-    V3 pmf;
-    const uint32_t ch = sampleWavelength(rayT * ts.tt, (maj - sigma_a) * m.invMajorant, rng, pmf);
-    const float sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
-    ts.t += sd;
-    if (ts.t > ts.t1 - kRayEps) {
-        r.pos = o + (ts.t1 + kRayEps) * d; r.dir = d;
-        const float rest = sd - (ts.t - (ts.t1 - kRayEps));
-        const V3 tr = analyticTr(rest, maj);
-        const V3 pdf = pmf * tr;
-        ts.tt = ts.tt * (tr / (pdf.x + pdf.y + pdf.z));
-        r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;
-        r.scattered = false;
-        return true;
-    }
+    const uint32_t ch = sampleWavelength(rayT * ts.tt, (maj - sigma_a) * m.invMajorant, rng, ts.pmf);
+    ts.sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
+    ts.t += ts.sd;
+    if (ts.t > ts.t1 - kRayEps) return kTrackExit;
     ts.density = m.densityMul * gridDensity(g, o + ts.t * d);
     const V3 sigma_s = scatC * ts.density;
     sigma_a = absC * ts.density;
     const V3 sigma_n = maj - sigma_a - sigma_s;
     const V3 P_s = sigma_s / (sigma_s + sigma_n);
+    if (rng.next() < comp(P_s, ch)) return kTrackScatter;
     const V3 P_n = sigma_n / (sigma_s + sigma_n);
-    if (rng.next() < comp(P_s, ch)) {
+    const V3 tr = analyticTr(ts.sd, maj);
+    const V3 pdf_distance = m.majorant * tr;
+    const V3 pdf = ts.pmf * pdf_distance * P_n;
+    ts.tt = ts.tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+    return kTrackContinue;
+}
+// The epilogue of the walk: medium.cpp:73-83 (left the medium) or :100-112 (scattered, new direction from the phase function)
+__device__ __forceinline__ void trackFinish(const DMedium& m, V3 o, V3 d, TrackState& ts, int how, Rng& rng, TrackResult& r)
+{
+    const V3 maj = mk(m.majorant);
+    if (how == kTrackExit) {
+        r.pos = o + (ts.t1 + kRayEps) * d; r.dir = d;
+        const float rest = ts.sd - (ts.t - (ts.t1 - kRayEps));
+        const V3 tr = analyticTr(rest, maj);
+        const V3 pdf = ts.pmf * tr;
+        ts.tt = ts.tt * (tr / (pdf.x + pdf.y + pdf.z));
+        r.scattered = false;
+    }
+    else {
+        const V3 absC = v3(m.sigma_a), scatC = v3(m.sigma_s);
+        const V3 sigma_s = scatC * ts.density, sigma_a = absC * ts.density;
+        const V3 sigma_n = maj - sigma_a - sigma_s;
+        const V3 P_s = sigma_s / (sigma_s + sigma_n);
         r.pos = o + ts.t * d;
         hgSample(m.g, d, rng, r.dir);
-        const V3 tr = analyticTr(sd, maj);
+        const V3 tr = analyticTr(ts.sd, maj);
         const V3 pdf_distance = m.majorant * tr;
-        const V3 pdf = pmf * pdf_distance * P_s;
+        const V3 pdf = ts.pmf * pdf_distance * P_s;
         ts.tt = ts.tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
-        r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;
         r.scattered = true;
-        return true;
     }
-    const V3 tr = analyticTr(sd, maj);
-    const V3 pdf_distance = m.majorant * tr;
-    const V3 pdf = pmf * pdf_distance * P_n;
-    ts.tt = ts.tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
-    return false;
+    r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;
 }
 
 // Medium::transmittance: analytic (medium.h:134-139) or ratio tracking (medium.h:360-386)
@@ -1950,7 +1963,9 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
                 if (what == kVolTrack) {
                     const DMedium m = sc.media[mi];
                     const DGrid g = sc.grids[m.grid];
-                    while (!trackStep(m, g, o, d, T, ts, rng, r, steps)) {}
+                    int how;
+                    while ((how = trackStep(m, g, o, d, T, ts, rng, steps)) == kTrackContinue) {}
+                    trackFinish(m, o, d, ts, how, rng, r);
                 }
                 wantRay = volumePost<COUNT>(sc, w, sc.media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, extraClosest, no, nd,
                                             nT, hasContrib, contrib);
@@ -1974,25 +1989,23 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
 //   kLaneTrack : trackStep() executed in lockstep by every tracking lane, stepsPerVote steps per vote, while at least
 //                `threshold` lanes are still walking (walk lengths differ by orders of magnitude: run per thread the loop
 //                keeps 7.6 of 32 lanes busy, ncu profiles/r01_notes.md)
+//   kLaneWalked: trackFinish() — the exit / scatter epilogue, outside the lockstep loop
 //   kLanePost  : volumePost(), inline closest hit of the next ray, back to kLanePre or finished
 //   kLaneIdle  : refilled from the compact bounce-0 queue (one atomic per 32 entries per warp)
 // One launch per wave, no host round trip.
-enum { kLaneIdle = 0, kLanePre, kLaneTrack, kLanePost };
-constexpr int kMediaSmem = 4;
+enum { kLaneIdle = 0, kLanePre, kLaneTrack, kLaneWalked, kLanePost };
+constexpr int kMediaSmem = 8; // media / grids staged in shared memory by k_volume_paths (the host falls back to the wavefront form above that)
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, int threshold, int stepsPerVote, unsigned long long* stats)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
     __shared__ DMedium s_media[kMediaSmem];
     __shared__ DGrid s_grids[kMediaSmem];
-    const bool staged = sc.nMedia <= kMediaSmem && sc.nGrids <= kMediaSmem;
-    if (staged) {
-        if (int(threadIdx.x) < sc.nMedia) s_media[threadIdx.x] = sc.media[threadIdx.x];
-        if (int(threadIdx.x) < sc.nGrids) s_grids[threadIdx.x] = sc.grids[threadIdx.x];
-        __syncthreads();
-    }
-    const DMedium* media = staged ? s_media : sc.media;
-    const DGrid* grids = staged ? s_grids : sc.grids;
+    if (int(threadIdx.x) < min(sc.nMedia, kMediaSmem)) s_media[threadIdx.x] = sc.media[threadIdx.x];
+    if (int(threadIdx.x) < min(sc.nGrids, kMediaSmem)) s_grids[threadIdx.x] = sc.grids[threadIdx.x];
+    __syncthreads();
+    const DMedium* media = s_media;
+    const DGrid* grids = s_grids;
     uint32_t* ctrl = q.ctrl;
     const uint32_t n = ctrl[kCtrlRays];
     const bool nee = (w.integrator == XRTG_INT_VOLUME_NEE);
@@ -2000,7 +2013,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
     uint32_t steps = 0, nClosest = 0;
     TraceCounters tc;
     // per-lane path state
-    int state = kLaneIdle, depth = 0, it = 0, mi = -1;
+    int state = kLaneIdle, depth = 0, it = 0, mi = -1, walkEnd = kTrackContinue;
     uint32_t pid = 0;
     V3 o = mk(0.f), d = mk(0.f), T = mk(0.f);
     Hit h{FLT_MAX, 0.f, 0.f, -1};
@@ -2045,6 +2058,10 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
         }
         if (__ballot_sync(0xffffffffu, state != kLaneIdle) == 0) break;
         // ---- lanes between walks: epilogue of the last walk, closest hit of the next ray, prologue of the next walk ----
+        if (state == kLaneWalked) {
+            trackFinish(media[mi], o, d, ts, walkEnd, rng, r);
+            state = kLanePost;
+        }
         if (state == kLanePost) {
             V3 no, nd, nT, contrib;
             bool hasContrib;
@@ -2068,7 +2085,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
             else state = what == kVolTrack ? kLaneTrack : kLanePost;
         }
         // ---- the walk: every tracking lane takes kTrackSteps steps per vote ----
-        const uint32_t pending = __ballot_sync(0xffffffffu, state == kLanePre || state == kLanePost || (state == kLaneIdle && !exhausted));
+        const uint32_t pending = __ballot_sync(0xffffffffu, state == kLanePre || state == kLanePost || state == kLaneWalked || (state == kLaneIdle && !exhausted));
         const uint32_t thr = pending ? uint32_t(threshold) : 1u;
         uint32_t busy = __popc(__ballot_sync(0xffffffffu, state == kLaneTrack));
         while (busy >= thr && busy > 0) {
@@ -2076,7 +2093,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
             for (int k = 0; k < stepsPerVote; ++k)
                 if (state == kLaneTrack) {
                     const DMedium& m = media[mi];
-                    if (trackStep(m, grids[m.grid], o, d, T, ts, rng, r, steps)) state = kLanePost;
+                    walkEnd = trackStep(m, grids[m.grid], o, d, T, ts, rng, steps);
+                    if (walkEnd != kTrackContinue) state = kLaneWalked;
                 }
             busy = __popc(__ballot_sync(0xffffffffu, state == kLaneTrack));
         }

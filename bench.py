@@ -67,7 +67,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -87,9 +87,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.2:
-                continue
+        inside = [(ts, line) for ts, line in self.rows if t0 <= ts <= t1 + 0.2]
+        if not inside and self.rows:   # timed region shorter than the sampling period: the sample closest to it
+            inside = [min(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+        for ts, line in inside:
             parts = [p.strip() for p in line.split(",")]
             try:
                 sm.append(float(parts[0]))

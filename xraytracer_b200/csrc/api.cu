@@ -600,6 +600,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     const int thrExt0 = envInt("XRT_THR_EXT0", deep ? 1 : 0), thrExt = envInt("XRT_THR_EXT", deep ? 16 : 0);
     const int thrCon = envInt("XRT_THR_CON", deep ? 16 : 0);
     const int spv = envInt("XRT_SPV", deep ? 4 : 1);
+    const int leafThr = envInt("XRT_LEAF_THR", 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
     const int missMode = integ == XRTG_INT_DIRECT ? 1 : (integ == XRTG_INT_WHITTED ? 2 : 0);
     // Small scenes (<= 64 triangles, shallow BVH): incoherent rays — every closest-hit bounce after the primary one and all
     // shadow rays — test every triangle from shared memory instead of walking the BVH; the warp stays converged and it is
@@ -656,7 +657,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             }
             tm.begin(kStageExtend);
             if (b == 0 && fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats);
-            else K.extend(st, s->ds, q, src, b, brute ? 1 : ((bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? thrExt0 : thrExt, spv);
+            else K.extend(st, s->ds, q, src, b, brute ? 1 : ((bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? thrExt0 : thrExt, spv, leafThr);
             ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
@@ -666,7 +667,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             tm.end();
             if (hasShadow) {
                 tm.begin(kStageConnect);
-                K.connect(st, s->ds, q, b, brute ? 1 : (bruteShadow ? 2 : 0), count, dstats, thrCon, spv); ++launches; ++nConnect;
+                K.connect(st, s->ds, q, b, brute ? 1 : (bruteShadow ? 2 : 0), count, dstats, thrCon, spv, leafThr); ++launches; ++nConnect;
                 tm.end();
             }
             if (volume) {
@@ -887,7 +888,7 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
     unsigned long long* dstats = static_cast<unsigned long long*>(s->stats.p);
     CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
     K.raygen(st, makeCamera(cam), q, w, dj);
-    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0 ? 1 : 0, false, dstats, 16, 1);
+    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0 ? 1 : 0, false, dstats, 16, 1, 8);
     CU(cudaGetLastError());
     // hits are indexed by path id = s * nPixels + pixel; the ABI wants [(pixel * spp) + s]
     std::vector<float4> tmp(nPaths);

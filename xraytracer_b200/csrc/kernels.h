@@ -11,9 +11,9 @@ struct KernelTable {
     void (*primary)(cudaStream_t, const DScene&, const DCamera&, const DQueues&, const DWave&, bool brute, int missMode, bool count,
                     unsigned long long* stats);
     void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, int brute /*0 BVH, 1 brute force, 2 small-scene smem*/, bool count, unsigned long long* stats,
-                   int refillThreshold, int stepsPerVote);
+                   int refillThreshold, int stepsPerVote, int leafThreshold);
     void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, int brute, bool count, unsigned long long* stats,
-                    int refillThreshold, int stepsPerVote);
+                    int refillThreshold, int stepsPerVote, int leafThreshold);
     void (*shadeSurface)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce);
     // small scenes: shade + connect + extend of one bounce in one kernel (k_bounce_small)
     void (*bounceSmall)(cudaStream_t, const DScene&, const DQueues&, const DWave&, int src, int bounce, unsigned long long* stats);

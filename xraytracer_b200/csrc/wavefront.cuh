@@ -666,39 +666,40 @@ __device__ __forceinline__ void beginTraversal(RayState& r, const DScene& sc)
     r.node = sc.nTris > 0 ? 0 : kSentinel;
 }
 
-// One step of the state machine: one inner node (if the lane is at one) and then one leaf (if that is where the lane
-// now stands). Returns true when ANY and an occluder was found.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ bool traverseStep(const DScene& sc, RayState& r, int* sstack, int* lstack, TraceCounters& tc)
+// The two kinds of step of the state machine. nodeStep: one inner node (both children's boxes, nearer child first, farther one
+// pushed). leafStep: the 1-4 triangles of one leaf; returns true when ANY and an occluder was found.
+__device__ __forceinline__ bool atInner(const RayState& r) { return r.node >= 0 && r.node != kSentinel; }
+template <bool COUNT>
+__device__ __forceinline__ void nodeStep(const DScene& sc, RayState& r, int* sstack, int* lstack, TraceCounters& tc)
 {
-    if (r.node >= 0 && r.node != kSentinel) {
-        const float4* __restrict__ nodes = sc.nodes;
-        const float4 n0 = __ldg(nodes + 4 * r.node), n1 = __ldg(nodes + 4 * r.node + 1), n2 = __ldg(nodes + 4 * r.node + 2);
-        const int4 n3 = __ldg(reinterpret_cast<const int4*>(nodes + 4 * r.node + 3));
-        if (COUNT) tc.nodes++;
-        float t0n, t1n;
-        const bool h0 = (n3.z >= 0) && slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.idir, r.ood, r.h.t, t0n);
-        const bool h1 = (n3.w >= 0) && slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r.idir, r.ood, r.h.t, t1n);
-        const int e0 = n3.z > 0 ? ~((n3.x << 2) | (n3.z - 1)) : n3.x;
-        const int e1 = n3.w > 0 ? ~((n3.y << 2) | (n3.w - 1)) : n3.y;
-        if (h0 && h1) {
-            const bool swap = t1n < t0n; // nearer child first
-            r.node = swap ? e1 : e0;
-            stackPush(sstack, lstack, r.sp, swap ? e0 : e1);
-        }
-        else if (h0) r.node = e0;
-        else if (h1) r.node = e1;
-        else r.node = stackPop(sstack, lstack, r.sp);
-    }
-    if (r.node < 0) {
-        const int code = ~r.node;
-        const int first = code >> 2, cnt = (code & 3) + 1;
-        const float4* __restrict__ tris = triArray(sc, false);
-        for (int i = 0; i < cnt; ++i) {
-            if (COUNT) tc.tris++;
-            if (triangleRecord<ANY, true>(tris + kTriF4 * (first + i), r.o, r.d, r.h, r.minId)) return true;
-        }
-        r.node = stackPop(sstack, lstack, r.sp);
+    const float4* __restrict__ nodes = sc.nodes;
+    const float4 n0 = __ldg(nodes + 4 * r.node), n1 = __ldg(nodes + 4 * r.node + 1), n2 = __ldg(nodes + 4 * r.node + 2);
+    const int4 n3 = __ldg(reinterpret_cast<const int4*>(nodes + 4 * r.node + 3));
+    if (COUNT) tc.nodes++;
+    // both slab tests unconditionally and the decisions as predicates / selects: the short-circuit form compiled into four
+    // divergent branches per node (empty slots have count < 0; their inverted boxes must still be masked explicitly)
+    float t0n, t1n;
+    const bool s0 = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, r.idir, r.ood, r.h.t, t0n);
+    const bool s1 = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, r.idir, r.ood, r.h.t, t1n);
+    const bool h0 = s0 & (n3.z >= 0), h1 = s1 & (n3.w >= 0);
+    const int e0 = n3.z > 0 ? ~((n3.x << 2) | (n3.z - 1)) : n3.x;
+    const int e1 = n3.w > 0 ? ~((n3.y << 2) | (n3.w - 1)) : n3.y;
+    const bool both = h0 & h1;
+    const bool swap = both & (t1n < t0n); // nearer child first
+    const int nearE = (swap | !h0) ? e1 : e0;
+    if (both) stackPush(sstack, lstack, r.sp, swap ? e0 : e1);
+    if (h0 | h1) r.node = nearE;
+    else r.node = stackPop(sstack, lstack, r.sp);
+}
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool leafTest(const DScene& sc, RayState& r, int leafCode, TraceCounters& tc)
+{
+    const int code = ~leafCode;
+    const int first = code >> 2, cnt = (code & 3) + 1;
+    const float4* __restrict__ tris = triArray(sc, false);
+    for (int i = 0; i < cnt; ++i) {
+        if (COUNT) tc.tris++;
+        if (triangleRecord<ANY, true>(tris + kTriF4 * (first + i), r.o, r.d, r.h, r.minId)) return true;
     }
     return false;
 }
@@ -706,7 +707,7 @@ __device__ __forceinline__ bool traverseStep(const DScene& sc, RayState& r, int*
 // anyOut != nullptr (parity hook): write the occlusion flag instead of adding the contribution.
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_trace(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats, float4* anyOut,
-                                                  int refillThreshold, int stepsPerVote)
+                                                  int refillThreshold, int stepsPerVote, int leafThreshold)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
     int lstack[kStackLocal];
@@ -772,17 +773,25 @@ __global__ void __launch_bounds__(kBlock) k_trace(DScene sc, DQueues q, int src,
         if (__ballot_sync(0xffffffffu, active) == 0) break;
         const uint32_t threshold = exhausted ? 1u : uint32_t(refillThreshold);
         // ---- traverse until too few lanes are still busy ----
+        // Leaves are POSTPONED: a lane that reaches a leaf waits until at least `leafThreshold` lanes of the warp stand at one (or
+        // no lane has an inner node left), then they test their triangles together: run immediately, the triangle code executed
+        // at 4 of 32 lanes (about 2 lanes reach a leaf per node step; ncu source view, profiles/r01_notes.md). Measured on the
+        // 1 M-triangle scene: threshold 1 / 4 / 8 / 12 / 16 -> 1378 / 1414 / 1376 / 1330 / 1251 Msamples/s; parking the leaf and
+        // walking on instead of waiting (speculative traversal) was no better (1366 at best).
         uint32_t busy;
         do {
-          for (int sv = 0; sv < stepsPerVote; ++sv)
-            if (active) {
-                bool fin = (r.node == kSentinel);
-                if (!fin) {
-                    const bool occ = traverseStep<ANY, COUNT>(sc, r, sstack, lstack, tc);
-                    if (ANY && occ) { r.h.prim = 1; fin = true; }
-                    else fin = (r.node == kSentinel);
+            for (int sv = 0; sv < stepsPerVote; ++sv) {
+                if (active && atInner(r)) nodeStep<COUNT>(sc, r, sstack, lstack, tc);
+                const bool atLeaf = active && r.node < 0;
+                const uint32_t leafMask = __ballot_sync(0xffffffffu, atLeaf);
+                const uint32_t advancing = __ballot_sync(0xffffffffu, active && atInner(r));
+                if (leafMask != 0 && (__popc(leafMask) >= leafThreshold || advancing == 0)) {
+                    if (atLeaf) {
+                        if (leafTest<ANY, COUNT>(sc, r, r.node, tc)) { r.h.prim = 1; r.node = kSentinel; }
+                        else r.node = stackPop(sstack, lstack, r.sp);
+                    }
                 }
-                if (fin) {
+                if (active && r.node == kSentinel) {
                     if (ANY) {
                         if (r.h.prim == 0) { // analytic spheres that are not emitter proxies (scene.cpp:206)
                             for (int s = 0; s < sc.nSpheres; ++s) {
@@ -2177,7 +2186,7 @@ inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam,
     else k_primary<false><<<g0, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
 }
 inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
-                         int thr, int spv)
+                         int thr, int spv, int leafThr)
 {
     static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
     if (!g0) {
@@ -2189,11 +2198,11 @@ inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, in
         else k_extend_simple<false><<<h0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
         return;
     }
-    if (count) k_trace<false, true><<<g1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv);
-    else k_trace<false, false><<<g0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv);
+    if (count) k_trace<false, true><<<g1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv, leafThr);
+    else k_trace<false, false><<<g0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv, leafThr);
 }
 inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, int brute, bool count, unsigned long long* stats,
-                          int thr, int spv)
+                          int thr, int spv, int leafThr)
 {
     static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
     if (!g0) {
@@ -2205,8 +2214,8 @@ inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, i
         else k_connect_simple<false><<<h0, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
         return;
     }
-    if (count) k_trace<true, true><<<g1, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv);
-    else k_trace<true, false><<<g0, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv);
+    if (count) k_trace<true, true><<<g1, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv, leafThr);
+    else k_trace<true, false><<<g0, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv, leafThr);
 }
 inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce)
 {
@@ -2261,8 +2270,8 @@ inline void launchTraceRays(cudaStream_t st, const DScene& sc, const DQueues& q,
 {
     const int grid = int(std::min<long long>((n + kBlock - 1) / kBlock, 148 * 16));
     k_pack_rays<<<grid > 0 ? grid : 1, kBlock, 0, st>>>(q, org, dir, tmax, uint32_t(n), anyhit ? 1 : 0);
-    if (anyhit) k_trace<true, false><<<gridFor((const void*)k_trace<true, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, out, 16, 1);
-    else k_trace<false, false><<<gridFor((const void*)k_trace<false, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, nullptr, 16, 1);
+    if (anyhit) k_trace<true, false><<<gridFor((const void*)k_trace<true, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, out, 16, 1, 8);
+    else k_trace<false, false><<<gridFor((const void*)k_trace<false, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, nullptr, 16, 1, 8);
 }
 
 } // namespace XRT_NS

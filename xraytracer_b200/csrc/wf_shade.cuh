@@ -1,0 +1,612 @@
+// wf_shade.cuh — part of wavefront.cuh (included inside namespace xrt::XRT_NS, in this order): surface shading: lights, Lambert, k_shade_surface and the fused per-bounce kernel of small scenes (k_bounce_small).
+// ---------------------------------------------------------------------------------------------------------
+// shading
+// ---------------------------------------------------------------------------------------------------------
+struct Surf {
+    V3 pos, ng, ns, dpdu, dpdv, albedo;
+    uint32_t meta;
+    float t1;
+};
+
+// Reconstructs what Mesh::intersect (primitive.cpp:100-110) / Sphere::intersect (primitive.h:112-122) store in
+// IntersectInfo. ng was normalised on the host with the reference's expression; ns is interpolated and NOT
+// re-normalised. A sphere hit leaves dpdu/dpdv at zero (the reference leaves them stale).
+__device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit& h, Surf& s)
+{
+    const float4 p3 = __ldg(sc.prims + 4 * h.prim + 3);
+    s.meta = __float_as_uint(p3.w);
+    s.albedo = xyz(p3);
+    s.pos = o + h.t * d;
+    s.t1 = h.u;
+    const uint32_t kind = s.meta & kMetaKindMask;
+    if (kind == XRTG_OBJ_MESH) {
+        const float4 p0 = __ldg(sc.prims + 4 * h.prim), p1 = __ldg(sc.prims + 4 * h.prim + 1), p2 = __ldg(sc.prims + 4 * h.prim + 2);
+        s.ng = mk(p0.w, p1.w, p2.w);
+        s.ns = xyz(p0) * (1.0f - h.u - h.v) + xyz(p1) * h.u + xyz(p2) * h.v;
+        orthonormalBasis(s.ns, s.dpdu, s.dpdv);
+    }
+    else if (kind == XRTG_OBJ_SPHERE) {
+        const float4 p0 = __ldg(sc.prims + 4 * h.prim);
+        s.ng = normalize(s.pos - xyz(p0));
+        s.ns = s.ng;
+        s.dpdu = mk(0.f); s.dpdv = mk(0.f);
+    }
+    else {
+        s.ng = mk(0.f); s.ns = mk(0.f); s.dpdu = mk(0.f); s.dpdv = mk(0.f);
+    }
+}
+__device__ __forceinline__ bool hasMaterial(const Surf& s) { return (s.meta & kMetaHasMaterial) != 0; }
+__device__ __forceinline__ int lightOf(const Surf& s) { return int((s.meta >> kMetaLightShift) & 0xfffu) - 1; }
+__device__ __forceinline__ int mediumOf(const Surf& s) { return int((s.meta >> kMetaMediumShift) & 0xfffu) - 1; }
+
+// AreaLight::Le (light.h:62-69)
+__device__ __forceinline__ V3 emitted(const DScene& sc, const Surf& s, V3 rayDir)
+{
+    const int li = lightOf(s);
+    if (li < 0) return mk(0.f);
+    return (dot(rayDir, s.ns) < 0) ? xyz(sc.lights[li].Le) : mk(0.f);
+}
+
+// AreaLight::sample: quad light.cpp:59-68, triangle light.cpp:21-30 + :43-47, sphere light.h:158-197.
+// Draw order as compiled by g++ (second-written getNext1D() draws first), pinned by the oracle KATs.
+__device__ __forceinline__ V3 sampleLight(const DLight& L, V3 position, V3& wi, float& pdf, float& tmax, Rng& rng)
+{
+    const int kind = __float_as_int(L.v0_kind.w);
+    const V3 v0 = xyz(L.v0_kind);
+    if (kind == XRTG_LIGHT_QUAD) {
+        const float rb = rng.next();
+        const float ra = rng.next();
+        const V3 d = (v0 + xyz(L.e1_r) * ra + xyz(L.e2) * rb) - position;
+        tmax = length(d);
+        const float dn = dot(d, xyz(L.Ng));
+        if (dn >= 0) return mk(0.f);
+        wi = d / tmax;
+        pdf = (tmax * tmax * tmax) / fabsf(dn);
+        return xyz(L.Le);
+    }
+    if (kind == XRTG_LIGHT_TRIANGLE) {
+        const float v = rng.next();
+        const float u = rng.next();
+        const float su = sqrtf(u);
+        const V3 A = v0, B = xyz(L.v1), C = xyz(L.v2);
+        const V3 p = C + (1.f - su) * (A - C) + (v * su) * (B - C);
+        const V3 d = p - position;
+        tmax = length(d);
+        const float dn = dot(d, xyz(L.Ng));
+        if (dn >= 0) return mk(0.f);
+        wi = d / tmax;
+        pdf = (2.f * tmax * tmax * tmax) / fabsf(dn);
+        return xyz(L.Le);
+    }
+    const float radius = L.e1_r.w;
+    V3 dz = v0 - position;
+    const float dz_len_2 = dot(dz, dz);
+    const float dz_len = sqrtf(dz_len_2);
+    dz = dz / mk(-dz_len);
+    V3 dx, dy;
+    orthonormalBasis(dz, dx, dy);
+    const float sin_theta_max_2 = radius * radius / dz_len_2;
+    const float sin_theta_max = sqrtf(sin_theta_max_2);
+    const float cos_theta_max = sqrtf(smax(0.f, 1.f - sin_theta_max_2));
+    const float cos_theta = 1 + (cos_theta_max - 1) * rng.next();
+    const float sin_theta_2 = 1.f - cos_theta * cos_theta;
+    const float cos_alpha = sin_theta_2 / sin_theta_max + cos_theta * sqrtf(smax(0.0f, 1 - sin_theta_2 / sin_theta_max_2));
+    const float sin_alpha = sqrtf(smax(0.0f, 1 - cos_alpha * cos_alpha));
+    const float phi = 2 * kPI * rng.next();
+    const V3 n = cosf(phi) * sin_alpha * dx + sinf(phi) * sin_alpha * dy + cos_alpha * dz;
+    const V3 p = v0 + n * radius;
+    const V3 d = p - position;
+    tmax = length(d);
+    const float d_dot_n = dot(d, n);
+    if (d_dot_n >= 0) return mk(0.f);
+    pdf = 1.f / (2.f * kPI * (1.f - cos_theta_max));
+    wi = d / tmax;
+    return xyz(L.Le);
+}
+
+// Lambert::sampleDir (material.h:55-73): UNIFORM hemisphere about ng using ns's tangent frame, pdf = 1/2PI
+__device__ __forceinline__ V3 lambertSampleDir(const Surf& s, Rng& rng, float& pdf)
+{
+    const float r1 = rng.next();
+    const float r2 = rng.next();
+    pdf = 1 / (2 * kPI);
+    const float sinTheta = sqrtf(1 - r1 * r1);
+    const float phi = 2 * kPI * r2;
+    const float x = sinTheta * cosf(phi);
+    const float z = sinTheta * sinf(phi);
+    return localToWorld(mk(x, r1, z), s.dpdu, s.ng, s.dpdv);
+}
+__device__ __forceinline__ V3 evalBxDF(const Surf& s) { return hasMaterial(s) ? s.albedo / kPI : mk(0.f); }
+__device__ __forceinline__ V3 sampleBxDF(const Surf& s, Rng& rng, V3& wi, float& pdf)
+{
+    if (!hasMaterial(s)) return mk(0.f);
+    wi = lambertSampleDir(s, rng, pdf);
+    return evalBxDF(s);
+}
+
+struct ShadeOut {
+    DQueues q;
+    uint32_t* ctrlNext; // ctrl block of bounce+1 (ray count)
+    uint32_t* ctrlCur;  // ctrl block of this bounce (shadow count)
+    int dst;
+};
+
+__device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, V3 d, float tmax, uint32_t pid, V3 c, uint32_t* scratch)
+{
+    const uint32_t slot = blockAppend(so.ctrlCur + kCtrlShadow, want, scratch);
+    if (want) {
+        so.q.s0[slot] = make_float4(o.x, o.y, o.z, tmax);
+        so.q.s1[slot] = make_float4(d.x, d.y, d.z, __int_as_float(int(pid)));
+        so.q.s2[slot] = make_float4(c.x, c.y, c.z, 0.f);
+    }
+}
+// warp-aggregated variant (one atomic per warp) for the volume kernel, whose warps run independently
+__device__ __forceinline__ void pushRayWarp(const ShadeOut& so, bool want, V3 o, V3 d, V3 T, uint32_t pid, int depth, uint32_t ctr)
+{
+    const uint32_t slot = warpAppend(so.ctrlNext + kCtrlRays, want);
+    if (want) {
+        so.q.q0[so.dst][slot] = make_float4(o.x, o.y, o.z, T.x);
+        so.q.q1[so.dst][slot] = make_float4(d.x, d.y, d.z, T.y);
+        so.q.q2[so.dst][slot] = make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr)));
+    }
+}
+__device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 d, V3 T, uint32_t pid, int depth, uint32_t ctr, uint32_t* scratch)
+{
+    const uint32_t slot = blockAppend(so.ctrlNext + kCtrlRays, want, scratch);
+    if (want) {
+        so.q.q0[so.dst][slot] = make_float4(o.x, o.y, o.z, T.x);
+        so.q.q1[so.dst][slot] = make_float4(d.x, d.y, d.z, T.y);
+        so.q.q2[so.dst][slot] = make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr)));
+    }
+}
+
+// Surface integrators: Normal (integrator.h:29-36), furnace (:59-66), Direct (:82-119), Indirect (:129-186),
+// GI (:205-287), Whitted's Lambert/delta-light branch (:302-394). One thread per ray-queue entry of bounce b.
+__global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQueues q, DWave w, int src, int bounce)
+{
+    __shared__ uint32_t s_scratch[kShadeWarps + 1];
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
+    const int kind = w.integrator;
+    // static partition: CTA b owns tiles b, b+grid, ... of kShadeBlock consecutive queue entries (uniform cost per entry,
+    // no work-fetch atomics); the trip count is uniform across the CTA, as the block-level appends require
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kShadeBlock < n; tile += gridDim.x) {
+        const uint32_t i = tile * kShadeBlock + threadIdx.x;
+        const bool live = i < n;
+        // per-lane outputs, appended collectively at the end of the iteration
+        bool wantRay = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        uint32_t pid = 0, ctr = 0;
+        int depth = 0;
+        // hit record + path word first; the 32 B origin/direction only for rays that hit something (41 % of the primary
+        // rays of the 1080p Cornell view): a miss costs 32 B instead of 64 B of HBM reads
+        float4 r0, r1, r2, hv;
+        r0 = r1 = r2 = hv = make_float4(0, 0, 0, 0);
+        hv.w = __int_as_float(-1);
+        if (live) {
+            hv = q.hits[i]; r2 = q.q2[src][i];
+            if (__float_as_int(hv.w) >= 0) { r0 = q.q0[src][i]; r1 = q.q1[src][i]; }
+        }
+        const V3 o = xyz(r0), d = xyz(r1);
+        V3 T = mk(r0.w, r1.w, r2.x);
+        pid = uint32_t(__float_as_int(r2.y));
+        depth = __float_as_int(r2.z);
+        Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+        Rng rng;
+        bool shadeLights = false, shadeDelta = false;
+        Surf s = {};
+        if (live) {
+            rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+            if (h.prim < 0) {
+                if (kind == XRTG_INT_DIRECT) addRadiance(q, pid, mk(float(0.18)));
+                else if (kind == XRTG_INT_WHITTED) addRadiance(q, pid, mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137)));
+            }
+            else {
+                makeSurf(sc, o, d, h, s);
+                if (kind == XRTG_INT_NORMAL) {
+                    addRadiance(q, pid, 0.5f * (s.ns + 1.0f));
+                }
+                else if (kind == XRTG_INT_FURNACE) {
+                    float pdf = 1.0f;
+                    V3 nextDir = mk(0.f);
+                    const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+                    const float cs = smax(0.0f, dot(nextDir, s.ng));
+                    addRadiance(q, pid, fr * cs * mk(1.0f) / pdf);
+                }
+                else if (kind == XRTG_INT_DIRECT) {
+                    if (lightOf(s) >= 0) addRadiance(q, pid, emitted(sc, s, d));
+                    else shadeLights = true;
+                }
+                else if (kind == XRTG_INT_WHITTED) {
+                    shadeDelta = hasMaterial(s);
+                }
+                else { // Indirect / GI
+                    bool alive = true;
+                    if (depth > 0) { // russian roulette (integrator.h:223-231)
+                        const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
+                        if (rng.next() >= p) alive = false;
+                        else T = T / mk(p);
+                    }
+                    if (alive && lightOf(s) >= 0) {
+                        if (kind == XRTG_INT_INDIRECT || depth == 0) addRadiance(q, pid, T * emitted(sc, s, d));
+                        alive = false;
+                    }
+                    if (alive) {
+                        shadeLights = (kind == XRTG_INT_GI);
+                        wantRay = true; // BSDF sampling happens after the light loop (draw order!)
+                    }
+                }
+            }
+        }
+        // ---- NEE over EVERY area light (integrator.h:95-108, :250-267) ----
+        if (kind == XRTG_INT_DIRECT || kind == XRTG_INT_GI) { // CTA-uniform: every thread takes part in the block appends
+            for (int li = 0; li < sc.nLights; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeLights) {
+                    float pdf = 0.0f;
+                    const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                    if (pdf != 0) {
+                        const float cs = smax(0.0f, dot(s.ng, wi));
+                        const V3 fr = evalBxDF(s);
+                        c = T * (fr * Lr * cs / pdf);
+                        want = true;
+                    }
+                }
+                const float bias = 0.01f;
+                pushShadow(so, want, s.pos + s.ng * bias, wi, tmax - bias, pid, c, s_scratch);
+            }
+        }
+        // ---- Whitted diffuse term over delta lights (integrator.h:328-343; PointLight/DistantLight light.cpp:120-142)
+        if (kind == XRTG_INT_WHITTED) {
+            for (int li = 0; li < sc.nDelta; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeDelta) {
+                    const DDelta L = sc.dlights[li];
+                    float pdf;
+                    if (__float_as_int(L.p_kind.w) == XRTG_DLIGHT_POINT) {
+                        const V3 ld = xyz(L.p_kind) - s.pos;
+                        const float dist = length(ld);
+                        wi = ld / dist; pdf = dist * dist; tmax = dist;
+                    }
+                    else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
+                    c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
+                    want = true;
+                }
+                pushShadow(so, want, s.pos + s.ng * float(0.1), wi, tmax, pid, c, s_scratch);
+            }
+        }
+        // ---- BSDF bounce (integrator.h:271-283) ----
+        if (wantRay) {
+            float pdf = 1.0f;
+            V3 nextDir = mk(0.f);
+            const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+            const float cs = smax(.0f, dot(nextDir, s.ng));
+            nT = T * (fr * cs / pdf);
+            no = s.pos + s.ng * 0.01f;
+            nd = nextDir;
+            wantRay = (depth + 1 < w.maxDepth);
+        }
+        if (live) ctr = rng.close();
+        if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Small scenes (<= kSmallSceneTris triangles — every scene the reference ships): ONE kernel per bounce that shades the hit,
+// traces the NEE shadow rays, samples the BSDF, traces the next closest hit and applies the NEXT depth's Russian roulette and
+// emitter test, all against the triangle list in shared memory. Only paths that go on to shade at depth+1 are appended
+// (ray + hit record, one atomic per CTA per 128 paths), so every lane that enters the kernel does useful work in every phase:
+// the shadow queue, the separate connect / extend launches, the hit-record round trip and the radiance atomics of the
+// three-kernel pipeline disappear (per path and bounce: 64 B in, <= 64 B out, one 16 B radiance read-modify-write).
+// The per-path draw order is the reference's: [RR] -> light samples -> BSDF sample (integrator.h:223-283); the RR draw of
+// depth+1 simply happens at the end of depth's kernel. Hit records are double-buffered (q.hits / q.s0) because CTAs append
+// to bounce b+1 while others still read bounce b.
+// ---------------------------------------------------------------------------------------------------------
+// Stages the scene's triangle list (primitive-id order) in shared memory; the throughput instantiation also builds the list of
+// OCCLUDERS (everything that is not an emitter proxy, scene.cpp:206) so the shadow loop carries no per-triangle flag test.
+__device__ __forceinline__ void stageSmallScene(const DScene& sc, float4* s_tris, float4* s_occ, int* s_nOcc)
+{
+    const float4* __restrict__ src = triArray(sc, true);
+    for (int k = threadIdx.x; k < kTriF4 * sc.nBruteTris; k += blockDim.x) s_tris[k] = src[k];
+    if constexpr (kExact) { if (threadIdx.x == 0) *s_nOcc = sc.nBruteTris; }
+    else if (threadIdx.x < 32) { // warp 0: order-preserving compaction, 32 triangles per round
+        int nOcc = 0;
+        for (int base = 0; base < sc.nBruteTris; base += 32) {
+            const int i = base + int(threadIdx.x);
+            const bool keep = i < sc.nBruteTris && (__float_as_int(src[4 * i + 3].y) & 1) == 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int slot = nOcc + __popc(m & ((1u << threadIdx.x) - 1u));
+                for (int k = 0; k < 4; ++k) s_occ[4 * slot + k] = src[4 * i + k];
+            }
+            nOcc += __popc(m);
+        }
+        if (threadIdx.x == 0) *s_nOcc = nOcc;
+    }
+    __syncthreads();
+}
+// Scene::occluded (scene.cpp:202-211) on a staged small scene
+__device__ __forceinline__ bool anyHitSmall(const DScene& sc, V3 o, V3 d, float tmax, const float4* occTris, int nOcc)
+{
+    if (sc.nBoxes > 0) return true; // BoxMesh::occluded is always true (primitive.h:266-268)
+    Hit h;
+    h.t = tmax; h.prim = 0x7fffffff; h.u = h.v = 0.f;
+    if (smallSceneTris<true, !kExact>(occTris, nOcc, o, d, h, -1)) return true;
+    for (int s = 0; s < sc.nSpheres; ++s) {
+        const float4 cr = __ldg(sc.spheres + 2 * s);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * s + 1));
+        float t;
+        if (meta.y == 0 && sphereT(cr, o, d, t) && t < tmax) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ float4* hitBuffer(const DQueues& q, int bounce) { return (bounce & 1) ? q.s0 : q.hits; }
+
+// Plane-paired small scene (small_scene.h), throughput instantiation: one record = one supporting plane + two triangles in it;
+// one ray/plane intersection and two barycentric plane equations per triangle. Branch-free per lane.
+struct SmallSection {
+    const float4* recs; // 5 per record: N|d , A: n1|d1 , n2|d2 , B: n1|d1 , n2|d2
+    const int* ids;     // 2 per record
+    int nRecords;
+};
+__device__ __forceinline__ SmallSection smallSection(const float4* blk, int off)
+{
+    const int4 h = *reinterpret_cast<const int4*>(blk + off);
+    return SmallSection{blk + h.z, reinterpret_cast<const int*>(blk + h.w), h.x};
+}
+__device__ __forceinline__ float insideness(const float4 a, const float4 b, V3 P)
+{
+    const float u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
+    const float v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
+    return fminf(fminf(u, v), 1.f - (u + v)); // >= 0 <=> u >= 0, v >= 0, u + v <= 1
+}
+// Any hit with eps < t < tmax among the occluders; lanes without a shadow ray pass tmax < 0. Must be called by all 32 lanes of
+// a converged warp: a plane that no lane can hit (behind every ray or beyond every tmax — the floor and the ceiling for every
+// shadow ray towards the Cornell light) is skipped with one vote.
+__device__ __forceinline__ bool groupedAnyHit(const SmallSection& S, V3 o, V3 d, float tmax)
+{
+    float acc = -1.f;
+    for (int r = 0; r < S.nRecords; ++r) {
+        const float4* rec = S.recs + 5 * r;
+        const float4 pl = rec[0];
+        const float det = dot(xyz(pl), d);
+        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
+        const bool vt = !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < tmax;
+        if (!__any_sync(0xffffffffu, vt)) continue;
+        const V3 P = o + t * d;
+        const float m = fmaxf(insideness(rec[1], rec[2], P), insideness(rec[3], rec[4], P));
+        acc = fmaxf(acc, vt ? m : -1.f);
+    }
+    return acc >= 0.f;
+}
+// Closest hit: strictly smaller t wins between records, A before B inside one (scene.cpp:193-197); lanes without a ray pass
+// want = false.
+__device__ __forceinline__ void groupedClosest(const SmallSection& S, V3 o, V3 d, bool want, Hit& h)
+{
+    float best = want ? FLT_MAX : -1.f;
+    int bi = -1;
+#pragma unroll 2
+    for (int r = 0; r < S.nRecords; ++r) {
+        const float4* rec = S.recs + 5 * r;
+        const float4 pl = rec[0];
+        const float det = dot(xyz(pl), d);
+        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
+        const V3 P = o + t * d;
+        const float m0 = insideness(rec[1], rec[2], P), m1 = insideness(rec[3], rec[4], P);
+        const bool take = fmaxf(m0, m1) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < best;
+        best = take ? t : best;
+        bi = take ? (m0 >= 0.f ? 2 * r : 2 * r + 1) : bi;
+    }
+    if (bi >= 0) {
+        const float4* rec = S.recs + 5 * (bi >> 1) + 1 + 2 * (bi & 1);
+        const float4 a = rec[0], b = rec[1];
+        const V3 P = o + best * d;
+        h.t = best;
+        h.u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
+        h.v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
+        h.prim = S.ids[bi];
+    }
+}
+
+// GROUPED: the scene carries a plane-paired block (throughput instantiation, no BoxMesh); otherwise the per-triangle lists.
+template <bool GROUPED>
+__global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
+{
+    constexpr int kListF4 = GROUPED ? 1 : kTriF4 * kSmallSceneTris;
+    __shared__ float4 s_tris[kListF4];
+    __shared__ float4 s_occ[(kExact || GROUPED) ? 1 : kTriF4 * kSmallSceneTris];
+    __shared__ float4 s_block[GROUPED ? kSmallBlockF4 : 1];
+    __shared__ uint32_t s_scratch[kBlock / 32 + 1];
+    __shared__ int s_nOcc;
+    SmallSection secAll{}, secOcc{};
+    const float4* occTris = nullptr;
+    int nOcc = 0;
+    if constexpr (GROUPED) {
+        for (int k = threadIdx.x; k < sc.smallBlockF4; k += blockDim.x) s_block[k] = sc.smallBlock[k];
+        __syncthreads();
+        const int4 hd = *reinterpret_cast<const int4*>(s_block);
+        secAll = smallSection(s_block, hd.x);
+        secOcc = smallSection(s_block, hd.y);
+    }
+    else {
+        stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
+        occTris = kExact ? s_tris : s_occ;
+        nOcc = s_nOcc;
+    }
+    // Scene::occluded / Scene::intersect on the staged scene. GROUPED: executed by the whole (converged) warp.
+    auto occluded = [&](bool want, V3 o, V3 d, float tmax) -> bool {
+        if constexpr (GROUPED) {
+            bool occ = groupedAnyHit(secOcc, o, d, want ? tmax : -1.f);
+            if (want && !occ)
+                for (int k = 0; k < sc.nSpheres; ++k) {
+                    const float4 cr = __ldg(sc.spheres + 2 * k);
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1));
+                    float t;
+                    if (meta.y == 0 && sphereT(cr, o, d, t) && t < tmax) { occ = true; break; }
+                }
+            return occ;
+        }
+        else return want && anyHitSmall(sc, o, d, tmax, occTris, nOcc);
+    };
+    auto closest = [&](bool want, V3 o, V3 d, Hit& h) {
+        if constexpr (GROUPED) {
+            h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
+            groupedClosest(secAll, o, d, want, h);
+            if (want)
+                for (int k = 0; k < sc.nSpheres; ++k) {
+                    const float4 cr = __ldg(sc.spheres + 2 * k);
+                    const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1));
+                    float t;
+                    if (sphereT(cr, o, d, t)) consider(h, t, 0.f, 0.f, meta.x);
+                }
+            if (h.prim == 0x7fffffff) h.prim = -1;
+        }
+        else if (want) {
+            TraceCounters tc;
+            closestHit<false, true>(sc, o, d, false, h, nullptr, tc, s_tris);
+        }
+    };
+
+    uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
+    const uint32_t n = ctrl[kCtrlRays];
+    uint32_t* nextCount = ctrl + kCtrlStride + kCtrlRays;
+    const float4* __restrict__ hitsIn = hitBuffer(q, bounce);
+    float4* __restrict__ hitsOut = hitBuffer(q, bounce + 1);
+    // (ternaries instead of q.q0[src]: a dynamic index would force a local-memory copy of the kernel parameter)
+    const float4* __restrict__ in0 = src ? q.q0[1] : q.q0[0];
+    const float4* __restrict__ in1 = src ? q.q1[1] : q.q1[0];
+    const float4* __restrict__ in2 = src ? q.q2[1] : q.q2[0];
+    float4* __restrict__ out0 = src ? q.q0[0] : q.q0[1];
+    float4* __restrict__ out1 = src ? q.q1[0] : q.q1[1];
+    float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
+    const int kind = w.integrator;
+    uint32_t nClosest = 0, nShadow = 0;
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
+        const uint32_t i = tile * kBlock + threadIdx.x;
+        const bool live = i < n;
+        // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
+        V3 d = mk(0.f), T = mk(0.f);
+        uint32_t pid = 0, ctr = 0;
+        int depth = 0;
+        float4 rad = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool radDirty = false;
+        auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; radDirty = true; };
+        Rng rng;
+        Surf s = {};
+        bool shadeLights = false, shadeDelta = false, bsdf = false;
+        if (live) {
+            const float4 hv = hitsIn[i], r0 = in0[i], r1 = in1[i], r2 = in2[i];
+            const V3 o = xyz(r0);
+            d = xyz(r1);
+            T = mk(r0.w, r1.w, r2.x);
+            pid = uint32_t(__float_as_int(r2.y));
+            depth = __float_as_int(r2.z);
+            rad = q.radiance[pid];
+            const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
+            rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
+            makeSurf(sc, o, d, h, s);
+            if (kind == XRTG_INT_DIRECT) {
+                if (lightOf(s) >= 0) add(emitted(sc, s, d));
+                else shadeLights = true;
+            }
+            else if (kind == XRTG_INT_WHITTED) shadeDelta = hasMaterial(s);
+            else { // Indirect / GI. Entries of bounce > 0 already passed RR and the emitter test in the kernel that traced them.
+                bool alive = true;
+                if (bounce == 0 && lightOf(s) >= 0) { add(T * emitted(sc, s, d)); alive = false; }
+                shadeLights = alive && kind == XRTG_INT_GI;
+                bsdf = alive;
+            }
+        }
+        // ---- phase 2: NEE over EVERY area light (integrator.h:95-108, :250-267), shadow ray traced inline ----
+        if (kind == XRTG_INT_DIRECT || kind == XRTG_INT_GI) {
+            for (int li = 0; li < sc.nLights; ++li) {
+                bool want = false;
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeLights) {
+                    float pdf = 0.0f;
+                    const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                    if (pdf != 0) {
+                        const float cs = smax(0.0f, dot(s.ng, wi));
+                        const V3 fr = evalBxDF(s);
+                        c = T * (fr * Lr * cs / pdf);
+                        want = true;
+                        ++nShadow;
+                    }
+                }
+                const float bias = 0.01f;
+                if (!occluded(want, s.pos + s.ng * bias, wi, tmax - bias) && want) add(c);
+            }
+        }
+        // ---- Whitted diffuse term over delta lights (integrator.h:328-343; light.cpp:120-142) ----
+        if (kind == XRTG_INT_WHITTED) {
+            for (int li = 0; li < sc.nDelta; ++li) {
+                V3 wi = mk(0.f), c = mk(0.f);
+                float tmax = 0.f;
+                if (shadeDelta) {
+                    const DDelta L = sc.dlights[li];
+                    float pdf;
+                    if (__float_as_int(L.p_kind.w) == XRTG_DLIGHT_POINT) {
+                        const V3 ld = xyz(L.p_kind) - s.pos;
+                        const float dist = length(ld);
+                        wi = ld / dist; pdf = dist * dist; tmax = dist;
+                    }
+                    else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
+                    c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
+                    ++nShadow;
+                }
+                if (!occluded(shadeDelta, s.pos + s.ng * float(0.1), wi, tmax) && shadeDelta) add(c);
+            }
+        }
+        // ---- phase 3: BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----
+        bool wantNext = false, trace = false;
+        V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
+        Hit nh{FLT_MAX, 0.f, 0.f, -1};
+        if (bsdf) {
+            float pdf = 1.0f;
+            V3 nextDir = mk(0.f);
+            const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
+            const float cs = smax(.0f, dot(nextDir, s.ng));
+            nT = T * (fr * cs / pdf);
+            no = s.pos + s.ng * 0.01f;
+            nd = nextDir;
+            trace = depth + 1 < w.maxDepth;
+        }
+        if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) closest(trace, no, nd, nh);
+        if (trace) {
+            ++nClosest;
+            if (nh.prim >= 0) {
+                const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
+                if (!(rng.next() >= p)) {
+                    nT = nT / mk(p);
+                    const uint32_t meta = __float_as_uint(__ldg(sc.prims + 4 * nh.prim + 3).w);
+                    if (((meta >> kMetaLightShift) & 0xfffu) == 0) wantNext = true;
+                    else if (kind == XRTG_INT_INDIRECT) { // Le at any depth (integrator.h:150-160); GI only at depth 0
+                        Surf s2;
+                        makeSurf(sc, no, nd, nh, s2);
+                        add(nT * emitted(sc, s2, nd));
+                    }
+                }
+            }
+        }
+        if (live) {
+            ctr = rng.close();
+            if (radDirty) q.radiance[pid] = rad;
+        }
+        const uint32_t slot = blockAppend<kBlock / 32>(nextCount, wantNext, s_scratch);
+        if (wantNext) {
+            out0[slot] = make_float4(no.x, no.y, no.z, nT.x);
+            out1[slot] = make_float4(nd.x, nd.y, nd.z, nT.y);
+            out2[slot] = make_float4(nT.z, __int_as_float(int(pid)), __int_as_float(depth + 1), __int_as_float(int(ctr)));
+            hitsOut[slot] = make_float4(nh.t, nh.u, nh.v, __int_as_float(nh.prim));
+        }
+    }
+    statAdd(stats, kStatClosest, nClosest);
+    statAdd(stats, kStatShadow, nShadow);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatBounceEntries, (unsigned long long)n);
+}

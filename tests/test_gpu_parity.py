@@ -307,7 +307,8 @@ def test_fast_mode_is_deterministic_and_seed_dependent(gpu_cornell):
 
 @pytest.mark.parametrize("light,integ,depth,exact", [
     ("quad", capi.INT_GI, 3, False), ("sphere", capi.INT_GI, 4, False), ("triangle", capi.INT_DIRECT, 1, False),
-    ("quad", capi.INT_INDIRECT, 3, False), ("quad", capi.INT_GI, 3, True), ("quad", capi.INT_INDIRECT, 2, True)])
+    ("quad", capi.INT_INDIRECT, 3, False), ("quad+sphere", capi.INT_GI, 3, False), ("quad", capi.INT_GI, 3, True),
+    ("quad+sphere", capi.INT_GI, 2, True), ("quad", capi.INT_INDIRECT, 2, True)])
 def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, depth, exact, monkeypatch):
     """k_bounce_small (shade + shadow rays + next closest hit + next RR in one kernel, plane-paired triangle records in the
     throughput build) draws the same numbers per path as shade -> connect -> extend, so with the same seed both pipelines

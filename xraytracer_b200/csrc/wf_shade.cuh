@@ -390,7 +390,7 @@ __device__ __forceinline__ void groupedClosest(const SmallSection& S, V3 o, V3 d
 {
     float best = want ? FLT_MAX : -1.f;
     int bi = -1;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = 0; r < S.nRecords; ++r) {
         const float4* rec = S.recs + 5 * r;
         const float4 pl = rec[0];

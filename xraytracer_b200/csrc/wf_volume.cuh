@@ -426,7 +426,26 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
     };
     auto add = [&](V3 c) { rad.x += c.x; rad.y += c.y; rad.z += c.z; dirty = true; };
     while (true) {
-        // ---- refill idle lanes from the warp's reservation of 32 consecutive queue entries ----
+        // ---- lanes that just ended a walk: its epilogue, NEE, the closest hit of the next ray ----
+        if (state == kLaneWalked) {
+            trackFinish(media[mi], o, d, ts, walkEnd, rng, r);
+            state = kLanePost;
+        }
+        if (state == kLanePost) {
+            V3 no, nd, nT, contrib;
+            bool hasContrib;
+            const bool cont = volumePost<COUNT>(sc, w, media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd,
+                                                nT, hasContrib, contrib);
+            if (hasContrib) add(contrib);
+            if (!cont || ++it == maxIter) finish();
+            else {
+                o = no; d = nd; T = nT;
+                closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+                ++nClosest;
+                state = kLanePre;
+            }
+        }
+        // ---- refill idle lanes (including those whose path just ended) from the warp's reservation of 32 queue entries ----
         const uint32_t need = __ballot_sync(0xffffffffu, state == kLaneIdle);
         if (need != 0 && !exhausted) {
             const uint32_t nNeed = __popc(need), rank = __popc(need & ((1u << lane) - 1u)), left = resEnd - resNext;
@@ -453,25 +472,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
             }
         }
         if (__ballot_sync(0xffffffffu, state != kLaneIdle) == 0) break;
-        // ---- lanes between walks: epilogue of the last walk, closest hit of the next ray, prologue of the next walk ----
-        if (state == kLaneWalked) {
-            trackFinish(media[mi], o, d, ts, walkEnd, rng, r);
-            state = kLanePost;
-        }
-        if (state == kLanePost) {
-            V3 no, nd, nT, contrib;
-            bool hasContrib;
-            const bool cont = volumePost<COUNT>(sc, w, media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd,
-                                                nT, hasContrib, contrib);
-            if (hasContrib) add(contrib);
-            if (!cont || ++it == maxIter) finish();
-            else {
-                o = no; d = nd; T = nT;
-                closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
-                ++nClosest;
-                state = kLanePre;
-            }
-        }
+        // ---- prologue of the next walk, for continuing and for fresh paths alike ----
         if (state == kLanePre) {
             V3 contrib;
             bool hasContrib;

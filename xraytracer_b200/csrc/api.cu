@@ -381,6 +381,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         G[i].nx = g.nx; G[i].ny = g.ny; G[i].nz = g.nz;
         std::memcpy(G[i].origin, g.origin, 12);
         G[i].voxel = g.voxel_size;
+        G[i].invVoxel = 1.0f / g.voxel_size;
         G[i].background = g.background;
         s->gridData.push_back(std::move(m));
     }

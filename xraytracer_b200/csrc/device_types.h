@@ -41,6 +41,7 @@ struct DGrid {
     int nx, ny, nz;
     float origin[3];
     float voxel, background;
+    float invVoxel; // 1 / voxel (throughput instantiation; the exact one divides like grid.h:71-77)
 };
 
 // Everything the kernels need to know about the scene; passed by value (fits the 4 KB param space).

@@ -12,7 +12,9 @@ __device__ __forceinline__ float gridVoxel(const DGrid& g, int x, int y, int z)
 }
 __device__ __forceinline__ float gridDensity(const DGrid& g, V3 p)
 {
-    const float fx = (p.x - g.origin[0]) / g.voxel, fy = (p.y - g.origin[1]) / g.voxel, fz = (p.z - g.origin[2]) / g.voxel;
+    float fx, fy, fz;
+    if constexpr (kExact) { fx = (p.x - g.origin[0]) / g.voxel; fy = (p.y - g.origin[1]) / g.voxel; fz = (p.z - g.origin[2]) / g.voxel; }
+    else { fx = (p.x - g.origin[0]) * g.invVoxel; fy = (p.y - g.origin[1]) * g.invVoxel; fz = (p.z - g.origin[2]) * g.invVoxel; }
     const float bx = floorf(fx), by = floorf(fy), bz = floorf(fz);
     const float wx = fx - bx, wy = fy - by, wz = fz - bz;
     const int x = int(bx), y = int(by), z = int(bz);
@@ -181,10 +183,18 @@ __device__ __forceinline__ int trackStep(const DMedium& m, const DGrid& g, V3 o,
     const V3 P_s = sigma_s / (sigma_s + sigma_n);
     if (rng.next() < comp(P_s, ch)) return kTrackScatter;
     const V3 P_n = sigma_n / (sigma_s + sigma_n);
-    const V3 tr = analyticTr(ts.sd, maj);
-    const V3 pdf_distance = m.majorant * tr;
-    const V3 pdf = ts.pmf * pdf_distance * P_n;
-    ts.tt = ts.tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+    if constexpr (kExact) {
+        const V3 tr = analyticTr(ts.sd, maj);
+        const V3 pdf_distance = m.majorant * tr;
+        const V3 pdf = ts.pmf * pdf_distance * P_n;
+        ts.tt = ts.tt * ((tr * sigma_n) / (pdf.x + pdf.y + pdf.z));
+    }
+    else {
+        // the majorant is the same for the three channels, so is tr = exp(-maj * sd), and it cancels:
+        // tr * sigma_n / sum(pmf * maj * tr * P_n) = sigma_n / (maj * sum(pmf * P_n))
+        const V3 pn = ts.pmf * P_n;
+        ts.tt = ts.tt * (sigma_n / (m.majorant * (pn.x + pn.y + pn.z)));
+    }
     return kTrackContinue;
 }
 // The epilogue of the walk: medium.cpp:73-83 (left the medium) or :100-112 (scattered, new direction from the phase function)
@@ -193,10 +203,13 @@ __device__ __forceinline__ void trackFinish(const DMedium& m, V3 o, V3 d, TrackS
     const V3 maj = mk(m.majorant);
     if (how == kTrackExit) {
         r.pos = o + (ts.t1 + kRayEps) * d; r.dir = d;
-        const float rest = ts.sd - (ts.t - (ts.t1 - kRayEps));
-        const V3 tr = analyticTr(rest, maj);
-        const V3 pdf = ts.pmf * tr;
-        ts.tt = ts.tt * (tr / (pdf.x + pdf.y + pdf.z));
+        if constexpr (kExact) {
+            const float rest = ts.sd - (ts.t - (ts.t1 - kRayEps));
+            const V3 tr = analyticTr(rest, maj);
+            const V3 pdf = ts.pmf * tr;
+            ts.tt = ts.tt * (tr / (pdf.x + pdf.y + pdf.z));
+        }
+        // (throughput instantiation: tr is channel-uniform and the pmf sums to one, so tr / sum(pmf * tr) = 1)
         r.scattered = false;
     }
     else {
@@ -206,10 +219,16 @@ __device__ __forceinline__ void trackFinish(const DMedium& m, V3 o, V3 d, TrackS
         const V3 P_s = sigma_s / (sigma_s + sigma_n);
         r.pos = o + ts.t * d;
         hgSample(m.g, d, rng, r.dir);
-        const V3 tr = analyticTr(ts.sd, maj);
-        const V3 pdf_distance = m.majorant * tr;
-        const V3 pdf = ts.pmf * pdf_distance * P_s;
-        ts.tt = ts.tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
+        if constexpr (kExact) {
+            const V3 tr = analyticTr(ts.sd, maj);
+            const V3 pdf_distance = m.majorant * tr;
+            const V3 pdf = ts.pmf * pdf_distance * P_s;
+            ts.tt = ts.tt * ((tr * sigma_s) / (pdf.x + pdf.y + pdf.z));
+        }
+        else {
+            const V3 ps = ts.pmf * P_s; // tr cancels as in trackStep
+            ts.tt = ts.tt * (sigma_s / (m.majorant * (ps.x + ps.y + ps.z)));
+        }
         r.scattered = true;
     }
     r.thr = anyNan(ts.tt) ? mk(0.f) : ts.tt;

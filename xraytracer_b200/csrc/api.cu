@@ -100,6 +100,8 @@ struct xrtg_scene {
     DScene ds{};
     xrtg_scene_info info{};
     int maxShadowPerPath = 1;
+    float boundsLo[3] = {0, 0, 0}, boundsHi[3] = {0, 0, 0}; // world bounds of every primitive (valid if hasBounds)
+    bool hasBounds = false;
     // workspace
     DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
     unsigned long long* statsHost = nullptr; // pinned
@@ -282,6 +284,21 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             prims[4 * id + 3] = rec3;
             ++bi;
         }
+    }
+    // ---- world bounds of everything a ray can hit (screen-space scissor of the primary kernel) ----
+    {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        auto grow = [&](const float* p, float r) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a] - r); hi[a] = std::max(hi[a], p[a] + r); } };
+        for (size_t k = 0; k < buildTris.size(); k += 3) grow(&buildTris[k], 0.f);
+        for (int i = 0; i < d->n_objects; ++i) {
+            const xrtg_object& o = d->objects[i];
+            if (o.kind == XRTG_OBJ_SPHERE) grow(d->spheres[o.first].center, std::fabs(d->spheres[o.first].radius));
+            else if (o.kind == XRTG_OBJ_BOX) { grow(d->boxes[o.first].pmin, 0.f); grow(d->boxes[o.first].pmax, 0.f); }
+        }
+        bool finite = nPrims > 0;
+        for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(lo[a]) && std::isfinite(hi[a]) && lo[a] <= hi[a];
+        s->hasBounds = finite;
+        if (finite) { std::memcpy(s->boundsLo, lo, 12); std::memcpy(s->boundsHi, hi, 12); }
     }
     // ---- BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
     Bvh bvh;
@@ -552,6 +569,50 @@ int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_p
     return 0;
 }
 
+// Conservative pixel rectangle that can see the scene's bounding box through PinholeCamera::sampleRay (camera.h:49-60):
+// dir_cam = ((2u-1)s, (1-2v)s/aspect, -1), dir_world = dir_cam * R (row vector, geometry.h:653-669), origin = c2w row 3. Each box
+// corner is taken back to camera space with R^-1 (double); if any corner is not strictly in front of the camera the scissor is
+// the full image. One pixel of margin on every side.
+void computeScissor(const xrtg_scene* s, const xrtg_camera* cam, int W, int H, int out[4])
+{
+    out[0] = 0; out[1] = 0; out[2] = W; out[3] = H;
+    if (!s->hasBounds) return;
+    const float* m = cam->c2w;
+    const double R[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}};
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    if (!(std::fabs(det) > 1e-12) || !(cam->scale > 0.f) || !(cam->aspect > 0.f)) return;
+    double inv[3][3];
+    inv[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det; inv[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det;
+    inv[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det; inv[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det;
+    inv[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det; inv[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+    inv[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det; inv[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det;
+    inv[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+    double span = 0.0;
+    for (int a = 0; a < 3; ++a) span = std::max(span, double(s->boundsHi[a]) - s->boundsLo[a]);
+    const double pad = 1e-4 * std::max(span, 1e-6);
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int c = 0; c < 8; ++c) {
+        const double P[3] = {(c & 1 ? s->boundsHi[0] + pad : s->boundsLo[0] - pad) - m[12], (c & 2 ? s->boundsHi[1] + pad : s->boundsLo[1] - pad) - m[13],
+                             (c & 4 ? s->boundsHi[2] + pad : s->boundsLo[2] - pad) - m[14]};
+        // row vector * R^-1
+        const double qx = P[0] * inv[0][0] + P[1] * inv[1][0] + P[2] * inv[2][0];
+        const double qy = P[0] * inv[0][1] + P[1] * inv[1][1] + P[2] * inv[2][1];
+        const double qz = P[0] * inv[0][2] + P[1] * inv[1][2] + P[2] * inv[2][2];
+        const double len = std::sqrt(qx * qx + qy * qy + qz * qz);
+        if (!(qz < -1e-6 * len)) return; // a corner beside or behind the camera: no scissor
+        const double lam = -qz;
+        const double u = 0.5 * (qx / (lam * cam->scale) + 1.0), v = 0.5 * (1.0 - qy * cam->aspect / (lam * cam->scale));
+        x0 = std::min(x0, u * W); x1 = std::max(x1, u * W);
+        y0 = std::min(y0, v * H); y1 = std::max(y1, v * H);
+    }
+    if (!(std::isfinite(x0) && std::isfinite(x1) && std::isfinite(y0) && std::isfinite(y1))) return;
+    out[0] = int(std::max(0.0, std::floor(x0) - 1.0)); out[2] = int(std::min(double(W), std::ceil(x1) + 1.0));
+    out[1] = int(std::max(0.0, std::floor(y0) - 1.0)); out[3] = int(std::min(double(H), std::ceil(y1) + 1.0));
+    if (out[2] < out[0]) out[2] = out[0];
+    if (out[3] < out[1]) out[3] = out[1];
+}
+
 // The whole render on `st`, result (mean or sum) written to device buffer `out`.
 int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats)
 {
@@ -587,6 +648,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     w.width = p->width; w.height = p->height; w.nPixels = nPixels;
     w.integrator = integ; w.maxDepth = p->max_depth; w.seed = p->seed;
     w.flags = 0;
+    w.sx0 = 0; w.sy0 = 0; w.sx1 = p->width; w.sy1 = p->height;
     w.mt = static_cast<uint32_t*>(s->mt.p);
     w.mti = static_cast<uint32_t*>(s->mti.p);
 
@@ -609,6 +671,12 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     const bool small = !deep && s->ds.nBruteTris > 0 && s->ds.nBruteTris <= 64;
     const bool bruteSecondary = envInt("XRT_BRUTE_SECONDARY", small ? 1 : 0) != 0, bruteShadow = envInt("XRT_BRUTE_SHADOW", small ? 1 : 0) != 0;
     const bool dump = std::getenv("XRT_STAGE_DUMP") != nullptr;
+    // throughput instantiation only: the exact one must advance every pixel's mt19937 stream by its two jitter draws
+    if (!exact && envInt("XRT_SCISSOR", 1) != 0) {
+        int sc4[4];
+        computeScissor(s, cam, p->width, p->height, sc4);
+        w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
+    }
     uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0, nBounce = 0;
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));

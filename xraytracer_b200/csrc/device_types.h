@@ -98,6 +98,9 @@ struct DWave {
     int integrator, maxDepth;
     uint32_t seed;
     uint32_t flags;         // development switches (none at present)
+    // Screen-space scissor [sx0, sx1) x [sy0, sy1): pixels outside it cannot see the scene's bounding box (every sample of such a
+    // pixel is a miss), so the primary kernel resolves them without generating a ray. Full image when unknown.
+    int sx0, sy0, sx1, sy1;
     // exact mode: per-pixel mt19937 state, word-major [624][nPixels], and the per-pixel cursor
     uint32_t* mt;
     uint32_t* mti;

@@ -421,9 +421,21 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
         V3 o = mk(0.f), d = mk(0.f);
         Hit h{FLT_MAX, 0.f, 0.f, -1};
         uint32_t ctr = 0;
+        bool inView = false;
+        uint32_t pi = 0, pj = 0;
         if (pid < n) {
             const uint32_t pix = pid % w.nPixels;
-            const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+            pi = pix / uint32_t(w.width); pj = pix % uint32_t(w.width);
+            inView = int(pj) >= w.sx0 && int(pj) < w.sx1 && int(pi) >= w.sy0 && int(pi) < w.sy1;
+            if (!inView) { // the pixel cannot see the scene's bounding box: every sample is a miss, no ray needed
+                V3 c = mk(0.f);
+                if (missMode == 1) c = mk(float(0.18));
+                else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
+                q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
+            }
+        }
+        if (inView) {
+            const uint32_t i = pi, j = pj;
             Rng rng;
             rng.open(w, pid, 0);
             const float r0 = rng.next();

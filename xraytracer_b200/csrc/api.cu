@@ -354,7 +354,21 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
         std::vector<float> block;
         SmallBlockInfo sbi;
-        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi)) {
+        // every point a shadow ray can start or end at (hull pruning of the occluder section, small_scene.h); a DistantLight's
+        // shadow rays leave the scene, so no pruning then
+        std::vector<float> hull(buildTris);
+        bool distant = false;
+        for (int i = 0; i < d->n_objects; ++i)
+            if (d->objects[i].kind == XRTG_OBJ_SPHERE) {
+                const xrtg_sphere& sp = d->spheres[d->objects[i].first];
+                for (int c = 0; c < 8; ++c)
+                    for (int a = 0; a < 3; ++a) hull.push_back(sp.center[a] + ((c >> a) & 1 ? sp.radius : -sp.radius));
+            }
+        for (int i = 0; i < d->n_delta_lights; ++i) {
+            if (d->delta_lights[i].kind == XRTG_DLIGHT_POINT) hull.insert(hull.end(), d->delta_lights[i].pos_or_dir, d->delta_lights[i].pos_or_dir + 3);
+            else distant = true;
+        }
+        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi, distant ? nullptr : hull.data(), int(hull.size() / 3))) {
             s->info.small_records_all = sbi.nRecordsAll;
             s->info.small_records_occ = sbi.nRecordsOcc;
             if (int rc = s->smallBlock.alloc(block.size() * sizeof(float))) return rc;

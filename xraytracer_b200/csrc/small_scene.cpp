@@ -113,7 +113,7 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
         makePlaneRecord(tris9 + 9 * size_t(t), tris9 + 9 * size_t(t) + 3, tris9 + 9 * size_t(t) + 6, t, emitterFlags ? emitterFlags[t] : 0, &recs[16 * size_t(t)]);
     std::vector<float> block;
     SmallBlockInfo bi;
-    const bool ok = buildSmallBlock(recs.data(), n, block, &bi);
+    const bool ok = buildSmallBlock(recs.data(), n, block, &bi, tris9, 3 * n); // hull = the triangles' own vertices
     if (info) *info = bi;
     if (!ok) return 1;
     auto asInt = [](float f) { int i; std::memcpy(&i, &f, 4); return i; };
@@ -147,28 +147,50 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
             }
         }
         for (int t = 0; t < n; ++t) {
-            const bool expect = sec == 0 || !(emitterFlags && (emitterFlags[t] & 1));
-            if (seen[size_t(t)] != (expect ? 1 : 0)) return -1;
+            const bool emitter = emitterFlags && (emitterFlags[t] & 1);
+            // a non-emitter may be missing from the occluder section only if the whole scene lies on one side of its plane
+            const bool pruned = sec == 1 && !emitter && seen[size_t(t)] == 0 && planeBoundsPoints(&recs[16 * size_t(t)], tris9, 3 * n);
+            const bool expect = sec == 0 || !emitter;
+            if (seen[size_t(t)] != (expect ? 1 : 0) && !pruned) return -1;
         }
     }
     return 0;
 }
 
-bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info)
+bool planeBoundsPoints(const float* rec, const float* points, int nPoints)
+{
+    const Plane p = planeOf(rec);
+    if (!p.valid || nPoints <= 0) return false;
+    double ext = 0.0;
+    for (int k = 0; k < 3 * nPoints; ++k) ext = std::fmax(ext, std::fabs(double(points[k])));
+    const double tol = 1e-5 * std::fmax(ext, 1e-6);
+    bool pos = false, neg = false;
+    for (int k = 0; k < nPoints; ++k) {
+        const double sd = p.n[0] * points[3 * k] + p.n[1] * points[3 * k + 1] + p.n[2] * points[3 * k + 2] - p.delta;
+        if (!(std::fabs(sd) < 1e300)) return false; // NaN / inf coordinates: keep the triangle
+        pos = pos || sd > tol;
+        neg = neg || sd < -tol;
+    }
+    return !(pos && neg);
+}
+
+bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints, int nHullPoints)
 {
     block.clear();
     if (nTris <= 0 || nTris > 64) return false;
     std::vector<Plane> planes{};
     planes.resize(size_t(nTris));
     std::vector<int> all, occ;
+    SmallBlockInfo bi;
     for (int t = 0; t < nTris; ++t) {
         planes[size_t(t)] = planeOf(ftrisId + 16 * size_t(t));
         all.push_back(t);
         int flags;
         std::memcpy(&flags, ftrisId + 16 * size_t(t) + 13, 4);
-        if ((flags & 1) == 0) occ.push_back(t);
+        if ((flags & 1) != 0) continue; // emitter proxy: never an occluder (scene.cpp:206)
+        if (hullPoints && planeBoundsPoints(ftrisId + 16 * size_t(t), hullPoints, nHullPoints)) { ++bi.nPruned; continue; }
+        occ.push_back(t);
     }
-    SmallBlockInfo bi;
     block.assign(4, 0.f);
     const size_t offAll = 1;
     int planesOcc = 0;

@@ -21,7 +21,7 @@ namespace xrt {
 constexpr int kSmallBlockMaxF4 = 704; // shared-memory budget of the kernel (11 KB)
 
 struct SmallBlockInfo {
-    int nRecordsAll = 0, nRecordsOcc = 0, nPlanesAll = 0;
+    int nRecordsAll = 0, nRecordsOcc = 0, nPlanesAll = 0, nPruned = 0;
 };
 
 // Plane-equation record of one triangle (16 floats: N|d, n1|d1, n2|d2, id|flags|0|0 — the last two as int bits), computed in
@@ -34,6 +34,14 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
 
 // ftrisId: 4 floats x 4 per triangle (N|d, n1|d1, n2|d2, id|flags) in primitive-id order. Returns false (block left empty) when
 // grouping does not pay (fewer than 4 triangles saved) or the block would not fit.
-bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info);
+//
+// hullPoints (3 floats each, may be null): every point a shadow ray can start or end at — all triangle vertices, the corners of
+// the spheres' bounding boxes, point-light positions. A triangle whose plane has ALL of them on one closed side (a wall of a
+// closed room: the scene lies inside its half-space) can never be crossed by a segment between two such points, so it is
+// left out of the occluder section. Pass null when a light is infinitely far away (DistantLight) — its shadow rays leave the hull.
+bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints = nullptr,
+                     int nHullPoints = 0);
+// true if all points lie on one closed side of the plane of record `rec` (16 floats), within 1e-5 of the points' extent
+bool planeBoundsPoints(const float* rec, const float* points, int nPoints);
 
 } // namespace xrt

@@ -10,7 +10,49 @@ struct Surf {
 
 // Reconstructs what Mesh::intersect (primitive.cpp:100-110) / Sphere::intersect (primitive.h:112-122) store in
 // IntersectInfo. ng was normalised on the host with the reference's expression; ns is interpolated and NOT
-// re-normalised. A sphere hit leaves dpdu/dpdv at zero (the reference leaves them stale).
+// re-normalised. A sphere hit keeps the reference's stale dpdu/dpdv in the exact instantiation (sphereStaleBasis), zero in the
+// throughput one.
+// Sphere::intersect never writes dpdu / dpdv (primitive.h:112-122): after Scene::intersect (scene.cpp:190-200) they still hold what
+// the last MESH hit that was the closest so far wrote while the objects before the sphere were visited — or zero if there was
+// none. The hits that "were the closest so far" form a decreasing sequence, so the last one is simply the closest hit among
+// the primitives with a smaller id; if that is another sphere, the question repeats for it. Exact instantiation only (the
+// throughput one keeps zeros: both are an artefact); BoxMesh objects (which reset info.t) are not modelled.
+// O(#triangles) per Lambert-sphere hit: the parity path, not the fast one.
+__device__ __noinline__ void sphereStaleBasis(const DScene& sc, V3 o, V3 d, int sphereId, V3& dpdu, V3& dpdv)
+{
+    dpdu = mk(0.f); dpdv = mk(0.f);
+    int cur = sphereId;
+    for (int guard = 0; guard <= sc.nSpheres; ++guard) {
+        Hit best{FLT_MAX, 0.f, 0.f, 0x7fffffff};
+        const float4* __restrict__ tris = sc.tris_id;
+        for (int i = 0; i < sc.nBruteTris; ++i) {
+            const float4 q0 = __ldg(tris + 3 * i);
+            const int id = __float_as_int(q0.w);
+            if (id >= cur) break; // primitive-id order
+            const float4 q1 = __ldg(tris + 3 * i + 1), q2 = __ldg(tris + 3 * i + 2);
+            float t, u, v;
+            if (rayTriangle(o, d, xyz(q0), xyz(q1), xyz(q2), t, u, v)) consider(best, t, u, v, id);
+        }
+        bool sphereWins = false;
+        for (int k = 0; k < sc.nSpheres; ++k) {
+            const float4 cr = __ldg(sc.spheres + 2 * k);
+            const int id = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1)).x;
+            float t;
+            if (id < cur && sphereT(cr, o, d, t) && (t < best.t || (t == best.t && id < best.prim))) { best.t = t; best.prim = id; sphereWins = true; }
+        }
+        if (best.prim == 0x7fffffff) return;          // nothing in front of the sphere in visiting order: zero-initialised
+        if (sphereWins && best.prim < cur) {           // an earlier sphere was the closest so far: look before it
+            bool isSphere = false;
+            for (int k = 0; k < sc.nSpheres; ++k) isSphere = isSphere || __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * k + 1)).x == best.prim;
+            if (isSphere) { cur = best.prim; continue; }
+        }
+        const float4 p0 = __ldg(sc.prims + 4 * best.prim), p1 = __ldg(sc.prims + 4 * best.prim + 1), p2 = __ldg(sc.prims + 4 * best.prim + 2);
+        const V3 ns = xyz(p0) * (1.0f - best.u - best.v) + xyz(p1) * best.u + xyz(p2) * best.v;
+        orthonormalBasis(ns, dpdu, dpdv);
+        return;
+    }
+}
+
 __device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit& h, Surf& s)
 {
     const float4 p3 = __ldg(sc.prims + 4 * h.prim + 3);
@@ -30,6 +72,9 @@ __device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit
         s.ng = normalize(s.pos - xyz(p0));
         s.ns = s.ng;
         s.dpdu = mk(0.f); s.dpdv = mk(0.f);
+        if constexpr (kExact) {
+            if ((s.meta & kMetaHasMaterial) != 0) sphereStaleBasis(sc, o, d, h.prim, s.dpdu, s.dpdv);
+        }
     }
     else {
         s.ng = mk(0.f); s.ns = mk(0.f); s.dpdu = mk(0.f); s.dpdv = mk(0.f);

@@ -712,6 +712,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         // connect -> extend; see wavefront.cuh.
         const bool volumePaths = fusedPrimary && volume && s->ds.nMedia <= 8 && s->ds.nGrids <= 8 && envInt("XRT_VOLUME_PATHS", 1) != 0;
         const bool fusedBounce = fusedPrimary && small && !brute && bruteSecondary && bruteShadow && envInt("XRT_FUSED_BOUNCE", 1) != 0 &&
+                                 s->ds.nPrims <= 96 && s->ds.nLights <= 8 && // what k_bounce_small stages in shared memory (kSmallPrims / kSmallLights)
                                  (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
         if (nIter == 0) CU(cudaMemsetAsync(q.radiance, 0, sizeof(float4) * size_t(w.nPaths), st));
         else if (!fusedPrimary) { K.raygen(st, dc, q, w, nullptr); ++launches; }

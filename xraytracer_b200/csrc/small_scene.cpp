@@ -41,6 +41,37 @@ void put(std::vector<float>& v, size_t f4, float a, float b, float c, float d)
 }
 float asFloat(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 
+// One logical record: 20 floats (N|d, A: n1|d1, n2|d2, B: n1|d1, n2|d2) + the two primitive ids.
+struct Rec {
+    float f[20];
+    int id[2];
+};
+Rec dummyRecord() // a plane no ray can hit (N = 0 -> det = 0) holding two triangles no point is inside of
+{
+    Rec r{};
+    r.f[3] = 1.f;
+    r.f[7] = r.f[11] = r.f[15] = r.f[19] = -1.f;
+    r.id[0] = r.id[1] = -1;
+    return r;
+}
+// Records are stored in PAIRS, component-interleaved, so that the kernel handles two records per packed fp32x2 instruction
+// (FFMA2 / FADD2 / FMUL2 of sm_100): float 2c + j of a pair's 40 floats is component c of its record j.
+void writeRecord(std::vector<float>& out, size_t offRecs, size_t offIds, size_t r, const Rec& rec)
+{
+    const size_t pair = r / 2, j = r % 2;
+    for (int c = 0; c < 20; ++c) out[4 * (offRecs + 10 * pair) + 2 * size_t(c) + j] = rec.f[c];
+    out[4 * (offIds + pair) + 2 * j] = asFloat(rec.id[0]);
+    out[4 * (offIds + pair) + 2 * j + 1] = asFloat(rec.id[1]);
+}
+Rec readRecord(const std::vector<float>& blk, size_t offRecs, size_t offIds, size_t r)
+{
+    Rec rec{};
+    const size_t pair = r / 2, j = r % 2;
+    for (int c = 0; c < 20; ++c) rec.f[c] = blk[4 * (offRecs + 10 * pair) + 2 * size_t(c) + j];
+    for (int k = 0; k < 2; ++k) std::memcpy(&rec.id[k], &blk[4 * (offIds + pair) + 2 * j + size_t(k)], 4);
+    return rec;
+}
+
 // one section; returns its size in float4
 size_t emitSection(const float* rec, const std::vector<int>& tris, const std::vector<Plane>& planes, size_t at, std::vector<float>& out, int& nRecords,
                    int& nPlanes)
@@ -55,32 +86,29 @@ size_t emitSection(const float* rec, const std::vector<int>& tris, const std::ve
     nPlanes = int(groups.size());
     nRecords = 0;
     for (auto& g : groups) nRecords += int((g.size() + 1) / 2);
-    const size_t offRecs = at + 1, offIds = offRecs + 5 * size_t(nRecords);
-    const size_t end = offIds + (2 * size_t(nRecords) + 3) / 4;
+    const size_t nPairs = (size_t(nRecords) + 1) / 2;
+    const size_t offRecs = at + 1, offIds = offRecs + 10 * nPairs;
+    const size_t end = offIds + nPairs;
     out.resize(4 * end, 0.f);
-    put(out, at, asFloat(nRecords), 0.f, asFloat(int(offRecs)), asFloat(int(offIds)));
+    put(out, at, asFloat(nRecords), asFloat(int(nPairs)), asFloat(int(offRecs)), asFloat(int(offIds)));
     size_t r = 0;
     for (const auto& g : groups) {
         const float* r0 = rec + 16 * size_t(g[0]); // the plane words of the group's first triangle serve every record of the plane
         for (size_t k = 0; k < g.size(); k += 2, ++r) {
+            Rec R = dummyRecord();
+            std::memcpy(R.f, r0, 16);
             const float* a = rec + 16 * size_t(g[k]);
-            put(out, offRecs + 5 * r, r0[0], r0[1], r0[2], r0[3]);
-            put(out, offRecs + 5 * r + 1, a[4], a[5], a[6], a[7]);
-            put(out, offRecs + 5 * r + 2, a[8], a[9], a[10], a[11]);
-            out[4 * offIds + 2 * r] = a[12];
+            std::memcpy(R.f + 4, a + 4, 32);
+            std::memcpy(&R.id[0], a + 12, 4);
             if (k + 1 < g.size()) {
                 const float* b = rec + 16 * size_t(g[k + 1]);
-                put(out, offRecs + 5 * r + 3, b[4], b[5], b[6], b[7]);
-                put(out, offRecs + 5 * r + 4, b[8], b[9], b[10], b[11]);
-                out[4 * offIds + 2 * r + 1] = b[12];
+                std::memcpy(R.f + 12, b + 4, 32);
+                std::memcpy(&R.id[1], b + 12, 4);
             }
-            else {
-                put(out, offRecs + 5 * r + 3, 0.f, 0.f, 0.f, -1.f);
-                put(out, offRecs + 5 * r + 4, 0.f, 0.f, 0.f, -1.f);
-                out[4 * offIds + 2 * r + 1] = asFloat(-1);
-            }
+            writeRecord(out, offRecs, offIds, r, R);
         }
     }
+    if (r % 2) writeRecord(out, offRecs, offIds, r, dummyRecord()); // odd count: the last pair's second half
     return end - at;
 }
 
@@ -121,12 +149,19 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
     if (size_t(total) * 4 != block.size() || total > kSmallBlockMaxF4) return -1;
     for (int sec = 0; sec < 2; ++sec) {
         const int off = asInt(block[size_t(sec)]);
-        const int nRec = asInt(block[4 * size_t(off)]), offRecs = asInt(block[4 * size_t(off) + 2]), offIds = asInt(block[4 * size_t(off) + 3]);
+        const int nRec = asInt(block[4 * size_t(off)]), nPairs = asInt(block[4 * size_t(off) + 1]), offRecs = asInt(block[4 * size_t(off) + 2]),
+                  offIds = asInt(block[4 * size_t(off) + 3]);
+        if (nPairs != (nRec + 1) / 2) return -1;
         std::vector<int> seen(size_t(n), 0);
-        for (int r = 0; r < nRec; ++r) {
-            const float* R = &block[4 * (size_t(offRecs) + 5 * size_t(r))];
+        for (int r = 0; r < 2 * nPairs; ++r) {
+            const Rec rec = readRecord(block, size_t(offRecs), size_t(offIds), size_t(r));
+            const float* R = rec.f;
+            if (r >= nRec) { // the dummy half of the last pair: a plane with N = 0
+                if (R[0] != 0.f || R[1] != 0.f || R[2] != 0.f || rec.id[0] != -1 || rec.id[1] != -1) return -1;
+                continue;
+            }
             for (int k = 0; k < 2; ++k) {
-                const int id = asInt(block[4 * size_t(offIds) + 2 * size_t(r) + size_t(k)]);
+                const int id = rec.id[k];
                 const float* a = R + 4 + 8 * k;
                 if (id < 0) { // padding: n1 = n2 = 0, d1 = d2 = -1
                     if (k == 0 || a[0] != 0.f || a[1] != 0.f || a[2] != 0.f || a[3] != -1.f || a[7] != -1.f) return -1;
@@ -200,8 +235,9 @@ bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block,
     const size_t total = offOcc + nOcc;
     put(block, 0, asFloat(int(offAll)), asFloat(int(offOcc)), asFloat(int(total)), 0.f);
     if (info) *info = bi;
-    // pays only if most triangles find a coplanar partner: ~48 instructions per record against ~33 per triangle of the plain loop
-    const bool pays = 48.0 * bi.nRecordsAll < 0.9 * 33.0 * nTris;
+    // pays only if most triangles find a coplanar partner: ~31 instructions per record (packed, two records at a time) against
+    // ~33 per triangle of the plain loop
+    const bool pays = 31.0 * bi.nRecordsAll < 0.8 * 33.0 * nTris;
     if (!pays || total > size_t(kSmallBlockMaxF4)) { block.clear(); return false; }
     return true;
 }

@@ -4,10 +4,14 @@
 // share ONE ray/plane intersection; each triangle then costs only its two barycentric plane equations. The block is copied
 // verbatim into shared memory by k_bounce_small (wavefront.cuh) — layout in float4 units:
 //   [0]            int4 (offAll, offOcc, totalF4, 0)
-//   section:       int4 (nRecords, 0, offRecords, offIds)          offsets from the start of the block
-//                  5 float4 per record:  N.xyz | d ,  n1.xyz | d1 , n2.xyz | d2  (triangle A) ,  n1 | d1 , n2 | d2  (triangle B)
-//                                        an unpaired triangle gets a B that no point is inside of (0 | -1 , 0 | -1)
-//                  2 ints per record:    primitive ids of A and B (-1 for padding)
+//   section:       int4 (nRecords, nPairs, offRecords, offIds)          offsets from the start of the block
+//                  one record = a supporting plane and two triangles in it, 20 floats:
+//                      N.xyz | d ,  A: n1.xyz | d1 , n2.xyz | d2 ,  B: n1 | d1 , n2 | d2
+//                  (an unpaired triangle gets a B that no point is inside of: 0 | -1 , 0 | -1)
+//                  10 float4 per PAIR of records, component-interleaved — float 2c + j is component c of record j — so that
+//                  the kernel computes two records per packed fp32x2 instruction; an odd count is completed by a dummy
+//                  record whose plane no ray can hit (N = 0)
+//                  1 int4 per pair: primitive ids (A, B) of record 0, (A, B) of record 1; -1 for padding
 // Records of one plane are consecutive, carry bit-identical plane words and are in primitive-id order, so "strictly smaller t
 // wins" between records and "A before B" inside one reproduce the reference's first-wins rule for coplanar duplicates.
 // `All` holds every mesh triangle (closest hit), `Occ` only the triangles that are not emitter proxies (Scene::occluded skips

@@ -53,22 +53,26 @@ __device__ __noinline__ void sphereStaleBasis(const DScene& sc, V3 o, V3 d, int 
     }
 }
 
-__device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit& h, Surf& s)
+template <bool SMEM>
+__device__ __forceinline__ float4 primWord(const float4* prims, int i) { return SMEM ? prims[i] : __ldg(prims + i); }
+// SMEM: `prims` is the CTA's shared-memory copy of the shading records (small scenes), otherwise sc.prims in global memory
+template <bool SMEM>
+__device__ __forceinline__ void makeSurfT(const DScene& sc, const float4* prims, V3 o, V3 d, const Hit& h, Surf& s)
 {
-    const float4 p3 = __ldg(sc.prims + 4 * h.prim + 3);
+    const float4 p3 = primWord<SMEM>(prims, 4 * h.prim + 3);
     s.meta = __float_as_uint(p3.w);
     s.albedo = xyz(p3);
     s.pos = o + h.t * d;
     s.t1 = h.u;
     const uint32_t kind = s.meta & kMetaKindMask;
     if (kind == XRTG_OBJ_MESH) {
-        const float4 p0 = __ldg(sc.prims + 4 * h.prim), p1 = __ldg(sc.prims + 4 * h.prim + 1), p2 = __ldg(sc.prims + 4 * h.prim + 2);
+        const float4 p0 = primWord<SMEM>(prims, 4 * h.prim), p1 = primWord<SMEM>(prims, 4 * h.prim + 1), p2 = primWord<SMEM>(prims, 4 * h.prim + 2);
         s.ng = mk(p0.w, p1.w, p2.w);
         s.ns = xyz(p0) * (1.0f - h.u - h.v) + xyz(p1) * h.u + xyz(p2) * h.v;
         orthonormalBasis(s.ns, s.dpdu, s.dpdv);
     }
     else if (kind == XRTG_OBJ_SPHERE) {
-        const float4 p0 = __ldg(sc.prims + 4 * h.prim);
+        const float4 p0 = primWord<SMEM>(prims, 4 * h.prim);
         s.ng = normalize(s.pos - xyz(p0));
         s.ns = s.ng;
         s.dpdu = mk(0.f); s.dpdv = mk(0.f);
@@ -80,17 +84,19 @@ __device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit
         s.ng = mk(0.f); s.ns = mk(0.f); s.dpdu = mk(0.f); s.dpdv = mk(0.f);
     }
 }
+__device__ __forceinline__ void makeSurf(const DScene& sc, V3 o, V3 d, const Hit& h, Surf& s) { makeSurfT<false>(sc, sc.prims, o, d, h, s); }
 __device__ __forceinline__ bool hasMaterial(const Surf& s) { return (s.meta & kMetaHasMaterial) != 0; }
 __device__ __forceinline__ int lightOf(const Surf& s) { return int((s.meta >> kMetaLightShift) & 0xfffu) - 1; }
 __device__ __forceinline__ int mediumOf(const Surf& s) { return int((s.meta >> kMetaMediumShift) & 0xfffu) - 1; }
 
 // AreaLight::Le (light.h:62-69)
-__device__ __forceinline__ V3 emitted(const DScene& sc, const Surf& s, V3 rayDir)
+__device__ __forceinline__ V3 emittedFrom(const DLight* lights, const Surf& s, V3 rayDir)
 {
     const int li = lightOf(s);
     if (li < 0) return mk(0.f);
-    return (dot(rayDir, s.ns) < 0) ? xyz(sc.lights[li].Le) : mk(0.f);
+    return (dot(rayDir, s.ns) < 0) ? xyz(lights[li].Le) : mk(0.f);
 }
+__device__ __forceinline__ V3 emitted(const DScene& sc, const Surf& s, V3 rayDir) { return emittedFrom(sc.lights, s, rayDir); }
 
 // AreaLight::sample: quad light.cpp:59-68, triangle light.cpp:21-30 + :43-47, sphere light.h:158-197.
 // Draw order as compiled by g++ (second-written getNext1D() draws first), pinned by the oracle KATs.
@@ -393,39 +399,64 @@ __device__ __forceinline__ bool anyHitSmall(const DScene& sc, V3 o, V3 d, float 
 __device__ __forceinline__ float4* hitBuffer(const DQueues& q, int bounce) { return (bounce & 1) ? q.s0 : q.hits; }
 
 // Plane-paired small scene (small_scene.h), throughput instantiation: one record = one supporting plane + two triangles in it;
-// one ray/plane intersection and two barycentric plane equations per triangle. Branch-free per lane.
+// one ray/plane intersection and two barycentric plane equations per triangle. Records come in component-interleaved PAIRS and
+// all the fp32 arithmetic of a pair runs as packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2, sm_100): 26 packed
+// instructions do what 52 scalar ones did, and the loops are bound by issue slots, not by the FMA pipe. Branch-free per lane.
 struct SmallSection {
-    const float4* recs; // 5 per record: N|d , A: n1|d1 , n2|d2 , B: n1|d1 , n2|d2
-    const int* ids;     // 2 per record
-    int nRecords;
+    const float4* recs; // 10 per pair of records (float 2c + j = component c of record j)
+    const int4* ids;    // per pair: (A, B) of record 0, (A, B) of record 1
+    int nPairs;
 };
 __device__ __forceinline__ SmallSection smallSection(const float4* blk, int off)
 {
     const int4 h = *reinterpret_cast<const int4*>(blk + off);
-    return SmallSection{blk + h.z, reinterpret_cast<const int*>(blk + h.w), h.x};
+    return SmallSection{blk + h.z, reinterpret_cast<const int4*>(blk + h.w), h.y};
 }
-__device__ __forceinline__ float insideness(const float4 a, const float4 b, V3 P)
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+// the ray, broadcast into both halves once per ray
+struct Ray2 {
+    float2 nox, noy, noz, dx, dy, dz, ox, oy, oz;
+};
+__device__ __forceinline__ Ray2 makeRay2(V3 o, V3 d)
 {
-    const float u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
-    const float v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
-    return fminf(fminf(u, v), 1.f - (u + v)); // >= 0 <=> u >= 0, v >= 0, u + v <= 1
+    return Ray2{make_float2(-o.x, -o.x), make_float2(-o.y, -o.y), make_float2(-o.z, -o.z), make_float2(d.x, d.x), make_float2(d.y, d.y),
+                make_float2(d.z, d.z), make_float2(o.x, o.x), make_float2(o.y, o.y), make_float2(o.z, o.z)};
+}
+// det = N.d and t = (d - N.o) / det of the two planes of a pair
+__device__ __forceinline__ void planes2(const float4 q0, const float4 q1, const Ray2& r, float2& det, float2& t)
+{
+    const float2 Nx = lo2(q0), Ny = hi2(q0), Nz = lo2(q1), dd = hi2(q1);
+    det = __ffma2_rn(Nz, r.dz, __ffma2_rn(Ny, r.dy, __fmul2_rn(Nx, r.dx)));
+    const float2 num = __ffma2_rn(Nx, r.nox, __ffma2_rn(Ny, r.noy, __ffma2_rn(Nz, r.noz, dd)));
+    t = __fmul2_rn(num, make_float2(1.0f / det.x, 1.0f / det.y));
+}
+// min(u, v, 1 - u - v) of one triangle slot (A: k = 2, B: k = 6) for both records of the pair; >= 0 <=> inside
+__device__ __forceinline__ float2 insideness2(const float4* q, int k, float2 Px, float2 Py, float2 Pz)
+{
+    const float4 a = q[k], b = q[k + 1], c = q[k + 2], e = q[k + 3];
+    const float2 u = __ffma2_rn(Px, lo2(a), __ffma2_rn(Py, hi2(a), __ffma2_rn(Pz, lo2(b), hi2(b))));
+    const float2 v = __ffma2_rn(Px, lo2(c), __ffma2_rn(Py, hi2(c), __ffma2_rn(Pz, lo2(e), hi2(e))));
+    const float2 w = __ffma2_rn(__fadd2_rn(u, v), make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+    return make_float2(fminf(fminf(u.x, v.x), w.x), fminf(fminf(u.y, v.y), w.y));
 }
 // Any hit with eps < t < tmax among the occluders; lanes without a shadow ray pass tmax < 0. Must be called by all 32 lanes of
-// a converged warp: a plane that no lane can hit (behind every ray or beyond every tmax — the floor and the ceiling for every
-// shadow ray towards the Cornell light) is skipped with one vote.
+// a converged warp: a pair of planes that no lane can hit (behind every ray or beyond every tmax) is skipped with one vote.
 __device__ __forceinline__ bool groupedAnyHit(const SmallSection& S, V3 o, V3 d, float tmax)
 {
+    const Ray2 r = makeRay2(o, d);
     float acc = -1.f;
-    for (int r = 0; r < S.nRecords; ++r) {
-        const float4* rec = S.recs + 5 * r;
-        const float4 pl = rec[0];
-        const float det = dot(xyz(pl), d);
-        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
-        const bool vt = !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < tmax;
-        if (!__any_sync(0xffffffffu, vt)) continue;
-        const V3 P = o + t * d;
-        const float m = fmaxf(insideness(rec[1], rec[2], P), insideness(rec[3], rec[4], P));
-        acc = fmaxf(acc, vt ? m : -1.f);
+    for (int p = 0; p < S.nPairs; ++p) {
+        const float4* q = S.recs + 10 * p;
+        float2 det, t;
+        planes2(q[0], q[1], r, det, t);
+        const bool v0 = !(fabsf(det.x) < FLT_EPSILON) && t.x > FLT_EPSILON && t.x < tmax;
+        const bool v1 = !(fabsf(det.y) < FLT_EPSILON) && t.y > FLT_EPSILON && t.y < tmax;
+        if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+        const float2 Px = __ffma2_rn(t, r.dx, r.ox), Py = __ffma2_rn(t, r.dy, r.oy), Pz = __ffma2_rn(t, r.dz, r.oz);
+        const float2 mA = insideness2(q, 2, Px, Py, Pz), mB = insideness2(q, 6, Px, Py, Pz);
+        acc = fmaxf(acc, v0 ? fmaxf(mA.x, mB.x) : -1.f);
+        acc = fmaxf(acc, v1 ? fmaxf(mA.y, mB.y) : -1.f);
     }
     return acc >= 0.f;
 }
@@ -433,28 +464,31 @@ __device__ __forceinline__ bool groupedAnyHit(const SmallSection& S, V3 o, V3 d,
 // want = false.
 __device__ __forceinline__ void groupedClosest(const SmallSection& S, V3 o, V3 d, bool want, Hit& h)
 {
+    const Ray2 r = makeRay2(o, d);
     float best = want ? FLT_MAX : -1.f;
     int bi = -1;
-#pragma unroll 4
-    for (int r = 0; r < S.nRecords; ++r) {
-        const float4* rec = S.recs + 5 * r;
-        const float4 pl = rec[0];
-        const float det = dot(xyz(pl), d);
-        const float t = fmaf(-o.x, pl.x, fmaf(-o.y, pl.y, fmaf(-o.z, pl.z, pl.w))) * (1.0f / det);
-        const V3 P = o + t * d;
-        const float m0 = insideness(rec[1], rec[2], P), m1 = insideness(rec[3], rec[4], P);
-        const bool take = fmaxf(m0, m1) >= 0.f && !(fabsf(det) < FLT_EPSILON) && t > FLT_EPSILON && t < best;
-        best = take ? t : best;
-        bi = take ? (m0 >= 0.f ? 2 * r : 2 * r + 1) : bi;
+#pragma unroll 2
+    for (int p = 0; p < S.nPairs; ++p) {
+        const float4* q = S.recs + 10 * p;
+        float2 det, t;
+        planes2(q[0], q[1], r, det, t);
+        const float2 Px = __ffma2_rn(t, r.dx, r.ox), Py = __ffma2_rn(t, r.dy, r.oy), Pz = __ffma2_rn(t, r.dz, r.oz);
+        const float2 mA = insideness2(q, 2, Px, Py, Pz), mB = insideness2(q, 6, Px, Py, Pz);
+        const bool take0 = fmaxf(mA.x, mB.x) >= 0.f && !(fabsf(det.x) < FLT_EPSILON) && t.x > FLT_EPSILON && t.x < best;
+        best = take0 ? t.x : best;
+        bi = take0 ? (mA.x >= 0.f ? 4 * p : 4 * p + 1) : bi;
+        const bool take1 = fmaxf(mA.y, mB.y) >= 0.f && !(fabsf(det.y) < FLT_EPSILON) && t.y > FLT_EPSILON && t.y < best;
+        best = take1 ? t.y : best;
+        bi = take1 ? (mA.y >= 0.f ? 4 * p + 2 : 4 * p + 3) : bi;
     }
-    if (bi >= 0) {
-        const float4* rec = S.recs + 5 * (bi >> 1) + 1 + 2 * (bi & 1);
-        const float4 a = rec[0], b = rec[1];
+    if (bi >= 0) { // re-derive u, v and the primitive id of the winner: slot bi = 4 * pair + 2 * record + (A / B)
+        const float* f = reinterpret_cast<const float*>(S.recs + 10 * (bi >> 2));
+        const int j = (bi >> 1) & 1, k = 8 + 16 * (bi & 1); // float index of n1.x of triangle A / B, record j in the odd floats
         const V3 P = o + best * d;
         h.t = best;
-        h.u = fmaf(P.x, a.x, fmaf(P.y, a.y, fmaf(P.z, a.z, a.w)));
-        h.v = fmaf(P.x, b.x, fmaf(P.y, b.y, fmaf(P.z, b.z, b.w)));
-        h.prim = S.ids[bi];
+        h.u = fmaf(P.x, f[k + j], fmaf(P.y, f[k + 2 + j], fmaf(P.z, f[k + 4 + j], f[k + 6 + j])));
+        h.v = fmaf(P.x, f[k + 8 + j], fmaf(P.y, f[k + 10 + j], fmaf(P.z, f[k + 12 + j], f[k + 14 + j])));
+        h.prim = reinterpret_cast<const int*>(S.ids)[bi];
     }
 }
 
@@ -468,6 +502,13 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     __shared__ float4 s_block[GROUPED ? kSmallBlockF4 : 1];
     __shared__ uint32_t s_scratch[kBlock / 32 + 1];
     __shared__ int s_nOcc;
+    // shading records and lights of a small scene live in shared memory too: the queue traffic streams through L1 and would keep
+    // evicting them (every entry reads 4-5 of these words on its dependency chain)
+    __shared__ float4 s_prims[4 * kSmallPrims];
+    __shared__ DLight s_lights[kSmallLights];
+    for (int k = threadIdx.x; k < 4 * sc.nPrims; k += blockDim.x) s_prims[k] = sc.prims[k];
+    for (int k = threadIdx.x; k < sc.nLights * int(sizeof(DLight) / sizeof(float4)); k += blockDim.x)
+        reinterpret_cast<float4*>(s_lights)[k] = reinterpret_cast<const float4*>(sc.lights)[k];
     SmallSection secAll{}, secOcc{};
     const float4* occTris = nullptr;
     int nOcc = 0;
@@ -554,15 +595,15 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
             rad = q.radiance[pid];
             const Hit h{hv.x, hv.y, hv.z, __float_as_int(hv.w)};
             rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
-            makeSurf(sc, o, d, h, s);
+            makeSurfT<true>(sc, s_prims, o, d, h, s);
             if (kind == XRTG_INT_DIRECT) {
-                if (lightOf(s) >= 0) add(emitted(sc, s, d));
+                if (lightOf(s) >= 0) add(emittedFrom(s_lights, s, d));
                 else shadeLights = true;
             }
             else if (kind == XRTG_INT_WHITTED) shadeDelta = hasMaterial(s);
             else { // Indirect / GI. Entries of bounce > 0 already passed RR and the emitter test in the kernel that traced them.
                 bool alive = true;
-                if (bounce == 0 && lightOf(s) >= 0) { add(T * emitted(sc, s, d)); alive = false; }
+                if (bounce == 0 && lightOf(s) >= 0) { add(T * emittedFrom(s_lights, s, d)); alive = false; }
                 shadeLights = alive && kind == XRTG_INT_GI;
                 bsdf = alive;
             }
@@ -575,7 +616,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
                 float tmax = 0.f;
                 if (shadeLights) {
                     float pdf = 0.0f;
-                    const V3 Lr = sampleLight(sc.lights[li], s.pos, wi, pdf, tmax, rng);
+                    const V3 Lr = sampleLight(s_lights[li], s.pos, wi, pdf, tmax, rng);
                     if (pdf != 0) {
                         const float cs = smax(0.0f, dot(s.ng, wi));
                         const V3 fr = evalBxDF(s);
@@ -629,12 +670,12 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
                 const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
                 if (!(rng.next() >= p)) {
                     nT = nT / mk(p);
-                    const uint32_t meta = __float_as_uint(__ldg(sc.prims + 4 * nh.prim + 3).w);
+                    const uint32_t meta = __float_as_uint(s_prims[4 * nh.prim + 3].w);
                     if (((meta >> kMetaLightShift) & 0xfffu) == 0) wantNext = true;
                     else if (kind == XRTG_INT_INDIRECT) { // Le at any depth (integrator.h:150-160); GI only at depth 0
                         Surf s2;
-                        makeSurf(sc, no, nd, nh, s2);
-                        add(nT * emitted(sc, s2, nd));
+                        makeSurfT<true>(sc, s_prims, no, nd, nh, s2);
+                        add(nT * emittedFrom(s_lights, s2, nd));
                     }
                 }
             }

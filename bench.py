@@ -372,8 +372,8 @@ def main():
                                            "shadow rays skip planes no lane of the warp can reach)",
                                   "records_closest": info["small_records_all"], "records_occluders": info["small_records_occ"]},
                         "launches": int(launches_b), "avg_launch_ms": b_ms / launches_b, "share_of_step": share,
-                        "note": "instruction-issue bound (ncu: ~65 % issue-active at 31 of 32 lanes), not memory bound: a 36-triangle scene cannot "
-                                "saturate HBM; the fraction says how far the queue traffic is from the HBM roof"}
+                        "note": "latency / dependency bound (ncu: ~57 % issue-active at 31 of 32 lanes, 4.6 warps per scheduler), not memory bound: a "
+                                "36-triangle scene cannot saturate HBM; the fraction says how far the queue traffic is from the HBM roof"}
         elif wl["integrator"].startswith("volume") and agg[7] > 0 and agg[4] > agg[3]:
             # ---- volume workloads: the dominant kernel is the path kernel k_volume_paths (delta tracking, run to completion) ----
             # achieved = algorithmic bytes / CUDA-event time of its launches, rank 0: SURVEY §8(d)'s 8 voxels x 4 B = 32 B per tracking

@@ -572,9 +572,29 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
     const int kind = w.integrator;
     uint32_t nClosest = 0, nShadow = 0;
-    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
+    // The queue entries of the CTA's NEXT tile are copied into shared memory with cp.async while the current tile is being
+    // worked on (each thread stages and later reads only its own 4 x 16 B, so no barrier is needed, just its own wait_group):
+    // the HBM latency of the four queue loads at the head of every tile's dependency chain is hidden behind a whole tile of work.
+    __shared__ float4 s_stage[2][4][kBlock];
+    auto stage = [&](int buf, uint64_t tile) {
+        const uint64_t e = tile * kBlock + threadIdx.x;
+        if (e < n) {
+            const float4* src[4] = {hitsIn + e, in0 + e, in1 + e, in2 + e};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint32_t dst = uint32_t(__cvta_generic_to_shared(&s_stage[buf][a][threadIdx.x]));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[a]) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, blockIdx.x);
+    int buf = 0;
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x, buf ^= 1) {
         const uint32_t i = tile * kBlock + threadIdx.x;
         const bool live = i < n;
+        stage(buf ^ 1, uint64_t(tile) + gridDim.x);
+        asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
         // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
         V3 d = mk(0.f), T = mk(0.f);
         uint32_t pid = 0, ctr = 0;
@@ -586,7 +606,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         Surf s = {};
         bool shadeLights = false, shadeDelta = false, bsdf = false;
         if (live) {
-            const float4 hv = hitsIn[i], r0 = in0[i], r1 = in1[i], r2 = in2[i];
+            const float4 hv = s_stage[buf][0][threadIdx.x], r0 = s_stage[buf][1][threadIdx.x], r1 = s_stage[buf][2][threadIdx.x], r2 = s_stage[buf][3][threadIdx.x];
             const V3 o = xyz(r0);
             d = xyz(r1);
             T = mk(r0.w, r1.w, r2.x);

@@ -293,7 +293,8 @@ int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float*
 
 /* Host-only structural check of the SAH BVH builder (no CUDA device needed): builds the tree over n triangles (9 floats each:
  * v0 v1 v2) and verifies that every triangle is referenced by exactly one leaf, that every child box (minus the conservative
- * padding) contains its subtree, that leaves hold at most max_leaf triangles and that the depth fits the traversal stacks.
+ * padding) contains its subtree, that leaves hold at most max_leaf triangles and that the depth fits the traversal stacks;
+ * then collapses the tree to the four-child form deep scenes are traversed in and checks the same properties on it.
  * Returns 0 if the tree is valid, a negative xrtg_status otherwise; the out parameters may be NULL. */
 int xrtg_bvh_selftest(const float* tris9, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost);
 

@@ -95,7 +95,7 @@ struct xrtg_scene {
     int device = 0;
     cudaStream_t stream = nullptr; // uploads + host-buffer renders
     // scene arrays (pinned host copy + device copy)
-    Mirror nodes, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
+    Mirror nodes, nodes4, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
     std::vector<std::unique_ptr<Mirror>> gridData;
     DScene ds{};
     xrtg_scene_info info{};
@@ -124,7 +124,7 @@ namespace {
 
 int uploadAll(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[] = {&s->nodes, &s->nodes4, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
     for (Mirror* m : all) {
         if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
@@ -349,6 +349,15 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         for (size_t k = 0; k < bvh.triOrder.size(); ++k)
             std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(bvh.triOrder[k]), 4 * sizeof(float4));
     }
+    // ---- deep trees: four-child form for the resumable traversal kernel (bvh.h) ----
+    if (bvh.nodes.size() > 512 && std::getenv("XRT_NO_BVH4") == nullptr) {
+        std::vector<Bvh4Node> wide;
+        const int depth4 = collapseBvh4(static_cast<const BvhNode*>(s->nodes.h), bvh.nodes.size(), wide);
+        if (3 * depth4 + 1 <= 64) { // a four-child node pushes up to three entries: must fit the traversal stack (24 shared + 40 local)
+            if (int rc = s->nodes4.alloc(sizeof(Bvh4Node) * wide.size())) return rc;
+            std::memcpy(s->nodes4.h, wide.data(), s->nodes4.bytes);
+        }
+    }
     // ---- small scenes: plane-grouped triangle block for k_bounce_small (small_scene.h) ----
     int smallBlockF4 = 0;
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
@@ -441,6 +450,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
 
     DScene& ds = s->ds;
     ds.nodes = static_cast<const float4*>(s->nodes.d);
+    ds.nodes4 = static_cast<const float4*>(s->nodes4.d);
     ds.tris = static_cast<const float4*>(s->tris.d);
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
     ds.ftris = static_cast<const float4*>(s->ftris.d);
@@ -890,6 +900,50 @@ int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* 
     if (!visit(0, 0, all)) return fail(XRTG_ERR_INVALID, err);
     for (int t = 0; t < n; ++t)
         if (seen[size_t(t)] != 1) return fail(XRTG_ERR_INVALID, "selftest: a triangle is referenced " + std::to_string(seen[size_t(t)]) + " times");
+    // ---- the four-child form of the same tree: same leaves, every child box contains its subtree ----
+    std::vector<Bvh4Node> wide;
+    const int depth4 = collapseBvh4(bvh.nodes.data(), bvh.nodes.size(), wide);
+    if (depth4 > bvh.depth) return fail(XRTG_ERR_INVALID, "selftest: the collapsed tree is deeper than the binary one");
+    std::fill(seen.begin(), seen.end(), 0);
+    std::function<bool(int, int, Range&)> visit4 = [&](int child, int count, Range& out) -> bool {
+        for (int a = 0; a < 3; ++a) { out.lo[a] = FLT_MAX; out.hi[a] = -FLT_MAX; }
+        if (count > 0) {
+            if (count > max_leaf) { err = "selftest: wide leaf larger than max_leaf"; return false; }
+            for (int k = 0; k < count; ++k) {
+                const uint32_t t = bvh.triOrder[size_t(child) + k];
+                seen[t]++;
+                for (int v = 0; v < 3; ++v)
+                    for (int a = 0; a < 3; ++a) {
+                        out.lo[a] = std::min(out.lo[a], tri[9 * size_t(t) + 3 * v + a]);
+                        out.hi[a] = std::max(out.hi[a], tri[9 * size_t(t) + 3 * v + a]);
+                    }
+            }
+            return true;
+        }
+        if (child < 0 || size_t(child) >= wide.size()) { err = "selftest: wide node index out of range"; return false; }
+        const Bvh4Node& nd = wide[size_t(child)];
+        int used = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (nd.count[k] < 0) continue;
+            ++used;
+            Range r;
+            if (!visit4(nd.child[k], nd.count[k], r)) return false;
+            const float lo[3] = {nd.lox[k], nd.loy[k], nd.loz[k]}, hi[3] = {nd.hix[k], nd.hiy[k], nd.hiz[k]};
+            for (int a = 0; a < 3; ++a) {
+                if (!(lo[a] <= r.lo[a] - 0.5f * bvh.pad) || !(hi[a] >= r.hi[a] + 0.5f * bvh.pad)) {
+                    err = "selftest: wide child box does not contain its subtree with the conservative padding";
+                    return false;
+                }
+                out.lo[a] = std::min(out.lo[a], r.lo[a]);
+                out.hi[a] = std::max(out.hi[a], r.hi[a]);
+            }
+        }
+        if (used == 0) { err = "selftest: wide node without children"; return false; }
+        return true;
+    };
+    if (!visit4(0, 0, all)) return fail(XRTG_ERR_INVALID, err);
+    for (int t = 0; t < n; ++t)
+        if (seen[size_t(t)] != 1) return fail(XRTG_ERR_INVALID, "selftest: the collapsed tree references a triangle " + std::to_string(seen[size_t(t)]) + " times");
     return 0;
 }
 

@@ -146,6 +146,72 @@ void setEmpty(BvhNode& n, int slot)
 
 } // namespace
 
+int collapseBvh4(const BvhNode* nodes, size_t nNodes, std::vector<Bvh4Node>& out)
+{
+    struct Slot { float lo[3], hi[3]; int32_t child, count; };
+    auto slotsOf = [&](int32_t n, Slot s[2]) {
+        const BvhNode& b = nodes[n];
+        for (int a = 0; a < 3; ++a) { s[0].lo[a] = b.lo0[a]; s[0].hi[a] = b.hi0[a]; s[1].lo[a] = b.lo1[a]; s[1].hi[a] = b.hi1[a]; }
+        s[0].child = b.child0; s[0].count = b.count0; s[1].child = b.child1; s[1].count = b.count1;
+    };
+    auto area = [](const Slot& s) {
+        const float dx = s.hi[0] - s.lo[0], dy = s.hi[1] - s.lo[1], dz = s.hi[2] - s.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    out.clear();
+    if (nNodes == 0) return 0;
+    struct Todo { int32_t bvh2, wide, depth; };
+    std::vector<Todo> stack{{0, 0, 1}};
+    out.emplace_back();
+    int depth = 0;
+    while (!stack.empty()) {
+        const Todo t = stack.back();
+        stack.pop_back();
+        depth = std::max(depth, t.depth);
+        Slot sl[4];
+        int n = 0;
+        Slot two[2];
+        slotsOf(t.bvh2, two);
+        for (int k = 0; k < 2; ++k) if (two[k].count >= 0) sl[n++] = two[k];
+        while (n < 4) { // open the largest inner child
+            int best = -1;
+            float bestArea = -1.f;
+            for (int k = 0; k < n; ++k)
+                if (sl[k].count == 0 && area(sl[k]) > bestArea) { bestArea = area(sl[k]); best = k; }
+            if (best < 0) break;
+            slotsOf(sl[best].child, two);
+            int added = 0;
+            Slot repl[2];
+            for (int k = 0; k < 2; ++k) if (two[k].count >= 0) repl[added++] = two[k];
+            if (added == 0) { sl[best] = sl[--n]; continue; }
+            if (n - 1 + added > 4) break;
+            sl[best] = repl[0];
+            if (added == 2) sl[n++] = repl[1];
+        }
+        Bvh4Node w;
+        for (int k = 0; k < 4; ++k) {
+            if (k < n) {
+                w.lox[k] = sl[k].lo[0]; w.loy[k] = sl[k].lo[1]; w.loz[k] = sl[k].lo[2];
+                w.hix[k] = sl[k].hi[0]; w.hiy[k] = sl[k].hi[1]; w.hiz[k] = sl[k].hi[2];
+                w.count[k] = sl[k].count;
+                if (sl[k].count == 0) { // inner: allocate the wide child now, fill it later
+                    w.child[k] = int32_t(out.size());
+                    out.emplace_back();
+                    stack.push_back({sl[k].child, w.child[k], t.depth + 1});
+                }
+                else w.child[k] = sl[k].child;
+            }
+            else {
+                w.lox[k] = w.loy[k] = w.loz[k] = FLT_MAX;
+                w.hix[k] = w.hiy[k] = w.hiz[k] = -FLT_MAX;
+                w.child[k] = 0; w.count[k] = -1;
+            }
+        }
+        out[size_t(t.wide)] = w;
+    }
+    return depth;
+}
+
 void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out)
 {
     out = Bvh();

@@ -28,6 +28,21 @@ struct Bvh {
     float pad = 0.f;                // absolute padding added to every box
 };
 
+// Four-child node for the resumable traversal kernel of deep trees (k_trace): 128 bytes = one cache line, children's boxes in SoA
+// so that two children share a packed fp32x2 instruction. Same child / count convention as BvhNode. One fetch decides among four
+// children: half as many DEPENDENT node fetches per ray as the two-child form, and the wait for the node fetch is the hottest
+// instruction of that kernel (profiles/r01_notes.md).
+struct Bvh4Node {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4], count[4];
+};
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be one 128-byte record");
+
+// Collapses a two-child tree (as produced by buildBvh or by the GPU LBVH builder) into four-child nodes: every wide node starts
+// from the two children of a BvhNode and repeatedly replaces its largest-area inner child by that child's two children. The
+// leaves and their (already padded) boxes are taken over unchanged. Returns the depth of the wide tree.
+int collapseBvh4(const BvhNode* nodes, size_t nNodes, std::vector<Bvh4Node>& out);
+
 // tri = n * 9 floats (v0 v1 v2). Binned SAH (16 bins, 3 axes), leaves of at most `maxLeaf` triangles.
 void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out);
 

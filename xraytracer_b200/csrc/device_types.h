@@ -47,6 +47,7 @@ struct DGrid {
 // Everything the kernels need to know about the scene; passed by value (fits the 4 KB param space).
 struct DScene {
     const float4* nodes;   // 4 float4 per BVH node (bvh.h: BvhNode)
+    const float4* nodes4;  // deep trees only: the same tree collapsed to four children per node, 8 float4 each (bvh.h: Bvh4Node); or nullptr
     const float4* tris;    // 3 float4 per triangle in LEAF order: v0|prim id, e1|flags(bit0 emitter), e2|0
     const float4* tris_id; // same triangles in PRIMITIVE-ID order (brute-force parity path), mesh triangles only
     // throughput instantiation only: 4 float4 per triangle = plane-equation form (N|d, n1|d1, n2|d2, id|flags|0|0), see

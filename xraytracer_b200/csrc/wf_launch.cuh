@@ -71,37 +71,49 @@ inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam,
     if (count) k_primary<true><<<g1, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
     else k_primary<false><<<g0, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
 }
+// k_trace instantiation for (closest / any hit, counters, two- / four-child tree)
+template <bool ANY>
+inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
+                        float4* anyOut, int thr, int spv, int leafThr)
+{
+    static thread_local int g[4] = {0, 0, 0, 0};
+    if (!g[0]) {
+        g[0] = gridFor((const void*)k_trace<ANY, false, false>); g[1] = gridFor((const void*)k_trace<ANY, true, false>);
+        g[2] = gridFor((const void*)k_trace<ANY, false, true>); g[3] = gridFor((const void*)k_trace<ANY, true, true>);
+    }
+    const bool wide = sc.nodes4 != nullptr;
+    if (wide) {
+        if (count) k_trace<ANY, true, true><<<g[3], kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, anyOut, thr, spv, leafThr);
+        else k_trace<ANY, false, true><<<g[2], kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, anyOut, thr, spv, leafThr);
+    }
+    else {
+        if (count) k_trace<ANY, true, false><<<g[1], kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, anyOut, thr, spv, leafThr);
+        else k_trace<ANY, false, false><<<g[0], kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, anyOut, thr, spv, leafThr);
+    }
+}
 inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
                          int thr, int spv, int leafThr)
 {
-    static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
-    if (!g0) {
-        g0 = gridFor((const void*)k_trace<false, false>); g1 = gridFor((const void*)k_trace<false, true>);
-        h0 = gridFor((const void*)k_extend_simple<false>); h1 = gridFor((const void*)k_extend_simple<true>);
-    }
+    static thread_local int h0 = 0, h1 = 0;
+    if (!h0) { h0 = gridFor((const void*)k_extend_simple<false>); h1 = gridFor((const void*)k_extend_simple<true>); }
     if (thr <= 0) { // shallow BVH: simple run-to-completion kernel
         if (count) k_extend_simple<true><<<h1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
         else k_extend_simple<false><<<h0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
         return;
     }
-    if (count) k_trace<false, true><<<g1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv, leafThr);
-    else k_trace<false, false><<<g0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, nullptr, thr, spv, leafThr);
+    launchTrace<false>(st, sc, q, src, bounce, brute, count, stats, nullptr, thr, spv, leafThr);
 }
 inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, int brute, bool count, unsigned long long* stats,
                           int thr, int spv, int leafThr)
 {
-    static thread_local int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
-    if (!g0) {
-        g0 = gridFor((const void*)k_trace<true, false>); g1 = gridFor((const void*)k_trace<true, true>);
-        h0 = gridFor((const void*)k_connect_simple<false>); h1 = gridFor((const void*)k_connect_simple<true>);
-    }
+    static thread_local int h0 = 0, h1 = 0;
+    if (!h0) { h0 = gridFor((const void*)k_connect_simple<false>); h1 = gridFor((const void*)k_connect_simple<true>); }
     if (thr <= 0) {
         if (count) k_connect_simple<true><<<h1, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
         else k_connect_simple<false><<<h0, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
         return;
     }
-    if (count) k_trace<true, true><<<g1, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv, leafThr);
-    else k_trace<true, false><<<g0, kBlock, 0, st>>>(sc, q, 0, bounce, brute, stats, nullptr, thr, spv, leafThr);
+    launchTrace<true>(st, sc, q, 0, bounce, brute, count, stats, nullptr, thr, spv, leafThr);
 }
 inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce)
 {
@@ -156,6 +168,6 @@ inline void launchTraceRays(cudaStream_t st, const DScene& sc, const DQueues& q,
 {
     const int grid = int(std::min<long long>((n + kBlock - 1) / kBlock, 148 * 16));
     k_pack_rays<<<grid > 0 ? grid : 1, kBlock, 0, st>>>(q, org, dir, tmax, uint32_t(n), anyhit ? 1 : 0);
-    if (anyhit) k_trace<true, false><<<gridFor((const void*)k_trace<true, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, out, 16, 1, 8);
-    else k_trace<false, false><<<gridFor((const void*)k_trace<false, false>), kBlock, 0, st>>>(sc, q, 0, 0, brute, stats, nullptr, 16, 1, 8);
+    if (anyhit) launchTrace<true>(st, sc, q, 0, 0, brute, false, stats, out, 16, 1, 8);
+    else launchTrace<false>(st, sc, q, 0, 0, brute, false, stats, nullptr, 16, 1, 8);
 }

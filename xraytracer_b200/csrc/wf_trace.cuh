@@ -146,6 +146,51 @@ __device__ __forceinline__ void nodeStep(const DScene& sc, RayState& r, int* sst
     if (h0 | h1) r.node = nearE;
     else r.node = stackPop(sstack, lstack, r.sp);
 }
+// Four-child node step (Bvh4Node): four slab tests — two children per packed fp32x2 instruction —, the hit children sorted by
+// entry distance with a 5-comparator network, the nearest becomes the current node, the others are pushed farthest first.
+__device__ __forceinline__ float2 f2lo(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 f2hi(const float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ void cmpSwap(float& ka, int& ea, float& kb, int& eb)
+{
+    const bool sw = kb < ka;
+    const float k0 = fminf(ka, kb), k1 = fmaxf(ka, kb);
+    const int e0 = sw ? eb : ea, e1 = sw ? ea : eb;
+    ka = k0; kb = k1; ea = e0; eb = e1;
+}
+template <bool COUNT>
+__device__ __forceinline__ void nodeStep4(const DScene& sc, RayState& r, int* sstack, int* lstack, TraceCounters& tc)
+{
+    const float4* __restrict__ nd = sc.nodes4 + 8 * size_t(r.node);
+    const float4 lx = __ldg(nd), ly = __ldg(nd + 1), lz = __ldg(nd + 2), hx = __ldg(nd + 3), hy = __ldg(nd + 4), hz = __ldg(nd + 5);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(nd + 6)), cn = __ldg(reinterpret_cast<const int4*>(nd + 7));
+    if (COUNT) tc.nodes++;
+    const float2 ix = make_float2(r.idir.x, r.idir.x), iy = make_float2(r.idir.y, r.idir.y), iz = make_float2(r.idir.z, r.idir.z);
+    const float2 ox = make_float2(-r.ood.x, -r.ood.x), oy = make_float2(-r.ood.y, -r.ood.y), oz = make_float2(-r.ood.z, -r.ood.z);
+    // children (0,1) in the low halves, (2,3) in the high halves
+    const float2 ax0 = __ffma2_rn(f2lo(lx), ix, ox), ax1 = __ffma2_rn(f2lo(hx), ix, ox), bx0 = __ffma2_rn(f2hi(lx), ix, ox), bx1 = __ffma2_rn(f2hi(hx), ix, ox);
+    const float2 ay0 = __ffma2_rn(f2lo(ly), iy, oy), ay1 = __ffma2_rn(f2lo(hy), iy, oy), by0 = __ffma2_rn(f2hi(ly), iy, oy), by1 = __ffma2_rn(f2hi(hy), iy, oy);
+    const float2 az0 = __ffma2_rn(f2lo(lz), iz, oz), az1 = __ffma2_rn(f2lo(hz), iz, oz), bz0 = __ffma2_rn(f2hi(lz), iz, oz), bz1 = __ffma2_rn(f2hi(hz), iz, oz);
+    auto nearFar = [&](float x0, float x1, float y0, float y1, float z0, float z1, float& tn) -> bool {
+        tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+        const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), r.h.t));
+        return tn <= tf;
+    };
+    float k0, k1, k2, k3;
+    const bool h0 = nearFar(ax0.x, ax1.x, ay0.x, ay1.x, az0.x, az1.x, k0) & (cn.x >= 0);
+    const bool h1 = nearFar(ax0.y, ax1.y, ay0.y, ay1.y, az0.y, az1.y, k1) & (cn.y >= 0);
+    const bool h2 = nearFar(bx0.x, bx1.x, by0.x, by1.x, bz0.x, bz1.x, k2) & (cn.z >= 0);
+    const bool h3 = nearFar(bx0.y, bx1.y, by0.y, by1.y, bz0.y, bz1.y, k3) & (cn.w >= 0);
+    int e0 = cn.x > 0 ? ~((ch.x << 2) | (cn.x - 1)) : ch.x, e1 = cn.y > 0 ? ~((ch.y << 2) | (cn.y - 1)) : ch.y;
+    int e2 = cn.z > 0 ? ~((ch.z << 2) | (cn.z - 1)) : ch.z, e3 = cn.w > 0 ? ~((ch.w << 2) | (cn.w - 1)) : ch.w;
+    k0 = h0 ? k0 : FLT_MAX; k1 = h1 ? k1 : FLT_MAX; k2 = h2 ? k2 : FLT_MAX; k3 = h3 ? k3 : FLT_MAX;
+    const int nHit = int(h0) + int(h1) + int(h2) + int(h3);
+    cmpSwap(k0, e0, k1, e1); cmpSwap(k2, e2, k3, e3); cmpSwap(k0, e0, k2, e2); cmpSwap(k1, e1, k3, e3); cmpSwap(k1, e1, k2, e2);
+    if (nHit > 3) stackPush(sstack, lstack, r.sp, e3);
+    if (nHit > 2) stackPush(sstack, lstack, r.sp, e2);
+    if (nHit > 1) stackPush(sstack, lstack, r.sp, e1);
+    if (nHit > 0) r.node = e0;
+    else r.node = stackPop(sstack, lstack, r.sp);
+}
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool leafTest(const DScene& sc, RayState& r, int leafCode, TraceCounters& tc)
 {
@@ -160,7 +205,7 @@ __device__ __forceinline__ bool leafTest(const DScene& sc, RayState& r, int leaf
 }
 
 // anyOut != nullptr (parity hook): write the occlusion flag instead of adding the contribution.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(kBlock) k_trace(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats, float4* anyOut,
                                                   int refillThreshold, int stepsPerVote, int leafThreshold)
 {
@@ -236,7 +281,10 @@ __global__ void __launch_bounds__(kBlock) k_trace(DScene sc, DQueues q, int src,
         uint32_t busy;
         do {
             for (int sv = 0; sv < stepsPerVote; ++sv) {
-                if (active && atInner(r)) nodeStep<COUNT>(sc, r, sstack, lstack, tc);
+                if (active && atInner(r)) {
+                    if (WIDE) nodeStep4<COUNT>(sc, r, sstack, lstack, tc); // deep trees carry a four-child form of the tree (api.cu)
+                    else nodeStep<COUNT>(sc, r, sstack, lstack, tc);
+                }
                 const bool atLeaf = active && r.node < 0;
                 const uint32_t leafMask = __ballot_sync(0xffffffffu, atLeaf);
                 const uint32_t advancing = __ballot_sync(0xffffffffu, active && atInner(r));

@@ -206,7 +206,7 @@ __device__ __forceinline__ bool leafTest(const DScene& sc, RayState& r, int leaf
 
 // anyOut != nullptr (parity hook): write the occlusion flag instead of adding the contribution.
 template <bool ANY, bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(kBlock) k_trace(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats, float4* anyOut,
+__global__ void __launch_bounds__(kBlock, 8) k_trace(DScene sc, DQueues q, int src, int bounce, int brute, unsigned long long* stats, float4* anyOut,
                                                   int refillThreshold, int stepsPerVote, int leafThreshold)
 {
     __shared__ int s_stack[kStackSmem * kBlock];

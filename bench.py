@@ -425,7 +425,7 @@ def main():
             "config": {"workload": args.workload + ": " + wl["desc"], "spp_per_gpu": my_spp, "integrator": wl["integrator"],
                        "max_depth": wl["max_depth"], "rng": "Philox4x32-7 counter RNG keyed (seed,pixel)/(sample,block)",
                        "parallelism": f"spp split over {world} GPU(s), scene replicated, one NCCL reduce(sum) of the {W}x{H}x3 fp32 buffer",
-                       "l2_policy": "per-step working set (ray/hit/shadow queues of 8.3M paths, ~1.5 GB) exceeds the 126 MB L2; no flush needed",
+                       "l2_policy": "per-wave working set (ray + hit queues and the per-path radiance of 8.3M paths, 0.5-1.5 GB) exceeds the 126 MB L2; no flush needed",
                        "triangles": info["n_triangles"], "bvh_nodes": info["n_bvh_nodes"]},
             "mrays_per_s": rays / (ms * 1e-3) / 1e6, "rays_per_sample": rays / samples,
             "gpu_launches": int(agg_all[2]),

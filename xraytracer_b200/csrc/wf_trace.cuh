@@ -447,6 +447,26 @@ __device__ __forceinline__ uint32_t blockAppend(uint32_t* counter, bool want, ui
     __syncthreads(); // scratch may be reused by the next call
     return slot;
 }
+// Two candidates per thread, one atomic and one barrier round per CTA: slots of a warp are laid out as [its A entries][its B entries].
+template <int NWARPS>
+__device__ __forceinline__ void blockAppend2(uint32_t* counter, bool wantA, bool wantB, uint32_t* scratch, uint32_t& slotA, uint32_t& slotB)
+{
+    const uint32_t ma = __ballot_sync(0xffffffffu, wantA), mb = __ballot_sync(0xffffffffu, wantB);
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    if (lane == 0) scratch[warp] = __popc(ma) + __popc(mb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) { const uint32_t c = scratch[w]; scratch[w] = total; total += c; }
+        scratch[NWARPS] = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    const uint32_t base = scratch[NWARPS] + scratch[warp], below = (1u << lane) - 1u;
+    slotA = base + __popc(ma & below);
+    slotB = base + __popc(ma) + __popc(mb & below);
+    __syncthreads(); // scratch may be reused by the next call
+}
 // ---------------------------------------------------------------------------------------------------------
 // primary: ray generation (renderer.cpp:42-52, camera.h:49-60) FUSED with the bounce-0 closest hit. Primary rays are
 // coherent and most of them miss in the benchmark views (59 % Cornell, 86 % volume), so instead of writing 8.3 M rays,
@@ -463,27 +483,14 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     const uint32_t n = w.nPaths;
     TraceCounters tc;
     uint32_t nHits = 0;
-    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
-        const uint32_t pid = tile * kBlock + threadIdx.x;
+    // one path: ray generation, scissor, closest hit; misses are resolved here
+    auto path = [&](uint32_t pid, V3& d, Hit& h, uint32_t& ctr) -> bool {
+        if (pid >= n) return false;
+        const uint32_t pix = pid % w.nPixels;
+        const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+        const bool inView = int(j) >= w.sx0 && int(j) < w.sx1 && int(i) >= w.sy0 && int(i) < w.sy1;
         bool hit = false;
-        V3 o = mk(0.f), d = mk(0.f);
-        Hit h{FLT_MAX, 0.f, 0.f, -1};
-        uint32_t ctr = 0;
-        bool inView = false;
-        uint32_t pi = 0, pj = 0;
-        if (pid < n) {
-            const uint32_t pix = pid % w.nPixels;
-            pi = pix / uint32_t(w.width); pj = pix % uint32_t(w.width);
-            inView = int(pj) >= w.sx0 && int(pj) < w.sx1 && int(pi) >= w.sy0 && int(pi) < w.sy1;
-            if (!inView) { // the pixel cannot see the scene's bounding box: every sample is a miss, no ray needed
-                V3 c = mk(0.f);
-                if (missMode == 1) c = mk(float(0.18));
-                else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
-                q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
-            }
-        }
-        if (inView) {
-            const uint32_t i = pi, j = pj;
+        if (inView) { // (outside: the pixel cannot see the scene's bounding box, every sample is a miss, no ray needed)
             Rng rng;
             rng.open(w, pid, 0);
             const float r0 = rng.next();
@@ -491,24 +498,39 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
             ctr = rng.close();
             const float u = (float(j) + r0) / float(uint32_t(w.width));
             const float v = (float(i) + r1) / float(uint32_t(w.height));
+            V3 o;
             cameraRay(cam, u, v, o, d);
             closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
             hit = h.prim >= 0;
-            V3 c = mk(0.f);
-            if (!hit) {
-                if (missMode == 1) c = mk(float(0.18));
-                else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
-            }
-            q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
         }
-        const uint32_t slot = blockAppend<kBlock / 32>(q.ctrl + kCtrlRays, hit, s_scratch);
-        nHits += hit ? 1u : 0u;
-        if (hit) {
-            q.q0[0][slot] = make_float4(o.x, o.y, o.z, 1.0f);
-            q.q1[0][slot] = make_float4(d.x, d.y, d.z, 1.0f);
-            q.q2[0][slot] = make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr)));
-            q.hits[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+        V3 c = mk(0.f);
+        if (!hit) {
+            if (missMode == 1) c = mk(float(0.18));
+            else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
         }
+        q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        return hit;
+    };
+    const V3 org = mk(cam.c2w[12], cam.c2w[13], cam.c2w[14]); // every primary ray starts at the camera position (camera.h:57)
+    auto emit = [&](uint32_t slot, uint32_t pid, V3 d, const Hit& h, uint32_t ctr) {
+        q.q0[0][slot] = make_float4(org.x, org.y, org.z, 1.0f);
+        q.q1[0][slot] = make_float4(d.x, d.y, d.z, 1.0f);
+        q.q2[0][slot] = make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr)));
+        q.hits[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+    };
+    // two tiles of 128 paths per round: half the barriers and atomics of the queue append per path
+    for (uint32_t tile = 2 * blockIdx.x; uint64_t(tile) * kBlock < n; tile += 2 * gridDim.x) {
+        const uint32_t pidA = tile * kBlock + threadIdx.x, pidB = pidA + kBlock;
+        V3 dA = mk(0.f), dB = mk(0.f);
+        Hit hA{FLT_MAX, 0.f, 0.f, -1}, hB{FLT_MAX, 0.f, 0.f, -1};
+        uint32_t cA = 0, cB = 0;
+        const bool hitA = path(pidA, dA, hA, cA);
+        const bool hitB = path(pidB, dB, hB, cB);
+        uint32_t slotA, slotB;
+        blockAppend2<kBlock / 32>(q.ctrl + kCtrlRays, hitA, hitB, s_scratch, slotA, slotB);
+        nHits += (hitA ? 1u : 0u) + (hitB ? 1u : 0u);
+        if (hitA) emit(slotA, pidA, dA, hA, cA);
+        if (hitB) emit(slotB, pidB, dB, hB, cB);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
     statAdd(stats, kStatPrimaryHits, nHits);

@@ -80,3 +80,58 @@ def test_random_small_scene_fused_vs_three_kernel_and_oracle(seed, monkeypatch):
         assert abs(float(f.mean()) - float(u.mean())) <= 1e-3 * float(u.mean()) + 1e-6, (seed, integ)
         differing = np.abs(f - u).max(axis=-1) > 1e-3 * (1.0 + np.abs(u).max(axis=-1))
         assert differing.mean() < 0.01, (seed, integ)
+
+
+def _grid_scene(n_quads, n_lights=1):
+    """n_quads floor tiles (2 triangles each) under `n_lights` small quad lights."""
+    s = scenes.HostScene()
+    side = int(np.ceil(np.sqrt(n_quads)))
+    tris = []
+    for k in range(n_quads):
+        x, z = (k % side) * 10.0, (k // side) * 10.0
+        tris += _quad((x, 0.0, z), (0, 0, 9.5), (9.5, 0, 0))
+    s.add_mesh("floor", np.array(tris), (0.7, 0.7, 0.7))
+    s.add_mesh("wall", np.array(_quad((0, 0, side * 10.0), (side * 10.0, 0, 0), (0, 40, 0))), (0.8, 0.3, 0.3))
+    for k in range(n_lights):
+        x = 5.0 + 7.0 * k
+        s.add_quad_light(f"QuadLight{k}", (x + 4.0, 30.0, 5.0), (x + 4.0, 30.0, 9.0), (x, 30.0, 5.0), (50.0, 50.0, 50.0))   # faces down
+    half = side * 5.0
+    cam = scenes.make_camera(128, 96, [-1, 0, 0, 0, 0, 0.8, 0.6, 0, 0, 0.6, -0.8, 0, half, 60.0, -40.0, 1], 60.0)   # looks forward and down
+    return s, cam
+
+
+@pytest.mark.parametrize("n_quads,n_lights", [(30, 1), (31, 1), (32, 1), (12, 9), (12, 2)])
+def test_pipeline_selection_boundaries(n_quads, n_lights):
+    """Scenes just below / above the limits that select the fused small-scene kernel (64 triangles, 8 lights): whichever pipeline
+    runs, the exact instantiation reproduces the oracle and the throughput one converges to the same mean."""
+    require_gpu()
+    host, cam = _grid_scene(n_quads, n_lights)
+    desc = host.flatten()
+    gpu, orc = api.GpuScene(desc, 0), api.OracleScene(desc)
+    W, H = 128, 96
+    assert np.array_equal(gpu.trace_primary(cam, W, H, 1), orc.trace_primary(cam, W, H, 1))
+    a, sa = gpu.render(cam, W, H, 2, capi.INT_GI, 3, flags=capi.FLAG_EXACT)
+    b, _, sb = orc.render(cam, W, H, 2, capi.INT_GI, 3)
+    assert sa["closest_rays"] == sb["closest_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
+    assert np.abs(a - b).max() <= 2e-5 * max(1.0, float(np.abs(b).max()))
+    f, sf = gpu.render(cam, W, H, 256, capi.INT_GI, 3, seed=3)
+    r, _, _ = orc.render(cam, W, H, 64, capi.INT_GI, 3)
+    assert float(r.mean()) > 1e-3 and abs(float(f.mean()) - float(r.mean())) < 0.03 * float(r.mean())
+    fused = sf["bounce_launches"] > 0
+    assert fused == (gpu.info()["n_triangles"] <= 64 and n_lights <= 8)
+
+
+def test_degenerate_views():
+    """1x1 image, a camera that looks away from the scene (every pixel outside the scissor), one sample per wave."""
+    require_gpu()
+    host = scenes.cornell_box("quad")
+    gpu = api.GpuScene(host.flatten(), 0)
+    img, st = gpu.render(scenes.make_camera(1, 1), 1, 1, 8, capi.INT_GI, 3, seed=1)
+    assert img.shape == (1, 1, 3) and np.isfinite(img).all() and st["samples"] == 8
+    away = scenes.make_camera(64, 48, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 278.0, 274.4, -750.0, 1], 60.0)   # looks down -z: away from the box
+    for integ, colour in ((capi.INT_GI, 0.0), (capi.INT_DIRECT, 0.18)):
+        img, st = gpu.render(away, 64, 48, 4, integ, 3, seed=1)
+        assert np.allclose(img, colour) and st["primary_hits"] == 0
+    a, _ = gpu.render(scenes.make_camera(96, 54), 96, 54, 6, capi.INT_GI, 3, seed=5, samples_per_wave=1)
+    b, _ = gpu.render(scenes.make_camera(96, 54), 96, 54, 6, capi.INT_GI, 3, seed=5, samples_per_wave=4)
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)

@@ -11,6 +11,10 @@
  *                                                               camera.h:49-60, scene.cpp:190-200
  *   xrtg_trace_rays       <- Scene::intersect / Scene::occluded  scene.cpp:190-211
  *   xrtg_image_to_u8      <- Image::gammaCorrection + writePPM / writeMat quantisation   image.h:80-136
+ *   xrtg_scene_create_multi, xrtg_reduce_finalize, xrtg_partial_buffer, xrtg_ipc_*
+ *                         <- the "one renderer, every core" role of ParallelRenderer::render (renderer.cpp:83-99) scaled to
+ *                            several GPUs: samples split across devices, `image /= n_samples` (renderer.cpp:98) fused into the
+ *                            peer-memory reduction of the per-device sums
  *
  * Conventions
  *   - every function returns 0 on success or a negative xrtg_status; xrtg_last_error() returns a
@@ -38,7 +42,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
 #endif
 
-#define XRTG_ABI_VERSION 1
+#define XRTG_ABI_VERSION 2
 
 typedef enum xrtg_status {
     XRTG_OK = 0,
@@ -192,7 +196,17 @@ enum {
     XRTG_FLAG_SUM_ONLY = 1u << 3,
     /* Bracket every kernel launch with CUDA events and report per-stage device time in xrtg_stats
      * (extend_ms / shade_ms / connect_ms / other_ms). Cheap: no extra work inside the kernels. */
-    XRTG_FLAG_STAGE_TIMES = 1u << 4
+    XRTG_FLAG_STAGE_TIMES = 1u << 4,
+    /* Parity hooks only (xrtg_trace_primary / xrtg_trace_rays): trace with the THROUGHPUT instantiation through the very entry
+     * points xrtg_render uses for this scene — k_primary incl. its screen-space scissor, the shared-memory small-scene tracer of
+     * k_bounce_small (plane-paired records, hull-pruned occluders), the simple kernels on mid-size scenes, k_trace on the wide
+     * BVH with plane-equation triangle records on deep ones — instead of the exact (no-FMA, Moeller-Trumbore) instantiation.
+     * t/u/v then differ from the reference in the last bits; primitive ids and occlusion flags must not (tests/test_gpu_fast_hooks.py). */
+    XRTG_FLAG_FAST_HOOK = 1u << 5,
+    /* xrtg_trace_rays(any_hit = 1) with XRTG_FLAG_FAST_HOOK: out_hits[i].prim holds, ON ENTRY, the id of the primitive the shadow
+     * ray starts on (-1 = unknown) — what the renderer knows when it traces an NEE ray and uses to pick the occluder section
+     * of a small scene (hull pruning, small_scene.h). */
+    XRTG_FLAG_HOOK_SRC_PRIM = 1u << 6
 };
 
 typedef struct xrtg_render_params {
@@ -228,6 +242,12 @@ typedef struct xrtg_stats {
     uint64_t primary_hits;   /* primary rays that hit something = entries of the compact bounce-0 queue */
     uint64_t bounce_entries; /* queue entries consumed by the fused per-bounce kernel of small scenes (0 = three-kernel pipeline) */
     uint64_t bounce_launches;/* launches of that kernel (counted in shade_launches as well) */
+    uint64_t rays_traced;    /* rays the kernels actually traced: closest_rays + shadow_rays minus the primary samples the
+                                screen-space scissor resolved without a ray (they still count as reference-equivalent rays) */
+    uint64_t truncated_paths;/* volume paths cut by the iteration bound 4*max_depth+8 (capped at 4096) on medium crossings without a
+                                scattering event; the reference's loop (integrator.h:418) is unbounded. 0 on every shipped scene */
+    float reduce_ms;         /* multi-GPU scenes: the fused peer-memory reduce + finalize (CUDA events on device 0)            */
+    int32_t n_devices;       /* devices that took part in the render                                                           */
 } xrtg_stats;
 
 /* Closest-hit record of the parity hooks. prim = global primitive id (-1 = miss). */
@@ -248,7 +268,31 @@ typedef struct xrtg_scene_info {
     int32_t bvh_builder;   /* 0 = host binned SAH, 1 = GPU linear BVH                                    */
     int32_t small_records_all, small_records_occ; /* plane-paired triangle records (80 B each) of a small scene's closest-hit /
                                                      occluder sections; 0 = no block (per-triangle lists or BVH only)  */
+    int32_t small_flagged;  /* small scenes: primitives whose shadow rays can start behind a hull-pruned plane (they test the
+                               unpruned occluder section)                                                               */
+    int32_t n_wide_nodes;   /* deep scenes: nodes of the wide (4- or 8-child) tree the traversal kernel walks          */
+    int32_t wide_arity;     /* 0 = none, 4 or 8                                                                         */
+    int32_t n_devices;      /* devices holding a replica of the scene                                                    */
 } xrtg_scene_info;
+
+/* Development / test switches of the pipeline selection; -1 (or any negative value) = the measured default. None of them
+ * changes WHAT is computed, only which kernels compute it — the tests flip them to compare one pipeline against another.
+ * The render path reads no environment variable; XRT_TUNING="key=value,..." (keys = the field names) is parsed once, at scene
+ * creation. */
+typedef struct xrtg_tuning {
+    int32_t fused_bounce;    /* small scenes: one k_bounce_small per bounce (1) or shade -> connect -> extend (0)              */
+    int32_t volume_paths;    /* shallow BVHs: k_volume_paths (1) or the wavefront iterations (0)                              */
+    int32_t scissor;         /* primary-ray screen-space scissor                                                              */
+    int32_t brute_secondary, brute_shadow; /* small scenes: shared-memory triangle loops instead of the BVH walk              */
+    int32_t thr_ext0, thr_ext, thr_con;    /* k_trace refill thresholds (0 = the simple run-to-completion kernels)            */
+    int32_t steps_per_vote, leaf_threshold;
+    int32_t thr_vol, spv_vol;              /* k_volume_paths lockstep-walk threshold / steps per vote                         */
+    int32_t wide_bvh;        /* deep scenes: 8 = eight-child quantised nodes, 4 = four-child nodes, 2 = two-child nodes       */
+    int32_t max_leaf;        /* creation time only (XRT_TUNING): triangles per leaf of the host SAH builder, 1..4             */
+    int32_t workspace_mb;    /* byte budget of the per-wave queues (default 6144); small values force pixel-tiled waves       */
+    int32_t stage_dump;      /* print every stage's CUDA-event time to stderr (with XRTG_FLAG_STAGE_TIMES)                    */
+    int32_t reserved[4];
+} xrtg_tuning;
 
 int xrtg_abi_version(void);
 int xrtg_device_count(void);
@@ -265,6 +309,32 @@ enum {
 };
 /* xrtg_scene_create with build flags. */
 int xrtg_scene_create2(const xrtg_scene_desc* desc, int device, uint32_t build_flags, xrtg_scene** out);
+/* Multi-GPU scene: the SAME host-side ingest and BVH build, then one replica of the scene arrays per device (devices[0..ngpus),
+ * NULL = 0..ngpus-1). xrtg_render / xrtg_render_device on such a handle split the samples of the call across the devices
+ * (device g renders sample indices [g*spp/G, (g+1)*spp/G) of every pixel; the counter RNG is keyed by sample index, so the
+ * union is the 1-GPU sample set), one host thread and one stream per device, and finish with ONE fused kernel per device that
+ * pulls its slice of every device's per-pixel SUM over NVLink peer memory, adds them in device order, applies the
+ * reference's `image /= n_samples` (renderer.cpp:98) and stores the slice into device 0's image — reduce and finalize in
+ * one pass, no NCCL, no Python. Single process; XRTG_FLAG_EXACT renders are not split (one mt19937 stream per pixel). */
+int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* devices, uint32_t build_flags, xrtg_scene** out);
+/* Number of devices behind a handle (1 for xrtg_scene_create). */
+int xrtg_scene_device_count(const xrtg_scene* scene);
+int xrtg_scene_set_tuning(xrtg_scene* scene, const xrtg_tuning* tuning);
+
+/* ---- one process per GPU (torchrun / MPI style deployments): the same fused reduce + finalize over CUDA IPC ------------- */
+/* The scene's exportable per-pixel SUM buffer (width*height*3 floats, plain cudaMalloc on the scene's device). */
+int xrtg_partial_buffer(xrtg_scene* scene, int width, int height, float** device_ptr);
+#define XRTG_IPC_HANDLE_BYTES 64
+int xrtg_ipc_export(const void* device_ptr, unsigned char handle[XRTG_IPC_HANDLE_BYTES]);
+/* Maps a buffer exported by another process on another (peer-accessible) device into this process. */
+int xrtg_ipc_open(xrtg_scene* scene, const unsigned char handle[XRTG_IPC_HANDLE_BYTES], void** device_ptr);
+int xrtg_ipc_close(xrtg_scene* scene, void* device_ptr);
+/* out[i] = (parts[0][i] + parts[1][i] + ... in this order) / divisor for i in [first, first + count); divisor <= 0 leaves
+ * the sum. `parts` and `out` may be local, peer-device or IPC-mapped pointers; asynchronous on `cuda_stream`. Every rank
+ * calls it on its own slice; the caller orders it after the renders of all ranks (a stream-ordered barrier). */
+int xrtg_reduce_finalize(xrtg_scene* scene, const float* const* parts, int nparts, float* out, size_t first, size_t count,
+                         float divisor, void* cuda_stream);
+
 /* Re-copies the already-built scene arrays host(pinned)->device (the e2e H2D leg). */
 int xrtg_scene_upload(xrtg_scene* scene);
 int xrtg_scene_get_info(const xrtg_scene* scene, xrtg_scene_info* out);
@@ -311,6 +381,11 @@ int xrtg_small_scene_selftest(const float* tris9, const int* emitter_flags, int 
  * clamp(uint32(255*x), 0, 255), written RGB (PPM order, bgr = 0) or BGR (cv::Mat order, bgr = 1). rgb_host = W*H*3 floats,
  * out_host = W*H*3 bytes (both host pointers). */
 int xrtg_image_to_u8(int device, const float* rgb_host, int width, int height, float gamma, int bgr, uint8_t* out_host);
+/* xrtg_render followed by that image post WITHOUT the float image leaving HBM: render, `image /= n_samples`, gammaCorrection
+ * and the 8-bit quantisation run on the device and only width*height*3 BYTES are copied to the host (what the reference's
+ * example mains do after render(): image.gammaCorrection(1.2f); image.writePPM(...), cornellbox.cpp:65-75). */
+int xrtg_render_u8(xrtg_scene* scene, const xrtg_camera* cam, const xrtg_render_params* p, float gamma, int bgr, uint8_t* out_host,
+                   xrtg_stats* stats);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

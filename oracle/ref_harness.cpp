@@ -2,6 +2,9 @@
 // /root/reference/Src (see oracle/Makefile). TEST INFRASTRUCTURE ONLY: nothing under oracle/ is linked,
 // imported or executed by the product path (libxrtgpu.so / libxrthost.so); only tests/, smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load the resulting oracle/_ref/libxrtref.so.
+// Built twice (oracle/Makefile): libxrtref.so = the CPU checker, no dependency on any product library (it only reads the
+// POD definitions of xrtgpu.h); libxrtrefgpu.so = the same plus RefGpuRenderer (-DXRT_REF_WITH_GPU), linked against
+// libxrtgpu.so, loaded by the drop-in test alone.
 //
 // What it adds on top of the reference (all additive, no reference source is copied):
 //   * a reference `Scene` built from the same flattened xrtg_scene_desc the GPU consumes;
@@ -172,6 +175,8 @@ struct xrtref_scene {
 };
 
 
+#ifdef XRT_REF_WITH_GPU // only libxrtrefgpu.so (tests/test_gpu_dropin_reference.py) carries the GPU binding and links libxrtgpu.so;
+                        // libxrtref.so — the CPU checker and the bench's reference arm — contains no reference to the product
 // ---------------------------------------------------------------------------------------------------------------------
 // RefGpuRenderer — the binding of INTEGRATION.md, compiled against the reference's OWN headers: a third sibling of
 // NormalRenderer / ParallelRenderer (renderer.h:22-47) that flattens a reference `Scene` and renders it through the C ABI
@@ -345,6 +350,8 @@ private:
 };
 
 } // namespace
+
+#endif // XRT_REF_WITH_GPU
 
 static std::unique_ptr<AreaLight> makeAreaLight(const xrtg_area_light& L)
 {
@@ -568,6 +575,7 @@ int xrtref_render(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_param
     return 0;
 }
 
+#ifdef XRT_REF_WITH_GPU
 // The same reference Scene / Camera / Integrator objects rendered through the GPU sibling renderer, called polymorphically
 // through the reference's `Renderer*` exactly as examples/cornellbox.cpp:61-63 would.
 int xrtref_render_gpu(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_params* p, float* rgb)
@@ -593,6 +601,8 @@ int xrtref_render_gpu(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_p
         }
     return 0;
 }
+
+#endif // XRT_REF_WITH_GPU
 
 // ParallelRenderer::render exactly as written (PSTL; serial on libstdc++ without TBB) — for the record.
 int xrtref_render_pstl(xrtref_scene* s, const xrtg_camera* c, const xrtg_render_params* p, float* rgb, double* seconds_out)

@@ -4,7 +4,7 @@ for wl in c3 c4; do
  for cfg in "0 0 0 1" "0 16 0 1" "1 16 16 4" "0 16 16 4" "16 16 16 4" "1 12 12 4" "1 20 20 4"; do
   set -- $cfg
   echo -n "$wl ext0=$1 ext=$2 con=$3 spv=$4 : "
-  XRT_THR_EXT0=$1 XRT_THR_EXT=$2 XRT_THR_CON=$3 XRT_SPV=$4 python scripts/profile_step.py $wl 8 | tail -1
+  XRT_TUNING="thr_ext0=$1,thr_ext=$2,thr_con=$3,steps_per_vote=$4" python scripts/profile_step.py $wl 8 | tail -1
  done
 done
 python scripts/profile_step.py c5 8 | tail -1

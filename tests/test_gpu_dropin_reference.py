@@ -9,7 +9,7 @@ from conftest import require_gpu
 from golden_cases import CASES, build_case
 from xraytracer_b200 import api, capi, scenes
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not capi.have_reference(), reason="oracle/_ref/libxrtref.so not built")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not capi.REF_GPU_LIB.exists(), reason="oracle/_ref/libxrtrefgpu.so not built")]
 
 
 def bits(a):
@@ -19,7 +19,7 @@ def bits(a):
 def test_gpu_renderer_beside_the_reference_cpu_renderer_on_one_reference_scene():
     require_gpu()
     host = scenes.cornell_box("quad")
-    ref = api.ReferenceScene(host.flatten())          # a reference Scene; from here on only reference objects are used
+    ref = api.ReferenceGpuScene(host.flatten())          # a reference Scene; from here on only reference objects are used
     W, H = 160, 120
     cam = scenes.make_camera(W, H)
     for integ, depth, exact_bits in ((capi.INT_NORMAL, 1, True), (capi.INT_DIRECT, 1, True), (capi.INT_GI, 3, False),
@@ -40,7 +40,7 @@ def test_gpu_renderer_on_reference_volume_scenes():
     for name in ("vpt_mis", "hetero"):
         case = CASES[name]
         host, cam = build_case(case)
-        ref = api.ReferenceScene(host.flatten())
+        ref = api.ReferenceGpuScene(host.flatten())
         for integ in (capi.INT_VOLUME, capi.INT_VOLUME_NEE):
             cpu, _, _ = ref.render(cam, case["w"], case["h"], 4, integ, 12)
             gpu = ref.render_gpu(cam, case["w"], case["h"], 4, integ, 12, flags=capi.FLAG_EXACT)

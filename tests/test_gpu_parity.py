@@ -174,16 +174,12 @@ def test_deep_bvh_render_uses_refill_kernel_and_matches_oracle():
         else:
             assert close_image(a, b) and rel_rmse(a, b) < 1e-4
     # and with refill forced on / off through the development overrides the image must not change
-    import os
     base, _ = gpu.render(cam, W, H, 4, capi.INT_GI, 3, seed=3)
-    for thr in ("0", "1", "8", "24"):
-        os.environ.update(XRT_THR_EXT0=thr, XRT_THR_EXT=thr, XRT_THR_CON=thr)
-        try:
-            alt, _ = gpu.render(cam, W, H, 4, capi.INT_GI, 3, seed=3)
-        finally:
-            for k in ("XRT_THR_EXT0", "XRT_THR_EXT", "XRT_THR_CON"):
-                os.environ.pop(k, None)
+    for thr in (0, 1, 8, 24):
+        gpu.set_tuning(thr_ext0=thr, thr_ext=thr, thr_con=thr)
+        alt, _ = gpu.render(cam, W, H, 4, capi.INT_GI, 3, seed=3)
         assert np.array_equal(bits(alt), bits(base)), thr
+    gpu.set_tuning()
 
 
 def test_coplanar_duplicates_and_axis_aligned_rays(gpu_cornell):
@@ -273,7 +269,7 @@ def test_volume_large_wave_with_mostly_missing_rays():
 
 
 @pytest.mark.parametrize("integ,exact", [(capi.INT_VOLUME, False), (capi.INT_VOLUME_NEE, False), (capi.INT_VOLUME, True), (capi.INT_VOLUME_NEE, True)])
-def test_volume_path_kernel_equals_wavefront_iterations(integ, exact, monkeypatch):
+def test_volume_path_kernel_equals_wavefront_iterations(integ, exact):
     """k_volume_paths runs each path to completion in one launch; the wavefront form does one iteration per launch. Same draws in
     the same order per path: identical tracking-step and ray counts, identical images."""
     require_gpu()
@@ -282,9 +278,9 @@ def test_volume_path_kernel_equals_wavefront_iterations(integ, exact, monkeypatc
     W, H, spp = 192, 108, 2 if exact else 8
     cam = scenes.make_camera(W, H)
     flags = capi.FLAG_EXACT if exact else 0
-    monkeypatch.setenv("XRT_VOLUME_PATHS", "1")
+    gpu.set_tuning(volume_paths=1)
     a, sa = gpu.render(cam, W, H, spp, integ, 8, seed=3, flags=flags)
-    monkeypatch.setenv("XRT_VOLUME_PATHS", "0")
+    gpu.set_tuning(volume_paths=0)
     b, sb = gpu.render(cam, W, H, spp, integ, 8, seed=3, flags=flags)
     assert sa["kernel_launches"] < sb["kernel_launches"]
     assert sa["tracking_steps"] == sb["tracking_steps"] and sa["closest_rays"] == sb["closest_rays"]
@@ -309,7 +305,7 @@ def test_fast_mode_is_deterministic_and_seed_dependent(gpu_cornell):
     ("quad", capi.INT_GI, 3, False), ("sphere", capi.INT_GI, 4, False), ("triangle", capi.INT_DIRECT, 1, False),
     ("quad", capi.INT_INDIRECT, 3, False), ("quad+sphere", capi.INT_GI, 3, False), ("quad", capi.INT_GI, 3, True),
     ("quad+sphere", capi.INT_GI, 2, True), ("quad", capi.INT_INDIRECT, 2, True)])
-def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, depth, exact, monkeypatch):
+def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, depth, exact):
     """k_bounce_small (shade + shadow rays + next closest hit + next RR in one kernel, plane-paired triangle records in the
     throughput build) draws the same numbers per path as shade -> connect -> extend, so with the same seed both pipelines
     render the same paths: ray counts agree and the images differ only where a hit point moved by an ulp across an edge."""
@@ -319,9 +315,9 @@ def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, de
     W, H, spp = 160, 90, 16 if not exact else 2
     cam = scenes.make_camera(W, H)
     flags = capi.FLAG_EXACT if exact else 0
-    monkeypatch.setenv("XRT_FUSED_BOUNCE", "1")
+    gpu.set_tuning(fused_bounce=1)
     a, sa = gpu.render(cam, W, H, spp, integ, depth, seed=11, flags=flags)
-    monkeypatch.setenv("XRT_FUSED_BOUNCE", "0")
+    gpu.set_tuning(fused_bounce=0)
     b, sb = gpu.render(cam, W, H, spp, integ, depth, seed=11, flags=flags)
     assert sa["kernel_launches"] < sb["kernel_launches"]
     if exact:   # same arithmetic, same order: identical counts, images equal to the last bits of the radiance sums
@@ -335,7 +331,7 @@ def test_fused_small_scene_kernel_matches_three_kernel_pipeline(light, integ, de
         assert differing.mean() < 0.01
 
 
-def test_primary_scissor_changes_nothing(monkeypatch):
+def test_primary_scissor_changes_nothing():
     """Pixels that cannot see the scene's bounding box are resolved without a ray (throughput instantiation). The counter RNG
     is keyed per path, so every other pixel draws the same numbers: images with and without the scissor are bit-identical,
     also for a camera inside the box (scissor = full image) and one that sees the box in a corner of the frame."""
@@ -348,17 +344,17 @@ def test_primary_scissor_changes_nothing(monkeypatch):
             scenes.make_camera(W, H, [-1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 1400.0, 900.0, -2000.0, 1], 50.0)]   # box off-centre
     for cam in cams:
         for integ, depth in ((capi.INT_GI, 3), (capi.INT_DIRECT, 1), (capi.INT_NORMAL, 1)):
-            monkeypatch.setenv("XRT_SCISSOR", "1")
+            gpu.set_tuning(scissor=1)
             a, sa = gpu.render(cam, W, H, 4, integ, depth, seed=9)
-            monkeypatch.setenv("XRT_SCISSOR", "0")
+            gpu.set_tuning(scissor=0)
             b, sb = gpu.render(cam, W, H, 4, integ, depth, seed=9)
             assert np.array_equal(bits(a), bits(b))
             assert sa["closest_rays"] == sb["closest_rays"] and sa["primary_hits"] == sb["primary_hits"]
     vol = scenes.volume_scene(n=16, light="quad")
     g2 = api.GpuScene(vol.flatten(), 0)
-    monkeypatch.setenv("XRT_SCISSOR", "1")
+    g2.set_tuning(scissor=1)
     a, sa = g2.render(cams[0], W, H, 4, capi.INT_VOLUME, 8, seed=9)
-    monkeypatch.setenv("XRT_SCISSOR", "0")
+    g2.set_tuning(scissor=0)
     b, sb = g2.render(cams[0], W, H, 4, capi.INT_VOLUME, 8, seed=9)
     assert np.array_equal(bits(a), bits(b)) and sa["tracking_steps"] == sb["tracking_steps"]
 

@@ -52,7 +52,7 @@ def random_scene(seed):
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
-def test_random_small_scene_fused_vs_three_kernel_and_oracle(seed, monkeypatch):
+def test_random_small_scene_fused_vs_three_kernel_and_oracle(seed):
     require_gpu()
     host, cam = random_scene(seed)
     desc = host.flatten()
@@ -70,11 +70,11 @@ def test_random_small_scene_fused_vs_three_kernel_and_oracle(seed, monkeypatch):
         assert sa["closest_rays"] == sb["closest_rays"] and sa["shadow_rays"] == sb["shadow_rays"], (seed, integ)
         assert np.abs(a - b).max() <= 2e-5 * max(1.0, float(np.abs(b).max())), (seed, integ)
         # throughput instantiation: plane-paired fused kernel against the three-kernel pipeline, same seed
-        monkeypatch.setenv("XRT_FUSED_BOUNCE", "1")
+        gpu.set_tuning(fused_bounce=1)
         f, sf = gpu.render(cam, W, H, 16, integ, depth, seed=seed)
-        monkeypatch.setenv("XRT_FUSED_BOUNCE", "0")
+        gpu.set_tuning(fused_bounce=0)
         u, su = gpu.render(cam, W, H, 16, integ, depth, seed=seed)
-        monkeypatch.delenv("XRT_FUSED_BOUNCE")
+        gpu.set_tuning()
         assert abs(sf["closest_rays"] - su["closest_rays"]) <= 2e-4 * su["closest_rays"] + 2, (seed, integ)
         assert abs(sf["shadow_rays"] - su["shadow_rays"]) <= 2e-4 * su["shadow_rays"] + 2, (seed, integ)
         assert abs(float(f.mean()) - float(u.mean())) <= 1e-3 * float(u.mean()) + 1e-6, (seed, integ)

@@ -37,14 +37,65 @@ def _rays(org, dir, tmax):
 class GpuScene:
     """Device scene (SAH BVH + flattened arrays resident in HBM) created through xrtg_scene_create."""
 
-    def __init__(self, desc, device: int = 0, build_flags: int = 0):
+    def __init__(self, desc, device: int = 0, build_flags: int = 0, devices=None):
+        """devices: None = one device (`device`); an int N = devices 0..N-1 behind ONE handle (xrtg_scene_create_multi);
+        a list = exactly those devices."""
         self.lib = capi.gpu()
         h = C.c_void_p()
-        rc = self.lib.xrtg_scene_create2(desc, device, build_flags, C.byref(h))
+        if devices is None:
+            rc = self.lib.xrtg_scene_create2(desc, device, build_flags, C.byref(h))
+        else:
+            ids = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+            arr = (C.c_int * len(ids))(*ids)
+            rc = self.lib.xrtg_scene_create_multi(desc, len(ids), arr, build_flags, C.byref(h))
+            device = ids[0]
         if rc != 0:
             raise RuntimeError(f"xrtg_scene_create failed ({rc}): {self.lib.xrtg_last_error().decode()}")
         self.h = h
         self.device = device
+
+    def set_tuning(self, **kw):
+        """Development / test switches of the pipeline selection (xrtg_tuning); omitted keys return to their defaults."""
+        t = capi.Tuning(**kw)
+        self._chk(self.lib.xrtg_scene_set_tuning(self.h, C.byref(t)), "xrtg_scene_set_tuning")
+
+    def device_count(self) -> int:
+        return self.lib.xrtg_scene_device_count(self.h)
+
+    def partial_buffer(self, width, height) -> int:
+        """Device pointer of the scene's exportable per-pixel SUM buffer (one process per GPU + CUDA IPC)."""
+        p = C.c_void_p()
+        self._chk(self.lib.xrtg_partial_buffer(self.h, width, height, C.byref(p)), "xrtg_partial_buffer")
+        return p.value
+
+    def ipc_export(self, device_ptr: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._chk(self.lib.xrtg_ipc_export(C.c_void_p(device_ptr), buf), "xrtg_ipc_export")
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._chk(self.lib.xrtg_ipc_open(self.h, buf, C.byref(p)), "xrtg_ipc_open")
+        return p.value
+
+    def ipc_close(self, device_ptr: int):
+        self._chk(self.lib.xrtg_ipc_close(self.h, C.c_void_p(device_ptr)), "xrtg_ipc_close")
+
+    def reduce_finalize(self, parts, out_ptr: int, first: int, count: int, divisor: float, stream: int = 0):
+        """out[i] = sum_k parts[k][i] / divisor over [first, first+count), asynchronously on `stream` (fused reduce + finalize;
+        parts / out may be peer-device or IPC-mapped pointers)."""
+        arr = (C.c_void_p * len(parts))(*[C.c_void_p(p) for p in parts])
+        self._chk(self.lib.xrtg_reduce_finalize(self.h, arr, len(parts), C.c_void_p(out_ptr), first, count, divisor, C.c_void_p(stream)),
+                  "xrtg_reduce_finalize")
+
+    def render_u8(self, cam, width, height, spp, integrator, max_depth=1, gamma=0.0, bgr=False, flags=0, seed=0):
+        """Render + `image /= spp` + gammaCorrection + 8-bit quantisation on the device; only the bytes come back."""
+        p = _params(width, height, spp, integrator, max_depth, flags, seed)
+        out = np.empty((height, width, 3), dtype=np.uint8)
+        st = capi.Stats()
+        self._chk(self.lib.xrtg_render_u8(self.h, C.byref(cam), C.byref(p), gamma, int(bgr), out.ctypes.data, C.byref(st)), "xrtg_render_u8")
+        return out, st.as_dict()
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -92,9 +143,13 @@ class GpuScene:
                   "xrtg_trace_primary")
         return hits.reshape(height, width, spp)
 
-    def trace_rays(self, org, dir, tmax=None, any_hit=False, flags=0):
+    def trace_rays(self, org, dir, tmax=None, any_hit=False, flags=0, src_prim=None):
+        """src_prim (any_hit with FLAG_FAST_HOOK): per ray, the primitive the shadow ray starts on (see XRTG_FLAG_HOOK_SRC_PRIM)."""
         org, dir, tmax = _rays(org, dir, tmax)
         hits = np.empty(len(org), dtype=HIT_DTYPE)
+        if src_prim is not None:
+            hits["prim"] = np.asarray(src_prim, dtype=np.int32)
+            flags |= capi.FLAG_HOOK_SRC_PRIM
         self._chk(self.lib.xrtg_trace_rays(self.h, len(org), org.ctypes.data, dir.ctypes.data,
                                             None if tmax is None else tmax.ctypes.data, int(any_hit), flags, hits.ctypes.data),
                   "xrtg_trace_rays")
@@ -207,6 +262,14 @@ class ReferenceScene(_CpuScene):
         buf = (C.c_int32 * 4096)()
         n = self.lib.xrtref_object_order(self.h, buf, 4096)
         return list(buf[:n])
+
+
+class ReferenceGpuScene(ReferenceScene):
+    """The same through libxrtrefgpu.so, which adds RefGpuRenderer (and with it a link to libxrtgpu.so): drop-in test only."""
+
+    @staticmethod
+    def _lib():
+        return capi.reference(with_gpu=True)
 
 
 def kat(lib, pfx, name, *args, n_out):

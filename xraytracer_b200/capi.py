@@ -86,7 +86,8 @@ class Stats(C.Structure):
                 ("shade_launches", C.c_uint64), ("connect_launches", C.c_uint64), ("render_ms", C.c_float),
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("primary_hits", C.c_uint64),
-                ("bounce_entries", C.c_uint64), ("bounce_launches", C.c_uint64)]
+                ("bounce_entries", C.c_uint64), ("bounce_launches", C.c_uint64), ("rays_traced", C.c_uint64),
+                ("truncated_paths", C.c_uint64), ("reduce_ms", C.c_float), ("n_devices", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -101,31 +102,53 @@ class SceneInfo(C.Structure):
                 ("bvh_depth", C.c_int32), ("bvh_sah_cost", C.c_float), ("build_ms", C.c_float),
                 ("upload_ms", C.c_float), ("device_bytes", C.c_uint64), ("upload_bytes", C.c_uint64),
                 ("bvh_build_ms", C.c_float), ("bvh_builder", C.c_int32),
-                ("small_records_all", C.c_int32), ("small_records_occ", C.c_int32)]
+                ("small_records_all", C.c_int32), ("small_records_occ", C.c_int32), ("small_flagged", C.c_int32),
+                ("n_wide_nodes", C.c_int32), ("wide_arity", C.c_int32), ("n_devices", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+TUNING_KEYS = ["fused_bounce", "volume_paths", "scissor", "brute_secondary", "brute_shadow", "thr_ext0", "thr_ext", "thr_con",
+               "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump"]
+
+
+class Tuning(C.Structure):
+    """xrtg_tuning: development / test switches of the pipeline selection; -1 = the measured default."""
+    _fields_ = [(k, C.c_int32) for k in TUNING_KEYS] + [("reserved", C.c_int32 * 4)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        for k in TUNING_KEYS:
+            setattr(self, k, int(kw.pop(k, -1)))
+        for i in range(4):
+            self.reserved[i] = -1
+        if kw:
+            raise TypeError(f"unknown tuning keys: {sorted(kw)}")
+
+
 # enums of xrtgpu.h
 INT_NORMAL, INT_FURNACE, INT_DIRECT, INT_INDIRECT, INT_GI, INT_WHITTED, INT_VOLUME, INT_VOLUME_NEE = range(8)
 INTEGRATOR_NAMES = ["normal", "furnace", "direct", "indirect", "gi", "whitted", "volume", "volume_nee"]
-FLAG_EXACT, FLAG_COUNTERS, FLAG_BRUTE_FORCE, FLAG_SUM_ONLY, FLAG_STAGE_TIMES = 1, 2, 4, 8, 16
+FLAG_EXACT, FLAG_COUNTERS, FLAG_BRUTE_FORCE, FLAG_SUM_ONLY, FLAG_STAGE_TIMES, FLAG_FAST_HOOK, FLAG_HOOK_SRC_PRIM = 1, 2, 4, 8, 16, 32, 64
 OBJ_MESH, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
 LIGHT_QUAD, LIGHT_TRIANGLE, LIGHT_SPHERE = 0, 1, 2
 MEDIUM_HOMOGENEOUS_MIS, MEDIUM_HOMOGENEOUS_ACHROMATIC, MEDIUM_HOMOGENEOUS_NOMIS, MEDIUM_HETEROGENEOUS = range(4)
-ABI_VERSION = 1
+ABI_VERSION = 2
 BUILD_LBVH_GPU = 1
 
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_create2", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
-               "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest", "xrtg_small_scene_selftest"]
+               "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest", "xrtg_small_scene_selftest", "xrtg_scene_create_multi",
+               "xrtg_scene_device_count", "xrtg_scene_set_tuning", "xrtg_partial_buffer", "xrtg_ipc_export", "xrtg_ipc_open",
+               "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8"]
 
 GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
 HOST_LIB = PKG / "host" / "libxrthost.so"
 ORACLE_LIB = ROOT / "oracle" / "libxrtoracle.so"
-REF_LIB = ROOT / "oracle" / "_ref" / "libxrtref.so"
+REF_LIB = ROOT / "oracle" / "_ref" / "libxrtref.so"          # CPU checker / reference arm: no product library behind it
+REF_GPU_LIB = ROOT / "oracle" / "_ref" / "libxrtrefgpu.so"   # the same + RefGpuRenderer -> libxrtgpu.so (drop-in test only)
 
 _cache = {}
 P = C.POINTER
@@ -163,6 +186,15 @@ def gpu():
     lib.xrtg_image_to_u8.argtypes = [C.c_int, VP, C.c_int, C.c_int, C.c_float, C.c_int, VP]
     lib.xrtg_bvh_selftest.argtypes = [VP, C.c_int, C.c_int, P(C.c_int), P(C.c_int), P(C.c_float)]
     lib.xrtg_small_scene_selftest.argtypes = [VP, VP, C.c_int, P(C.c_int), P(C.c_int), P(C.c_int)]
+    lib.xrtg_scene_create_multi.argtypes = [P(SceneDesc), C.c_int, P(C.c_int), C.c_uint32, P(VP)]
+    lib.xrtg_scene_device_count.argtypes = [VP]
+    lib.xrtg_scene_set_tuning.argtypes = [VP, P(Tuning)]
+    lib.xrtg_partial_buffer.argtypes = [VP, C.c_int, C.c_int, P(VP)]
+    lib.xrtg_ipc_export.argtypes = [VP, VP]
+    lib.xrtg_ipc_open.argtypes = [VP, VP, P(VP)]
+    lib.xrtg_ipc_close.argtypes = [VP, VP]
+    lib.xrtg_reduce_finalize.argtypes = [VP, P(VP), C.c_int, VP, C.c_size_t, C.c_size_t, C.c_float, VP]
+    lib.xrtg_render_u8.argtypes = [VP, P(Camera), P(RenderParams), C.c_float, C.c_int, VP, P(Stats)]
     lib._typed = True
     return lib
 
@@ -236,13 +268,15 @@ def have_reference() -> bool:
     return REF_LIB.exists()
 
 
-def reference():
-    """oracle/_ref/libxrtref.so — the compiled reference. TEST / BASELINE USE ONLY."""
-    lib = _load(REF_LIB, "compiled reference libxrtref.so")
+def reference(with_gpu: bool = False):
+    """oracle/_ref/libxrtref.so — the compiled reference. TEST / BASELINE USE ONLY. with_gpu: libxrtrefgpu.so, the variant
+    that also carries RefGpuRenderer and therefore links libxrtgpu.so (tests/test_gpu_dropin_reference.py)."""
+    lib = _load(REF_GPU_LIB, "compiled reference + GPU binding libxrtrefgpu.so") if with_gpu else _load(REF_LIB, "compiled reference libxrtref.so")
     if not getattr(lib, "_typed", False):
         _type_oracle(lib, "xrtref_", False)
         lib.xrtref_object_order.argtypes = [VP, P(C.c_int32), C.c_int]
         lib.xrtref_render_pstl.argtypes = [VP, P(Camera), P(RenderParams), VP, P(C.c_double)]
-        lib.xrtref_render_gpu.argtypes = [VP, P(Camera), P(RenderParams), VP]
+        if with_gpu:
+            lib.xrtref_render_gpu.argtypes = [VP, P(Camera), P(RenderParams), VP]
         lib._typed = True
     return lib

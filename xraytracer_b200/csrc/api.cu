@@ -19,112 +19,46 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "lbvh.h"
+#include "scene_impl.h"
 
 using namespace xrt;
 
 namespace {
-
 thread_local std::string g_err;
+float4 f4(const float* p, float w) { return make_float4(p[0], p[1], p[2], w); }
+float asF(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+float asF(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+} // namespace
 
+namespace xrt {
 int fail(int code, const std::string& msg)
 {
     g_err = msg;
     return code;
 }
+} // namespace xrt
 
-#define CU(call)                                                                                                    \
-    do {                                                                                                            \
-        cudaError_t e__ = (call);                                                                                   \
-        if (e__ != cudaSuccess)                                                                                     \
-            return fail(e__ == cudaErrorMemoryAllocation ? XRTG_ERR_OOM : XRTG_ERR_CUDA,                            \
-                        std::string(#call) + ": " + cudaGetErrorString(e__));                                       \
-    } while (0)
-
-// pinned host array + device mirror
-struct Mirror {
-    void* h = nullptr;
-    void* d = nullptr;
-    size_t bytes = 0;
-    int alloc(size_t n)
-    {
-        release();
-        bytes = n;
-        if (n == 0) return 0;
-        CU(cudaMallocHost(&h, n));
-        CU(cudaMalloc(&d, n));
-        return 0;
+xrtg_scene::~xrtg_scene()
+{
+    for (size_t k = 1; k < replicas.size(); ++k) { // replica 0 is this scene itself
+        cudaSetDevice(replicas[k]->device);
+        delete replicas[k];
     }
-    void release()
-    {
-        if (h) cudaFreeHost(h);
-        if (d) cudaFree(d);
-        h = d = nullptr;
-        bytes = 0;
-    }
-    ~Mirror() { release(); }
-};
+    cudaSetDevice(device);
+    if (statsHost) cudaFreeHost(statsHost);
+    if (ctrlHost) cudaFreeHost(ctrlHost);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : stageEvents) cudaEventDestroy(e);
+    if (doneEvent) cudaEventDestroy(doneEvent);
+    if (pullEvent) cudaEventDestroy(pullEvent);
+    if (stream) cudaStreamDestroy(stream);
+}
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t n)
-    {
-        if (n <= bytes) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        CU(cudaMalloc(&p, n));
-        bytes = n;
-        return 0;
-    }
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-
-float4 f4(const float* p, float w) { return make_float4(p[0], p[1], p[2], w); }
-float asF(int v) { float f; std::memcpy(&f, &v, 4); return f; }
-float asF(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
-
-struct Timer {
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
-};
-
-} // namespace
-
-struct xrtg_scene {
-    int device = 0;
-    cudaStream_t stream = nullptr; // uploads + host-buffer renders
-    // scene arrays (pinned host copy + device copy)
-    Mirror nodes, nodes4, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
-    std::vector<std::unique_ptr<Mirror>> gridData;
-    DScene ds{};
-    xrtg_scene_info info{};
-    int maxShadowPerPath = 1;
-    float boundsLo[3] = {0, 0, 0}, boundsHi[3] = {0, 0, 0}; // world bounds of every primitive (valid if hasBounds)
-    bool hasBounds = false;
-    // workspace
-    DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
-    unsigned long long* statsHost = nullptr; // pinned
-    uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
-    cudaEvent_t ev[4] = {};
-    std::vector<cudaEvent_t> stageEvents; // pairs, with COUNTERS
-    std::vector<int> stageKinds;
-
-    ~xrtg_scene()
-    {
-        if (statsHost) cudaFreeHost(statsHost);
-        if (ctrlHost) cudaFreeHost(ctrlHost);
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
-        for (auto& e : stageEvents) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
-    }
-};
-
-namespace {
+namespace xrt {
 
 int uploadAll(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->nodes4, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
     for (Mirror* m : all) {
         if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
@@ -137,6 +71,10 @@ int uploadAll(xrtg_scene* s)
     s->info.upload_bytes = total;
     return 0;
 }
+
+} // namespace xrt
+
+namespace {
 
 int checkDesc(const xrtg_scene_desc* d)
 {
@@ -159,6 +97,40 @@ int checkDesc(const xrtg_scene_desc* d)
             return fail(XRTG_ERR_INVALID, "heterogeneous medium without a grid");
     return 0;
 }
+
+// XRT_TUNING="key=value,key=value": development overrides, read ONCE per scene creation (the render path reads no environment)
+struct TuningKey { const char* name; int32_t xrtg_tuning::*field; };
+const TuningKey kTuningKeys[] = {
+    {"fused_bounce", &xrtg_tuning::fused_bounce}, {"volume_paths", &xrtg_tuning::volume_paths}, {"scissor", &xrtg_tuning::scissor},
+    {"brute_secondary", &xrtg_tuning::brute_secondary}, {"brute_shadow", &xrtg_tuning::brute_shadow}, {"thr_ext0", &xrtg_tuning::thr_ext0},
+    {"thr_ext", &xrtg_tuning::thr_ext}, {"thr_con", &xrtg_tuning::thr_con}, {"steps_per_vote", &xrtg_tuning::steps_per_vote},
+    {"leaf_threshold", &xrtg_tuning::leaf_threshold}, {"thr_vol", &xrtg_tuning::thr_vol}, {"spv_vol", &xrtg_tuning::spv_vol},
+    {"wide_bvh", &xrtg_tuning::wide_bvh}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
+    {"stage_dump", &xrtg_tuning::stage_dump}};
+
+void tuningFromEnvironment(Tuning& tu)
+{
+    const char* e = std::getenv("XRT_TUNING");
+    if (!e) return;
+    std::string str(e);
+    size_t pos = 0;
+    while (pos < str.size()) {
+        size_t end = str.find(',', pos);
+        if (end == std::string::npos) end = str.size();
+        const std::string item = str.substr(pos, end - pos);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos) {
+            const std::string key = item.substr(0, eq);
+            const int val = std::atoi(item.c_str() + eq + 1);
+            bool known = false;
+            for (const TuningKey& k : kTuningKeys)
+                if (key == k.name) { tu.t.*(k.field) = val; known = true; }
+            if (!known) std::fprintf(stderr, "libxrtgpu: XRT_TUNING: unknown key '%s' ignored\n", key.c_str());
+        }
+        pos = end + 1;
+    }
+}
+int tv(int32_t v, int dflt) { return v >= 0 ? int(v) : dflt; } // tuning value or the measured default
 
 } // namespace
 
@@ -194,6 +166,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     CU(cudaSetDevice(device));
     auto s = std::make_unique<xrtg_scene>();
     s->device = device;
+    tuningFromEnvironment(s->tuning);
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) CU(cudaEventCreate(&e));
     CU(cudaMallocHost(&s->statsHost, sizeof(unsigned long long) * kStatCount));
@@ -330,10 +303,13 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     }
     if (!builtOnGpu) {
         Timer tbv;
-        // at most 4 triangles per leaf (the leaf code of k_trace holds count-1 in 2 bits); XRT_MAX_LEAF overrides for experiments
-        const char* ml = std::getenv("XRT_MAX_LEAF");
-        const int maxLeaf = ml ? std::min(4, std::max(1, std::atoi(ml))) : 4;
+        // at most 4 triangles per leaf (the leaf code of k_trace holds count-1 in 2 bits)
+        const int maxLeaf = std::min(4, std::max(1, tv(s->tuning.t.max_leaf, 4)));
         buildBvh(buildTris.data(), uint32_t(nMeshTris), maxLeaf, bvh);
+        // The traversal stacks hold 24 shared + 40 local = 64 entries and a two-child walk pushes at most one entry per level:
+        // the builder stops SAH splits at depth 56 and then halves index ranges, so depth <= 56 + log2(n / maxLeaf) can exceed
+        // that on pathological input (hundreds of thousands of coincident centroids). Refuse instead of overflowing silently.
+        if (bvh.depth > 60) return fail(XRTG_ERR_UNSUPPORTED, "BVH depth " + std::to_string(bvh.depth) + " exceeds the traversal stack (60): degenerate triangle distribution");
         s->info.bvh_build_ms = tbv.ms();
         s->info.bvh_builder = 0;
         if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
@@ -350,12 +326,14 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(bvh.triOrder[k]), 4 * sizeof(float4));
     }
     // ---- deep trees: four-child form for the resumable traversal kernel (bvh.h) ----
-    if (bvh.nodes.size() > 512 && std::getenv("XRT_NO_BVH4") == nullptr) {
+    if (bvh.nodes.size() > 512 && tv(s->tuning.t.wide_bvh, 4) >= 4) {
         std::vector<Bvh4Node> wide;
         const int depth4 = collapseBvh4(static_cast<const BvhNode*>(s->nodes.h), bvh.nodes.size(), wide);
         if (3 * depth4 + 1 <= 64) { // a four-child node pushes up to three entries: must fit the traversal stack (24 shared + 40 local)
             if (int rc = s->nodes4.alloc(sizeof(Bvh4Node) * wide.size())) return rc;
             std::memcpy(s->nodes4.h, wide.data(), s->nodes4.bytes);
+            s->info.n_wide_nodes = int(wide.size());
+            s->info.wide_arity = 4;
         }
     }
     // ---- small scenes: plane-grouped triangle block for k_bounce_small (small_scene.h) ----
@@ -363,21 +341,60 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
         std::vector<float> block;
         SmallBlockInfo sbi;
-        // every point a shadow ray can start or end at (hull pruning of the occluder section, small_scene.h); a DistantLight's
-        // shadow rays leave the scene, so no pruning then
+        // Every point a shadow ray can start or end at (hull pruning of the occluder section, small_scene.h): triangle vertices,
+        // the bounding corners of the spheres (grown by the largest shadow-ray bias), point lights. A DistantLight's shadow rays
+        // leave the scene, so no pruning then.
+        const float kMaxBias = 0.1f; // Whitted's 0.1 (integrator.h:337) covers Direct / GI's 0.01 (integrator.h:100, 260)
         std::vector<float> hull(buildTris);
         bool distant = false;
         for (int i = 0; i < d->n_objects; ++i)
             if (d->objects[i].kind == XRTG_OBJ_SPHERE) {
                 const xrtg_sphere& sp = d->spheres[d->objects[i].first];
+                const float r = std::fabs(sp.radius) + kMaxBias;
                 for (int c = 0; c < 8; ++c)
-                    for (int a = 0; a < 3; ++a) hull.push_back(sp.center[a] + ((c >> a) & 1 ? sp.radius : -sp.radius));
+                    for (int a = 0; a < 3; ++a) hull.push_back(sp.center[a] + ((c >> a) & 1 ? r : -r));
             }
         for (int i = 0; i < d->n_delta_lights; ++i) {
             if (d->delta_lights[i].kind == XRTG_DLIGHT_POINT) hull.insert(hull.end(), d->delta_lights[i].pos_or_dir, d->delta_lights[i].pos_or_dir + 3);
             else distant = true;
         }
-        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi, distant ? nullptr : hull.data(), int(hull.size() / 3))) {
+        std::vector<int> pruned;
+        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi, distant ? nullptr : hull.data(), int(hull.size() / 3), &pruned)) {
+            // Shadow rays do not start ON the surfaces: the origin is hit + bias * ng with ng never flipped towards the ray
+            // (SURVEY §9-T3). On a triangle whose normal points OUT of the hull the origin lies behind a hull plane and the
+            // reference lets that plane shadow it. An origin p + b * ng (b <= kMaxBias) is a convex combination of the
+            // triangle's vertices and the vertices pushed out by kMaxBias, so it suffices to test those: a triangle with such a
+            // vertex behind a pruned plane is flagged and its shadow rays test the unpruned occluder section (wf_shade.cuh).
+            float ext = 0.f;
+            for (float v : hull) ext = std::max(ext, std::fabs(v));
+            const double tol = 1e-5 * std::max(double(ext), 1e-6); // the tolerance planeBoundsPoints() pruned with
+            const float* recs = reinterpret_cast<const float*>(ftrisId);
+            // a pruned plane has the scene on ONE side; which one is the sign of the summed vertex distances
+            std::vector<double> side(pruned.size(), 0.0);
+            for (size_t k = 0; k < pruned.size(); ++k)
+                for (size_t h = 0; h + 2 < buildTris.size(); h += 3) side[k] += planeSignedDistance(recs + 16 * size_t(pruned[k]), &buildTris[h]);
+            for (int t = 0; t < nMeshTris && !pruned.empty(); ++t) {
+                int id;
+                std::memcpy(&id, recs + 16 * size_t(t) + 12, 4);
+                const float* v = &buildTris[size_t(t) * 9];
+                const float4 n0 = prims[4 * id], n1 = prims[4 * id + 1], n2 = prims[4 * id + 2];
+                const float ng[3] = {n0.w, n1.w, n2.w};
+                bool outside = false;
+                for (int k = 0; k < 3 && !outside; ++k) {
+                    const float q[3] = {v[3 * k] + kMaxBias * ng[0], v[3 * k + 1] + kMaxBias * ng[1], v[3 * k + 2] + kMaxBias * ng[2]};
+                    for (size_t pk = 0; pk < pruned.size(); ++pk) {
+                        const double sd = planeSignedDistance(recs + 16 * size_t(pruned[pk]), q);
+                        if ((side[pk] >= 0.0 && sd < -tol) || (side[pk] < 0.0 && sd > tol)) { outside = true; break; }
+                    }
+                }
+                if (outside) {
+                    uint32_t meta;
+                    std::memcpy(&meta, &prims[4 * id + 3].w, 4);
+                    meta |= kMetaShadowOutside;
+                    std::memcpy(&prims[4 * id + 3].w, &meta, 4);
+                    ++s->info.small_flagged;
+                }
+            }
             s->info.small_records_all = sbi.nRecordsAll;
             s->info.small_records_occ = sbi.nRecordsOcc;
             if (int rc = s->smallBlock.alloc(block.size() * sizeof(float))) return rc;
@@ -451,6 +468,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     DScene& ds = s->ds;
     ds.nodes = static_cast<const float4*>(s->nodes.d);
     ds.nodes4 = static_cast<const float4*>(s->nodes4.d);
+    ds.nodes8 = static_cast<const uint4*>(s->nodes8.d);
     ds.tris = static_cast<const float4*>(s->tris.d);
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
     ds.ftris = static_cast<const float4*>(s->ftris.d);
@@ -475,6 +493,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     s->info.bvh_depth = bvh.depth;
     s->info.bvh_sah_cost = bvh.sahCost;
     s->info.device_bytes = s->info.upload_bytes;
+    s->info.n_devices = 1;
     *out = s.release();
     return 0;
 }
@@ -482,10 +501,20 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
 int xrtg_scene_upload(xrtg_scene* s)
 {
     if (!s) return fail(XRTG_ERR_INVALID, "scene is NULL");
-    CU(cudaSetDevice(s->device));
     Timer t;
-    if (int rc = uploadAll(s)) return rc;
-    CU(cudaStreamSynchronize(s->stream));
+    const std::vector<xrtg_scene*> all = s->replicas.empty() ? std::vector<xrtg_scene*>{s} : s->replicas;
+    for (xrtg_scene* r : all) { // every replica's copies are enqueued before the first one is waited for
+        CU(cudaSetDevice(r->device));
+        if (int rc = uploadAll(r)) return rc;
+    }
+    size_t total = 0;
+    for (xrtg_scene* r : all) {
+        CU(cudaSetDevice(r->device));
+        CU(cudaStreamSynchronize(r->stream));
+        total += r->info.upload_bytes;
+    }
+    CU(cudaSetDevice(s->device));
+    s->info.upload_bytes = total; // all devices
     s->info.upload_ms = t.ms();
     return 0;
 }
@@ -528,7 +557,7 @@ struct StageTimer {
     }
 };
 
-int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, int maxIter, bool exact)
+int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, size_t maxShadow, int maxIter, bool exact)
 {
     const size_t f4b = sizeof(float4);
     for (int k = 0; k < 2; ++k) {
@@ -537,10 +566,12 @@ int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, int maxI
         if (int rc = s->q2[k].ensure(f4b * maxPaths)) return rc;
     }
     if (int rc = s->hits.ensure(f4b * maxPaths)) return rc;
-    const size_t nShadow = size_t(maxPaths) * s->maxShadowPerPath;
+    // shadow queue: one entry per (path, light) in the three-kernel pipeline; s0 doubles as the second hit buffer of the fused
+    // bounce kernel, so it is never smaller than the ray queue
+    const size_t nShadow = std::max<size_t>(maxShadow, maxPaths);
     if (int rc = s->s0.ensure(f4b * nShadow)) return rc;
-    if (int rc = s->s1.ensure(f4b * nShadow)) return rc;
-    if (int rc = s->s2.ensure(f4b * nShadow)) return rc;
+    if (int rc = s->s1.ensure(f4b * std::max<size_t>(maxShadow, 1))) return rc;
+    if (int rc = s->s2.ensure(f4b * std::max<size_t>(maxShadow, 1))) return rc;
     if (int rc = s->radiance.ensure(f4b * maxPaths)) return rc;
     if (int rc = s->ctrl.ensure(sizeof(uint32_t) * kCtrlStride * size_t(maxIter + 2))) return rc;
     if (int rc = s->accum.ensure(sizeof(float) * 3 * size_t(nPixels))) return rc;
@@ -580,6 +611,10 @@ DCamera makeCamera(const xrtg_camera* c)
 
 bool isVolume(int integ) { return integ == XRTG_INT_VOLUME || integ == XRTG_INT_VOLUME_NEE; }
 
+} // namespace
+
+namespace xrt {
+
 int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p)
 {
     if (!s || !cam || !p) return fail(XRTG_ERR_INVALID, "NULL argument");
@@ -592,6 +627,10 @@ int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_p
     if (p->integrator == XRTG_INT_VOLUME_NEE && s->ds.nLights == 0) return fail(XRTG_ERR_INVALID, "VolumePathTracingNEE needs an area light");
     return 0;
 }
+
+} // namespace xrt
+
+namespace {
 
 // Conservative pixel rectangle that can see the scene's bounding box through PinholeCamera::sampleRay (camera.h:49-60):
 // dir_cam = ((2u-1)s, (1-2v)s/aspect, -1), dir_world = dir_cam * R (row vector, geometry.h:653-669), origin = c2w row 3. Each box
@@ -637,6 +676,49 @@ void computeScissor(const xrtg_scene* s, const xrtg_camera* cam, int W, int H, i
     if (out[3] < out[1]) out[3] = out[1];
 }
 
+// Which kernels render this scene. Chosen per (scene, integrator); the parity hooks with XRTG_FLAG_FAST_HOOK ask the same
+// function, so they exercise exactly the entry points a render would.
+//   deep    : > 512 BVH nodes -> raygen + k_trace (refillable state machine over the wide tree) + shade + k_trace<any>
+//   small   : <= 64 triangles -> incoherent rays test every triangle from shared memory (SmallTracer)
+//   fusedBounce : small scene + surface integrator -> k_primary, then ONE k_bounce_small per bounce
+//   volumePaths : shallow BVH + volume integrator -> k_primary, then every path to completion in k_volume_paths
+// Measured defaults (profiles/r01_notes.md); every switch can be overridden through xrtg_scene_set_tuning.
+struct Pipeline {
+    bool deep, small, fusedPrimary, fusedBounce, volumePaths, bruteSecondary, bruteShadow, scissor;
+    int thrExt0, thrExt, thrCon, spv, leafThr, thrVol, spvVol;
+};
+Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, bool brute)
+{
+    const xrtg_tuning& t = s->tuning.t;
+    Pipeline P{};
+    P.deep = s->info.n_bvh_nodes > 512;
+    P.thrExt0 = tv(t.thr_ext0, P.deep ? 1 : 0);
+    P.thrExt = tv(t.thr_ext, P.deep ? 16 : 0);
+    P.thrCon = tv(t.thr_con, P.deep ? 16 : 0);
+    P.spv = tv(t.steps_per_vote, P.deep ? 4 : 1);
+    P.leafThr = tv(t.leaf_threshold, 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
+    P.thrVol = tv(t.thr_vol, 16);
+    P.spvVol = tv(t.spv_vol, 2);
+    P.small = !P.deep && s->ds.nBruteTris > 0 && s->ds.nBruteTris <= 64;
+    P.bruteSecondary = tv(t.brute_secondary, P.small ? 1 : 0) != 0;
+    P.bruteShadow = tv(t.brute_shadow, P.small ? 1 : 0) != 0;
+    // throughput instantiation only: the exact one must advance every pixel's mt19937 stream by its two jitter draws
+    P.scissor = !exact && tv(t.scissor, 1) != 0;
+    // Shallow BVHs: ray generation is fused with the primary closest hit (k_primary, compact hit-only queue). Deep BVHs: separate
+    // raygen + the refillable traversal kernel, which is faster there even on primary rays.
+    P.fusedPrimary = !P.deep && nIter > 0;
+    const bool volume = integ == XRTG_INT_VOLUME || integ == XRTG_INT_VOLUME_NEE;
+    P.volumePaths = P.fusedPrimary && volume && s->ds.nMedia <= 8 && s->ds.nGrids <= 8 && tv(t.volume_paths, 1) != 0;
+    P.fusedBounce = P.fusedPrimary && P.small && !brute && P.bruteSecondary && P.bruteShadow && tv(t.fused_bounce, 1) != 0 &&
+                    s->ds.nPrims <= 96 && s->ds.nLights <= 8 && // what k_bounce_small stages in shared memory (kSmallPrims / kSmallLights)
+                    (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
+    return P;
+}
+
+} // namespace
+
+namespace xrt {
+
 // The whole render on `st`, result (mean or sum) written to device buffer `out`.
 int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats)
 {
@@ -648,21 +730,31 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     const int integ = p->integrator;
     const bool volume = isVolume(integ);
 
-    // samples per wave: exact = 1 (the mt19937 stream of a pixel is sequential across its samples)
-    uint32_t S = 1;
-    if (!exact) {
-        const uint64_t target = 8u << 20; // ~8M paths in flight
-        S = p->samples_per_wave > 0 ? uint32_t(p->samples_per_wave) : uint32_t(std::max<uint64_t>(1, target / nPixels));
-        S = std::min<uint32_t>(S, uint32_t(p->spp));
-        while (uint64_t(S) * nPixels > (1ull << 31) - 64) --S;
-    }
     int nIter;
     if (integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI) nIter = p->max_depth;
-    else if (volume) nIter = std::min(4 * p->max_depth + 8, 4096);
+    else if (volume) nIter = std::min(4 * p->max_depth + 8, 4096); // medium crossings per path; cut paths are counted (truncated_paths)
     else nIter = 1;
     const bool hasShadow = (integ == XRTG_INT_DIRECT || integ == XRTG_INT_GI || integ == XRTG_INT_WHITTED);
+    const Pipeline P = choosePipeline(s, integ, nIter, exact, brute);
 
-    if (int rc = ensureWorkspace(s, nPixels, S * nPixels, nIter, exact)) return rc;
+    // ---- wave size from a BYTE budget ----
+    // A wave is `S` samples of a range of `tile` pixels. Workspace per path: 2 x 48 B ping-pong ray queue + 16 B hit + 16 B
+    // radiance, plus — in the three-kernel pipeline only — 48 B per shadow-queue entry x one entry per area (or delta) light:
+    // an emissive mesh of a few hundred triangle lights needs tens of KB per path, so the wave shrinks (down to a range of
+    // pixels at one sample each) instead of the allocation failing. Default budget 6 GiB, ~8 M paths at most.
+    const size_t shadowPerPath = (hasShadow && !P.fusedBounce) ? size_t(s->maxShadowPerPath) : 0;
+    const size_t bytesPerPath = 128 + 48 * shadowPerPath;
+    const size_t budget = size_t(tv(s->tuning.t.workspace_mb, 6144)) << 20;
+    uint64_t maxPaths = std::min<uint64_t>(8u << 20, std::max<uint64_t>(budget / bytesPerPath, 1024));
+    uint32_t S = 1, tile = nPixels; // exact: one sample per wave (the mt19937 stream of a pixel is sequential across its samples)
+    if (!exact) {
+        if (p->samples_per_wave > 0) S = std::min<uint32_t>(uint32_t(p->samples_per_wave), uint32_t(p->spp));
+        else S = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(maxPaths / nPixels, uint64_t(p->spp))));
+    }
+    if (S == 1 && maxPaths < nPixels) tile = uint32_t(maxPaths); // not even one sample of every pixel fits: waves over pixel ranges
+    while (uint64_t(S) * tile > (1ull << 31) - 64) --S;
+
+    if (int rc = ensureWorkspace(s, nPixels, S * tile, size_t(S) * tile * shadowPerPath, nIter, exact)) return rc;
     DQueues q = makeQueues(s);
     const DCamera dc = makeCamera(cam);
     float* accum = static_cast<float*>(s->accum.p);
@@ -677,71 +769,48 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     w.mti = static_cast<uint32_t*>(s->mti.p);
 
     StageTimer tm{s, st, count || (p->flags & XRTG_FLAG_STAGE_TIMES) != 0};
-    // traversal tunables (development overrides through the environment)
-    auto envInt = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
-    // Traversal kernel choice (measured sweep + ncu, profiles/r01_notes.md): deep BVHs use the refillable state-machine
-    // kernel k_trace (threshold 16, 4 steps per vote: 1.25x on the 1M-triangle scene); shallow BVHs (Cornell: 17 nodes,
-    // ~7 node visits per ray) use the simple run-to-completion kernels (threshold 0), which execute ~30 % fewer
-    // instructions per ray.
-    const bool deep = s->info.n_bvh_nodes > 512;
-    const int thrExt0 = envInt("XRT_THR_EXT0", deep ? 1 : 0), thrExt = envInt("XRT_THR_EXT", deep ? 16 : 0);
-    const int thrCon = envInt("XRT_THR_CON", deep ? 16 : 0);
-    const int spv = envInt("XRT_SPV", deep ? 4 : 1);
-    const int leafThr = envInt("XRT_LEAF_THR", 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
     const int missMode = integ == XRTG_INT_DIRECT ? 1 : (integ == XRTG_INT_WHITTED ? 2 : 0);
-    // Small scenes (<= 64 triangles, shallow BVH): incoherent rays — every closest-hit bounce after the primary one and all
-    // shadow rays — test every triangle from shared memory instead of walking the BVH; the warp stays converged and it is
-    // what the reference does anyway (measured on c3: extend 2.15 -> 1.70 ms, connect 1.24 -> 1.10 ms per 8 spp).
-    const bool small = !deep && s->ds.nBruteTris > 0 && s->ds.nBruteTris <= 64;
-    const bool bruteSecondary = envInt("XRT_BRUTE_SECONDARY", small ? 1 : 0) != 0, bruteShadow = envInt("XRT_BRUTE_SHADOW", small ? 1 : 0) != 0;
-    const bool dump = std::getenv("XRT_STAGE_DUMP") != nullptr;
-    // throughput instantiation only: the exact one must advance every pixel's mt19937 stream by its two jitter draws
-    if (!exact && envInt("XRT_SCISSOR", 1) != 0) {
+    const bool dump = tv(s->tuning.t.stage_dump, 0) != 0;
+    if (P.scissor) {
         int sc4[4];
         computeScissor(s, cam, p->width, p->height, sc4);
         w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
     }
-    uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0, nBounce = 0;
+    uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0, nBounce = 0, truncatedHost = 0;
     CU(cudaEventRecord(s->ev[0], st));
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
     CU(cudaMemsetAsync(dstats, 0, sizeof(unsigned long long) * kStatCount, st));
     if (exact) { K.seedMt(st, w); ++launches; }
 
+    for (uint32_t pix0 = 0; pix0 < nPixels; pix0 += tile)
     for (uint32_t done = 0; done < uint32_t(p->spp); done += S) {
         const uint32_t sw = std::min<uint32_t>(S, uint32_t(p->spp) - done);
+        w.pixelBase = pix0;
+        w.wavePixels = std::min<uint32_t>(tile, nPixels - pix0);
         w.samplesThisWave = sw;
-        w.nPaths = sw * nPixels;
+        w.nPaths = sw * w.wavePixels;
         w.sampleBase = uint32_t(p->sample_offset) + done;
         tm.begin(kStageOther);
         CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * size_t(nIter + 2), st));
-        // Shallow BVHs: ray generation is fused with the primary closest hit (k_primary, compact hit-only queue).
-        // Deep BVHs: separate raygen + the refillable traversal kernel, which is faster there even on primary rays.
         // No bounce at all (maxDepth 0): only the per-path radiance has to be cleared.
-        const bool fusedPrimary = !deep && nIter > 0;
-        // Small scenes under the ray-tracing surface integrators: per bounce ONE kernel (k_bounce_small) instead of shade ->
-        // connect -> extend; see wavefront.cuh.
-        const bool volumePaths = fusedPrimary && volume && s->ds.nMedia <= 8 && s->ds.nGrids <= 8 && envInt("XRT_VOLUME_PATHS", 1) != 0;
-        const bool fusedBounce = fusedPrimary && small && !brute && bruteSecondary && bruteShadow && envInt("XRT_FUSED_BOUNCE", 1) != 0 &&
-                                 s->ds.nPrims <= 96 && s->ds.nLights <= 8 && // what k_bounce_small stages in shared memory (kSmallPrims / kSmallLights)
-                                 (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
         if (nIter == 0) CU(cudaMemsetAsync(q.radiance, 0, sizeof(float4) * size_t(w.nPaths), st));
-        else if (!fusedPrimary) { K.raygen(st, dc, q, w, nullptr); ++launches; }
+        else if (!P.fusedPrimary) { K.raygen(st, dc, q, w, nullptr); ++launches; }
         tm.end();
         for (int b = 0; b < nIter; ++b) {
             const int src = b & 1;
-            if (volumePaths) { // volume integrators on a shallow BVH: primary, then every path to completion in one launch
+            if (P.volumePaths) { // volume integrators on a shallow BVH: primary, then every path to completion in one launch
                 tm.begin(kStageExtend);
-                K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
+                K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
                 tm.end();
                 tm.begin(kStageShade);
-                K.volumePaths(st, s->ds, q, w, brute, nIter, envInt("XRT_THR_VOL", 16), envInt("XRT_SPV_VOL", 2), count, dstats); ++launches; ++nShade;
+                K.volumePaths(st, s->ds, q, w, brute, nIter, P.thrVol, P.spvVol, count, dstats); ++launches; ++nShade;
                 tm.end();
                 break;
             }
-            if (fusedBounce) { // small scene: primary, then one fused shade + connect + extend kernel per bounce
+            if (P.fusedBounce) { // small scene: primary, then one fused shade + connect + extend kernel per bounce
                 if (b == 0) {
                     tm.begin(kStageExtend);
-                    K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats); ++launches; ++nExtend;
+                    K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
                     tm.end();
                 }
                 tm.begin(kStageShade);
@@ -750,8 +819,8 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 continue;
             }
             tm.begin(kStageExtend);
-            if (b == 0 && fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats);
-            else K.extend(st, s->ds, q, src, b, brute ? 1 : ((bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? thrExt0 : thrExt, spv, leafThr);
+            if (b == 0 && P.fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr);
+            else K.extend(st, s->ds, q, src, b, brute ? 1 : ((P.bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? P.thrExt0 : P.thrExt, P.spv, P.leafThr);
             ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
@@ -761,7 +830,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             tm.end();
             if (hasShadow) {
                 tm.begin(kStageConnect);
-                K.connect(st, s->ds, q, b, brute ? 1 : (bruteShadow ? 2 : 0), count, dstats, thrCon, spv, leafThr); ++launches; ++nConnect;
+                K.connect(st, s->ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
                 tm.end();
             }
             if (volume) {
@@ -769,6 +838,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 CU(cudaMemcpyAsync(s->ctrlHost, q.ctrl + (b + 1) * kCtrlStride + kCtrlRays, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 if (s->ctrlHost[0] == 0) break;
+                if (b + 1 == nIter) truncatedHost += s->ctrlHost[0]; // paths still alive at the iteration bound
             }
         }
         tm.begin(kStageOther);
@@ -795,6 +865,9 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         stats->tracking_steps = s->statsHost[kStatSteps];
         stats->primary_hits = s->statsHost[kStatPrimaryHits];
         stats->bounce_entries = s->statsHost[kStatBounceEntries];
+        stats->rays_traced = stats->closest_rays + stats->shadow_rays - s->statsHost[kStatScissored];
+        stats->truncated_paths = s->statsHost[kStatTruncated] + truncatedHost;
+        stats->n_devices = 1;
         stats->bounce_launches = nBounce;
         stats->kernel_launches = launches;
         stats->extend_launches = nExtend; stats->shade_launches = nShade; stats->connect_launches = nConnect;
@@ -814,7 +887,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     return 0;
 }
 
-} // namespace
+} // namespace xrt
 
 __global__ void k_image_to_u8(const float* __restrict__ rgb, unsigned char* __restrict__ out, size_t nPixels, float invGamma, int bgr)
 {
@@ -969,11 +1042,21 @@ int xrtg_image_to_u8(int device, const float* rgb_host, int width, int height, f
     return 0;
 }
 
+int xrtg_scene_set_tuning(xrtg_scene* s, const xrtg_tuning* t)
+{
+    if (!s || !t) return fail(XRTG_ERR_INVALID, "NULL argument");
+    for (xrtg_scene* r : s->replicas.empty() ? std::vector<xrtg_scene*>{s} : s->replicas) r->tuning.t = *t;
+    return 0;
+}
+
+int xrtg_scene_device_count(const xrtg_scene* s) { return s ? std::max<int>(1, int(s->replicas.size())) : 0; }
+
 int xrtg_render_device(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgb_device, void* cuda_stream,
                        xrtg_stats* stats)
 {
     if (int rc = checkParams(s, cam, p)) return rc;
     if (!rgb_device) return fail(XRTG_ERR_INVALID, "rgb_device is NULL");
+    if (s->replicas.size() > 1) return fail(XRTG_ERR_UNSUPPORTED, "xrtg_render_device on a multi-GPU scene: use xrtg_render (host buffer)");
     CU(cudaSetDevice(s->device));
     return renderOnStream(s, cam, p, rgb_device, static_cast<cudaStream_t>(cuda_stream), stats);
 }
@@ -982,6 +1065,7 @@ int xrtg_render(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params*
 {
     if (int rc = checkParams(s, cam, p)) return rc;
     if (!rgb_host) return fail(XRTG_ERR_INVALID, "rgb_host is NULL");
+    if (s->replicas.size() > 1 && !(p->flags & XRTG_FLAG_EXACT) && p->spp >= 2) return renderMulti(s, cam, p, rgb_host, stats);
     CU(cudaSetDevice(s->device));
     const size_t bytes = sizeof(float) * 3 * size_t(p->width) * size_t(p->height);
     if (int rc = s->outDev.ensure(bytes)) return rc;
@@ -998,6 +1082,43 @@ int xrtg_render(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params*
     return 0;
 }
 
+int xrtg_render_u8(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float gamma, int bgr, uint8_t* out_host, xrtg_stats* stats)
+{
+    if (int rc = checkParams(s, cam, p)) return rc;
+    if (!out_host) return fail(XRTG_ERR_INVALID, "out_host is NULL");
+    if (p->flags & XRTG_FLAG_SUM_ONLY) return fail(XRTG_ERR_INVALID, "xrtg_render_u8 quantises the MEAN image: XRTG_FLAG_SUM_ONLY makes no sense here");
+    if (s->replicas.size() > 1) return fail(XRTG_ERR_UNSUPPORTED, "xrtg_render_u8 on a multi-GPU scene: render with xrtg_render, then xrtg_image_to_u8");
+    CU(cudaSetDevice(s->device));
+    const size_t n = size_t(p->width) * size_t(p->height);
+    if (int rc = s->outDev.ensure(sizeof(float) * 3 * n)) return rc;
+    if (int rc = s->rayTmp[3].ensure(3 * n)) return rc;
+    xrtg_stats local{};
+    if (int rc = renderOnStream(s, cam, p, static_cast<float*>(s->outDev.p), s->stream, stats ? &local : nullptr)) return rc;
+    // the float image never leaves HBM: gamma + quantisation read it where k_finalize wrote it, 3 bytes per pixel go to the host
+    k_image_to_u8<<<int(std::min<size_t>((n + 255) / 256, 148 * 8)), 256, 0, s->stream>>>(static_cast<const float*>(s->outDev.p), static_cast<unsigned char*>(s->rayTmp[3].p), n,
+                                                                                          gamma > 0.f ? 1.0f / gamma : 0.f, bgr);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    CU(cudaMemcpyAsync(out_host, s->rayTmp[3].p, 3 * n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev[3], s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (stats) {
+        *stats = local;
+        CU(cudaEventElapsedTime(&stats->d2h_ms, s->ev[2], s->ev[3]));
+    }
+    return 0;
+}
+
+// The production pipeline a parity hook with XRTG_FLAG_FAST_HOOK has to exercise: what choosePipeline() picks for a GIIntegrator
+// render of this scene. 0 = k_trace, 1 = simple kernels, 2 = small-scene tracer (launchTraceRays).
+static int hookMode(const xrtg_scene* s, uint32_t flags)
+{
+    if (!(flags & XRTG_FLAG_FAST_HOOK) || (flags & XRTG_FLAG_BRUTE_FORCE)) return 0;
+    const Pipeline P = choosePipeline(s, XRTG_INT_GI, 3, false, false);
+    if (P.fusedBounce) return 2;
+    return P.deep ? 0 : 1;
+}
+
 int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int height, int spp, const float* jitter_uv, uint32_t flags,
                        xrtg_hit* out)
 {
@@ -1007,30 +1128,55 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
     const uint32_t nPixels = uint32_t(width) * uint32_t(height);
     const uint64_t nPaths = uint64_t(nPixels) * uint64_t(spp);
     if (nPaths > (1ull << 30)) return fail(XRTG_ERR_UNSUPPORTED, "too many primary rays for one call");
-    const KernelTable& K = exactKernels(); // primary-hit parity always uses the no-FMA instantiation
-    if (int rc = ensureWorkspace(s, nPixels, uint32_t(nPaths), 1, true)) return rc;
+    const bool fastHook = (flags & XRTG_FLAG_FAST_HOOK) != 0;
+    const bool brute = (flags & XRTG_FLAG_BRUTE_FORCE) != 0;
+    const KernelTable& X = exactKernels();                    // the mt19937 jitter stream (renderer.cpp:44-47) always comes from here
+    const KernelTable& K = fastHook ? fastKernels() : X;      // default: primary-hit parity uses the no-FMA instantiation
+    if (int rc = ensureWorkspace(s, nPixels, uint32_t(nPaths), 0, 1, true)) return rc;
     if (int rc = s->jitter.ensure(sizeof(float) * 2 * nPaths)) return rc;
     DQueues q = makeQueues(s);
     cudaStream_t st = s->stream;
     DWave w{};
-    w.width = width; w.height = height; w.nPixels = nPixels; w.nPaths = uint32_t(nPaths);
+    w.width = width; w.height = height; w.nPixels = nPixels; w.pixelBase = 0; w.wavePixels = nPixels; w.nPaths = uint32_t(nPaths);
     w.samplesThisWave = uint32_t(spp); w.sampleBase = 0; w.integrator = XRTG_INT_NORMAL; w.maxDepth = 1;
+    w.sx0 = 0; w.sy0 = 0; w.sx1 = width; w.sy1 = height;
     w.mt = static_cast<uint32_t*>(s->mt.p);
     w.mti = static_cast<uint32_t*>(s->mti.p);
     float* dj = static_cast<float*>(s->jitter.p);
     if (jitter_uv) CU(cudaMemcpyAsync(dj, jitter_uv, sizeof(float) * 2 * nPaths, cudaMemcpyHostToDevice, st));
     else {
-        K.seedMt(st, w);
-        K.genJitter(st, w, spp, dj);
+        X.seedMt(st, w);
+        X.genJitter(st, w, spp, dj);
     }
     unsigned long long* dstats = static_cast<unsigned long long*>(s->stats.p);
     CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
-    K.raygen(st, makeCamera(cam), q, w, dj);
-    K.extend(st, s->ds, q, 0, 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0 ? 1 : 0, false, dstats, 16, 1, 8);
+    const float4* hitsByPath = q.hits;
+    if (fastHook && !choosePipeline(s, XRTG_INT_GI, 3, false, brute).deep) {
+        // shallow BVH: the production primary kernel (raygen fused with the bounce-0 closest hit, screen-space scissor, compact
+        // hit-only queue), fed with the supplied jitter; its queue is scattered back to one record per path
+        const Pipeline P = choosePipeline(s, XRTG_INT_GI, 3, false, brute);
+        if (P.scissor) {
+            int sc4[4];
+            computeScissor(s, cam, width, height, sc4);
+            w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
+        }
+        if (int rc = s->rayTmp[3].ensure(sizeof(float4) * nPaths)) return rc;
+        K.primary(st, s->ds, makeCamera(cam), q, w, brute, 0, false, dstats, dj);
+        K.scatterPrimaryHits(st, q, static_cast<float4*>(s->rayTmp[3].p), uint32_t(nPaths));
+        hitsByPath = static_cast<const float4*>(s->rayTmp[3].p);
+    }
+    else {
+        K.raygen(st, makeCamera(cam), q, w, dj);
+        if (fastHook) { // deep BVH: the renderer's own bounce-0 launch (k_trace on the wide tree, production refill settings)
+            const Pipeline P = choosePipeline(s, XRTG_INT_GI, 3, false, brute);
+            K.extend(st, s->ds, q, 0, 0, brute ? 1 : 0, false, dstats, P.thrExt0, P.spv, P.leafThr);
+        }
+        else K.extend(st, s->ds, q, 0, 0, brute ? 1 : 0, false, dstats, 16, 1, 8);
+    }
     CU(cudaGetLastError());
     // hits are indexed by path id = s * nPixels + pixel; the ABI wants [(pixel * spp) + s]
     std::vector<float4> tmp(nPaths);
-    CU(cudaMemcpyAsync(tmp.data(), q.hits, sizeof(float4) * nPaths, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tmp.data(), hitsByPath, sizeof(float4) * nPaths, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (uint64_t pid = 0; pid < nPaths; ++pid) {
         const uint64_t pix = pid % nPixels, k = pid / nPixels;
@@ -1052,12 +1198,8 @@ int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir
     if (n > (1ll << 30)) return fail(XRTG_ERR_UNSUPPORTED, "too many rays for one call");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
-    // the rays are staged into the renderer's own queues and traced by the renderer's own traversal kernel
-    const int shadowPerPath = s->maxShadowPerPath;
-    s->maxShadowPerPath = 1;
-    const int rc0 = ensureWorkspace(s, 1, uint32_t(n), 1, false);
-    s->maxShadowPerPath = shadowPerPath;
-    if (rc0) return rc0;
+    // the rays are staged into the renderer's own queues and traced by the renderer's own traversal kernels
+    if (int rc = ensureWorkspace(s, 1, uint32_t(n), size_t(n), 1, false)) return rc;
     if (int rc = s->rayTmp[0].ensure(sizeof(float) * 3 * size_t(n))) return rc;
     if (int rc = s->rayTmp[1].ensure(sizeof(float) * 3 * size_t(n))) return rc;
     if (int rc = s->rayTmp[2].ensure(sizeof(float) * size_t(n))) return rc;
@@ -1067,10 +1209,17 @@ int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir
     if (tmax) CU(cudaMemcpyAsync(s->rayTmp[2].p, tmax, sizeof(float) * size_t(n), cudaMemcpyHostToDevice, st));
     DQueues q = makeQueues(s);
     CU(cudaMemsetAsync(q.ctrl, 0, sizeof(uint32_t) * kCtrlStride * 3, st));
-    const KernelTable& K = exactKernels(); // parity hooks always use the no-FMA instantiation
+    // XRTG_FLAG_HOOK_SRC_PRIM: out_hits[i].prim carries, on entry, the primitive the shadow ray starts on (what the renderer
+    // knows when it traces an NEE ray); -1 everywhere otherwise
+    const bool srcPrim = any_hit && (flags & XRTG_FLAG_FAST_HOOK) && (flags & XRTG_FLAG_HOOK_SRC_PRIM);
+    if (srcPrim) CU(cudaMemcpyAsync(s->rayTmp[3].p, out_hits, sizeof(float4) * size_t(n), cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(s->rayTmp[3].p, 0xff, sizeof(float4) * size_t(n), st));
+    // default: the no-FMA instantiation through k_trace; XRTG_FLAG_FAST_HOOK: the throughput instantiation through the
+    // production entry points of this scene (hookMode)
+    const KernelTable& K = (flags & XRTG_FLAG_FAST_HOOK) ? fastKernels() : exactKernels();
     K.traceRays(st, s->ds, q, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
                 tmax ? static_cast<const float*>(s->rayTmp[2].p) : nullptr, n, any_hit != 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0,
-                static_cast<float4*>(s->rayTmp[3].p), static_cast<unsigned long long*>(s->stats.p));
+                static_cast<float4*>(s->rayTmp[3].p), static_cast<unsigned long long*>(s->stats.p), hookMode(s, flags));
     CU(cudaGetLastError());
     static_assert(sizeof(xrtg_hit) == sizeof(float4), "xrtg_hit must be 16 bytes");
     CU(cudaMemcpyAsync(out_hits, any_hit ? s->rayTmp[3].p : static_cast<void*>(q.hits), sizeof(float4) * size_t(n), cudaMemcpyDeviceToHost, st));

@@ -10,6 +10,7 @@ namespace xrt {
 enum : uint32_t {
     kMetaKindMask = 3u,      // xrtg_object_kind
     kMetaHasMaterial = 4u,
+    kMetaShadowOutside = 8u, // small scenes: shadow rays from this primitive can start behind a hull-pruned plane (api.cu)
     kMetaLightShift = 8,     // (area light index + 1) in bits 8..19
     kMetaMediumShift = 20,   // (medium index + 1) in bits 20..31
 };
@@ -48,6 +49,7 @@ struct DGrid {
 struct DScene {
     const float4* nodes;   // 4 float4 per BVH node (bvh.h: BvhNode)
     const float4* nodes4;  // deep trees only: the same tree collapsed to four children per node, 8 float4 each (bvh.h: Bvh4Node); or nullptr
+    const uint4* nodes8;   // deep trees: eight-child nodes with 8-bit quantised child boxes, 80 B = 5 uint4 each (bvh.h: Bvh8Node); or nullptr
     const float4* tris;    // 3 float4 per triangle in LEAF order: v0|prim id, e1|flags(bit0 emitter), e2|0
     const float4* tris_id; // same triangles in PRIMITIVE-ID order (brute-force parity path), mesh triangles only
     // throughput instantiation only: 4 float4 per triangle = plane-equation form (N|d, n1|d1, n2|d2, id|flags|0|0), see
@@ -88,12 +90,16 @@ struct DQueues {
 enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
 
 // device-side statistics (uint64 each)
-enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatCount };
+enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatScissored, kStatTruncated, kStatCount };
 
 struct DWave {
     int width, height;
-    uint32_t nPixels;
-    uint32_t nPaths;        // nPixels * samplesThisWave
+    uint32_t nPixels;       // pixels of the whole image (stride of the per-pixel mt19937 state)
+    // A wave covers the pixel range [pixelBase, pixelBase + wavePixels) x samplesThisWave samples: the whole image unless the
+    // per-path workspace is so large (hundreds of area lights -> shadow-queue entries per path) that one sample of every pixel
+    // would not fit the workspace budget. Path id = s * wavePixels + (pixel - pixelBase).
+    uint32_t pixelBase, wavePixels;
+    uint32_t nPaths;        // wavePixels * samplesThisWave
     uint32_t sampleBase;    // index of the first sample of this wave (sample_offset + done so far)
     uint32_t samplesThisWave;
     int integrator, maxDepth;

@@ -10,7 +10,7 @@ const KernelTable& exactKernels()
 {
     using namespace exact;
     static const KernelTable t = {launchSeedMt, launchRaygen, launchPrimary, launchExtend, launchConnect, launchShadeSurface, launchBounceSmall, launchShadeVolume, launchVolumePaths,
-                                  launchAccumulate, launchFinalize, launchTraceRays, launchGenJitter};
+                                  launchAccumulate, launchFinalize, launchTraceRays, launchScatterPrimaryHits, launchGenJitter};
     return t;
 }
 } // namespace xrt

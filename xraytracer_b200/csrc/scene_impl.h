@@ -1,0 +1,135 @@
+// scene_impl.h — internals of the xrtg_scene handle shared by api.cu (ingest, single-device render, parity hooks) and multi.cu
+// (scene replicas on several devices, the fused peer-memory reduce + finalize).
+#pragma once
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include <xrtgpu.h>
+#include "device_types.h"
+
+namespace xrt {
+
+// thread-local last-error slot behind xrtg_last_error()
+int fail(int code, const std::string& msg);
+
+#define CU(call)                                                                                                    \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess)                                                                                     \
+            return ::xrt::fail(e__ == cudaErrorMemoryAllocation ? XRTG_ERR_OOM : XRTG_ERR_CUDA,                     \
+                               std::string(#call) + ": " + cudaGetErrorString(e__));                                \
+    } while (0)
+
+// pinned host array + device mirror. A replica of a scene on another device SHARES the pinned host copy of the primary
+// (ownsHost = false) and owns only its device copy.
+struct Mirror {
+    void* h = nullptr;
+    void* d = nullptr;
+    size_t bytes = 0;
+    bool ownsHost = true;
+    int alloc(size_t n)
+    {
+        release();
+        bytes = n;
+        if (n == 0) return 0;
+        CU(cudaMallocHost(&h, n));
+        CU(cudaMalloc(&d, n));
+        return 0;
+    }
+    int mirrorOf(const Mirror& src) // device copy on the CURRENT device of src's host array
+    {
+        release();
+        bytes = src.bytes;
+        h = src.h;
+        ownsHost = false;
+        if (bytes == 0) return 0;
+        CU(cudaMalloc(&d, bytes));
+        return 0;
+    }
+    void release()
+    {
+        if (h && ownsHost) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        bytes = 0;
+        ownsHost = true;
+    }
+    ~Mirror() { release(); }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        CU(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// Development / test switches of the pipeline selection (xrtg_tuning; -1 = the measured default). None of them changes what is
+// computed, only which kernels compute it. Set with xrtg_scene_set_tuning, or once at scene creation from the XRT_TUNING
+// environment variable ("key=value,key=value"); the render path itself reads no environment variable.
+struct Tuning {
+    xrtg_tuning t;
+    bool stageDump = false;
+    Tuning() { std::memset(&t, 0xff, sizeof(t)); } // every field -1
+};
+
+} // namespace xrt
+
+struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forward-declares it inside its default-visibility region)
+    int device = 0;
+    cudaStream_t stream = nullptr; // uploads + host-buffer renders
+    // scene arrays (pinned host copy + device copy)
+    xrt::Mirror nodes, nodes4, nodes8, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
+    std::vector<std::unique_ptr<xrt::Mirror>> gridData;
+    xrt::DScene ds{};
+    xrtg_scene_info info{};
+    xrt::Tuning tuning;
+    int maxShadowPerPath = 1;
+    float boundsLo[3] = {0, 0, 0}, boundsHi[3] = {0, 0, 0}; // world bounds of every primitive (valid if hasBounds)
+    bool hasBounds = false;
+    // workspace
+    xrt::DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
+    unsigned long long* statsHost = nullptr; // pinned
+    uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
+    cudaEvent_t ev[4] = {};
+    std::vector<cudaEvent_t> stageEvents; // pairs, with COUNTERS
+    std::vector<int> stageKinds;
+    // multi-GPU (multi.cu): replicas of this scene on further devices; empty for a single-device scene. Replica 0 is `this`.
+    std::vector<xrtg_scene*> replicas;
+    cudaEvent_t doneEvent = nullptr; // recorded on `stream` when this device's share of a multi-GPU render is complete
+    cudaEvent_t pullEvent = nullptr; // ... when its slice of the fused reduce + finalize has been stored into device 0's image
+    bool peerChecked = false, peerAll = false;
+    xrt::DevBuf multiOut;            // device 0: the final image of a multi-GPU render
+    xrt::DevBuf partial;             // exportable per-pixel SUM buffer (xrtg_partial_buffer; one process per GPU + CUDA IPC)
+    std::vector<std::unique_ptr<xrt::DevBuf>> peerStage; // device 0, topologies without peer mapping: staged copies of the other sums
+
+    ~xrtg_scene();
+};
+
+namespace xrt {
+// api.cu
+int uploadAll(xrtg_scene* s);
+int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats);
+int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p);
+// multi.cu
+int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out);
+int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgbHost, xrtg_stats* stats);
+void launchReduceFinalize(cudaStream_t st, const float* const* parts, int nParts, float* out, size_t n0, size_t n1, float divisor);
+} // namespace xrt

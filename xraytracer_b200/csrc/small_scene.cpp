@@ -192,6 +192,14 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
     return 0;
 }
 
+double planeSignedDistance(const float* rec, const float* point)
+{
+    const double N[3] = {rec[0], rec[1], rec[2]};
+    const double len = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+    if (!(len > 0.0)) return 0.0;
+    return (N[0] * point[0] + N[1] * point[1] + N[2] * point[2] - double(rec[3])) / len;
+}
+
 bool planeBoundsPoints(const float* rec, const float* points, int nPoints)
 {
     const Plane p = planeOf(rec);
@@ -209,31 +217,44 @@ bool planeBoundsPoints(const float* rec, const float* points, int nPoints)
     return !(pos && neg);
 }
 
-bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints, int nHullPoints)
+bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints, int nHullPoints,
+                     std::vector<int>* pruned)
 {
     block.clear();
     if (nTris <= 0 || nTris > 64) return false;
     std::vector<Plane> planes{};
     planes.resize(size_t(nTris));
-    std::vector<int> all, occ;
+    std::vector<int> all, occ, occFull;
     SmallBlockInfo bi;
+    if (pruned) pruned->clear();
     for (int t = 0; t < nTris; ++t) {
         planes[size_t(t)] = planeOf(ftrisId + 16 * size_t(t));
         all.push_back(t);
         int flags;
         std::memcpy(&flags, ftrisId + 16 * size_t(t) + 13, 4);
         if ((flags & 1) != 0) continue; // emitter proxy: never an occluder (scene.cpp:206)
-        if (hullPoints && planeBoundsPoints(ftrisId + 16 * size_t(t), hullPoints, nHullPoints)) { ++bi.nPruned; continue; }
+        occFull.push_back(t);
+        if (hullPoints && planeBoundsPoints(ftrisId + 16 * size_t(t), hullPoints, nHullPoints)) {
+            ++bi.nPruned;
+            if (pruned) pruned->push_back(t);
+            continue;
+        }
         occ.push_back(t);
     }
     block.assign(4, 0.f);
     const size_t offAll = 1;
-    int planesOcc = 0;
+    int planesOcc = 0, recordsFull = 0;
     const size_t nAll = emitSection(ftrisId, all, planes, offAll, block, bi.nRecordsAll, bi.nPlanesAll);
     const size_t offOcc = offAll + nAll;
     const size_t nOcc = emitSection(ftrisId, occ, planes, offOcc, block, bi.nRecordsOcc, planesOcc);
-    const size_t total = offOcc + nOcc;
-    put(block, 0, asFloat(int(offAll)), asFloat(int(offOcc)), asFloat(int(total)), 0.f);
+    // third section: EVERY occluder, for shadow rays that start outside the hull (see small_scene.h); the pruned section itself
+    // when nothing was pruned
+    size_t offFull = offOcc, total = offOcc + nOcc;
+    if (bi.nPruned > 0) {
+        offFull = total;
+        total += emitSection(ftrisId, occFull, planes, offFull, block, recordsFull, planesOcc);
+    }
+    put(block, 0, asFloat(int(offAll)), asFloat(int(offOcc)), asFloat(int(total)), asFloat(int(offFull)));
     if (info) *info = bi;
     // pays only if most triangles find a coplanar partner: ~31 instructions per record (packed, two records at a time) against
     // ~33 per triangle of the plain loop

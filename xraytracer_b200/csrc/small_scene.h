@@ -3,7 +3,7 @@
 // Coplanar triangles (the two halves of every OBJ quad, the Cornell floor with both block footprints) are tested in PAIRS that
 // share ONE ray/plane intersection; each triangle then costs only its two barycentric plane equations. The block is copied
 // verbatim into shared memory by k_bounce_small (wavefront.cuh) — layout in float4 units:
-//   [0]            int4 (offAll, offOcc, totalF4, 0)
+//   [0]            int4 (offAll, offOcc, totalF4, offOccFull)
 //   section:       int4 (nRecords, nPairs, offRecords, offIds)          offsets from the start of the block
 //                  one record = a supporting plane and two triangles in it, 20 floats:
 //                      N.xyz | d ,  A: n1.xyz | d1 , n2.xyz | d2 ,  B: n1 | d1 , n2 | d2
@@ -15,7 +15,11 @@
 // Records of one plane are consecutive, carry bit-identical plane words and are in primitive-id order, so "strictly smaller t
 // wins" between records and "A before B" inside one reproduce the reference's first-wins rule for coplanar duplicates.
 // `All` holds every mesh triangle (closest hit), `Occ` only the triangles that are not emitter proxies (Scene::occluded skips
-// those, scene.cpp:206).
+// those, scene.cpp:206) and whose plane does not have the whole scene on one side (hull pruning, below), `OccFull` every
+// triangle that is not an emitter proxy: the integrators start shadow rays at hit + bias * ng with ng never flipped towards the
+// ray, so a hit on a triangle whose normal points out of the hull starts its shadow ray BEHIND a hull plane and
+// the reference lets that plane shadow it. Such primitives are flagged (kMetaShadowOutside, api.cu) and a warp with a
+// flagged lane tests the full section; `OccFull` = `Occ` when nothing was pruned.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -44,7 +48,9 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
 // closed room: the scene lies inside its half-space) can never be crossed by a segment between two such points, so it is
 // left out of the occluder section. Pass null when a light is infinitely far away (DistantLight) — its shadow rays leave the hull.
 bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints = nullptr,
-                     int nHullPoints = 0);
+                     int nHullPoints = 0, std::vector<int>* pruned = nullptr);
+// signed distance of `point` to the plane of record `rec` (16 floats), positive on the side the triangle's normal e1 x e2 points to
+double planeSignedDistance(const float* rec, const float* point);
 // true if all points lie on one closed side of the plane of record `rec` (16 floats), within 1e-5 of the points' extent
 bool planeBoundsPoints(const float* rec, const float* points, int nPoints);
 

@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cstdlib>
+#include <vector>
 #include <cuda_runtime.h>
 #include "device_types.h"
 #include <xrtgpu.h>

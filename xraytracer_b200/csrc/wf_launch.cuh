@@ -7,10 +7,11 @@
 __global__ void __launch_bounds__(kBlock) k_accumulate(DQueues q, DWave w, float* __restrict__ accum, unsigned long long* stats)
 {
     uint32_t dropped = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < w.nPixels; p += gridDim.x * blockDim.x) {
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < w.wavePixels; lp += gridDim.x * blockDim.x) {
+        const uint32_t p = w.pixelBase + lp;
         float ax = accum[3 * size_t(p)], ay = accum[3 * size_t(p) + 1], az = accum[3 * size_t(p) + 2];
         for (uint32_t s = 0; s < w.samplesThisWave; ++s) {
-            const float4 r = q.radiance[size_t(s) * w.nPixels + p];
+            const float4 r = q.radiance[size_t(s) * w.wavePixels + lp];
             if (isnan(r.x) || isnan(r.y) || isnan(r.z)) { ++dropped; continue; }
             else if (isinf(r.x) || isinf(r.y) || isinf(r.z)) { ++dropped; continue; }
             else if (r.x < 0 || r.y < 0 || r.z < 0) { ++dropped; continue; }
@@ -32,19 +33,22 @@ __global__ void __launch_bounds__(kBlock) k_finalize(const float* __restrict__ a
 // host-side launchers (called from api.cpp through the table in kernels.h)
 // ---------------------------------------------------------------------------------------------------------
 // persistent grids: (resident CTAs per SM for this kernel) x (number of SMs) — 148 on B200
+// The result depends on the kernel AND on the current device (a multi-GPU scene launches the same kernels on every device from
+// one process), so it is cached per (function, device).
 inline int gridFor(const void* fn, int block = kBlock)
 {
-    static thread_local int cachedDev = -1;
-    static thread_local int sms = 0;
+    struct Entry { const void* fn; int dev, block, grid; };
+    static thread_local std::vector<Entry> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev != cachedDev) {
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cachedDev = dev;
-    }
-    int perSm = 0;
+    for (const Entry& e : cache)
+        if (e.fn == fn && e.dev == dev && e.block == block) return e.grid;
+    int sms = 0, perSm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, block, 0);
-    return sms * (perSm < 1 ? 1 : perSm);
+    const int grid = sms * (perSm < 1 ? 1 : perSm);
+    cache.push_back(Entry{fn, dev, block, grid});
+    return grid;
 }
 
 inline void launchSeedMt(cudaStream_t st, const DWave& w)
@@ -59,28 +63,22 @@ inline void launchGenJitter(cudaStream_t st, const DWave& w, int spp, float* jit
 }
 inline void launchRaygen(cudaStream_t st, const DCamera& cam, const DQueues& q, const DWave& w, const float* jitter)
 {
-    static thread_local int grid = 0;
-    if (!grid) grid = gridFor((const void*)k_raygen);
-    k_raygen<<<grid, kBlock, 0, st>>>(cam, q, w, jitter);
+    k_raygen<<<gridFor((const void*)k_raygen), kBlock, 0, st>>>(cam, q, w, jitter);
 }
 inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam, const DQueues& q, const DWave& w, bool brute, int missMode,
-                          bool count, unsigned long long* stats)
+                          bool count, unsigned long long* stats, const float* jitter)
 {
-    static thread_local int g0 = 0, g1 = 0;
-    if (!g0) { g0 = gridFor((const void*)k_primary<false>); g1 = gridFor((const void*)k_primary<true>); }
-    if (count) k_primary<true><<<g1, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
-    else k_primary<false><<<g0, kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats);
+    if (jitter) k_primary<false, true><<<gridFor((const void*)k_primary<false, true>), kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats, jitter);
+    else if (count) k_primary<true, false><<<gridFor((const void*)k_primary<true, false>), kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats, nullptr);
+    else k_primary<false, false><<<gridFor((const void*)k_primary<false, false>), kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats, nullptr);
 }
 // k_trace instantiation for (closest / any hit, counters, two- / four-child tree)
 template <bool ANY>
 inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
                         float4* anyOut, int thr, int spv, int leafThr)
 {
-    static thread_local int g[4] = {0, 0, 0, 0};
-    if (!g[0]) {
-        g[0] = gridFor((const void*)k_trace<ANY, false, false>); g[1] = gridFor((const void*)k_trace<ANY, true, false>);
-        g[2] = gridFor((const void*)k_trace<ANY, false, true>); g[3] = gridFor((const void*)k_trace<ANY, true, true>);
-    }
+    const int g[4] = {gridFor((const void*)k_trace<ANY, false, false>), gridFor((const void*)k_trace<ANY, true, false>),
+                      gridFor((const void*)k_trace<ANY, false, true>), gridFor((const void*)k_trace<ANY, true, true>)};
     const bool wide = sc.nodes4 != nullptr;
     if (wide) {
         if (count) k_trace<ANY, true, true><<<g[3], kBlock, 0, st>>>(sc, q, src, bounce, brute, stats, anyOut, thr, spv, leafThr);
@@ -94,8 +92,7 @@ inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int
 inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
                          int thr, int spv, int leafThr)
 {
-    static thread_local int h0 = 0, h1 = 0;
-    if (!h0) { h0 = gridFor((const void*)k_extend_simple<false>); h1 = gridFor((const void*)k_extend_simple<true>); }
+    const int h0 = gridFor((const void*)k_extend_simple<false>), h1 = gridFor((const void*)k_extend_simple<true>);
     if (thr <= 0) { // shallow BVH: simple run-to-completion kernel
         if (count) k_extend_simple<true><<<h1, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
         else k_extend_simple<false><<<h0, kBlock, 0, st>>>(sc, q, src, bounce, brute, stats);
@@ -106,25 +103,21 @@ inline void launchExtend(cudaStream_t st, const DScene& sc, const DQueues& q, in
 inline void launchConnect(cudaStream_t st, const DScene& sc, const DQueues& q, int bounce, int brute, bool count, unsigned long long* stats,
                           int thr, int spv, int leafThr)
 {
-    static thread_local int h0 = 0, h1 = 0;
-    if (!h0) { h0 = gridFor((const void*)k_connect_simple<false>); h1 = gridFor((const void*)k_connect_simple<true>); }
+    const int h0 = gridFor((const void*)k_connect_simple<false>), h1 = gridFor((const void*)k_connect_simple<true>);
     if (thr <= 0) {
-        if (count) k_connect_simple<true><<<h1, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
-        else k_connect_simple<false><<<h0, kBlock, 0, st>>>(sc, q, bounce, brute, stats);
+        if (count) k_connect_simple<true><<<h1, kBlock, 0, st>>>(sc, q, bounce, brute, stats, nullptr);
+        else k_connect_simple<false><<<h0, kBlock, 0, st>>>(sc, q, bounce, brute, stats, nullptr);
         return;
     }
     launchTrace<true>(st, sc, q, 0, bounce, brute, count, stats, nullptr, thr, spv, leafThr);
 }
 inline void launchShadeSurface(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce)
 {
-    static thread_local int grid = 0;
-    if (!grid) grid = gridFor((const void*)k_shade_surface, kShadeBlock);
-    k_shade_surface<<<grid, kShadeBlock, 0, st>>>(sc, q, w, src, bounce);
+    k_shade_surface<<<gridFor((const void*)k_shade_surface, kShadeBlock), kShadeBlock, 0, st>>>(sc, q, w, src, bounce);
 }
 inline void launchBounceSmall(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, unsigned long long* stats)
 {
-    static thread_local int g0 = 0, g1 = 0;
-    if (!g0) { g0 = gridFor((const void*)k_bounce_small<false>); g1 = gridFor((const void*)k_bounce_small<true>); }
+    const int g0 = gridFor((const void*)k_bounce_small<false>), g1 = gridFor((const void*)k_bounce_small<true>);
     const bool grouped = !kExact && sc.smallBlockF4 > 0 && sc.nBoxes == 0;
     if (grouped) k_bounce_small<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
     else k_bounce_small<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, stats);
@@ -132,28 +125,19 @@ inline void launchBounceSmall(cudaStream_t st, const DScene& sc, const DQueues& 
 inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, int src, int bounce, bool brute, bool count,
                               unsigned long long* stats)
 {
-    static thread_local int g0 = 0, g1 = 0;
-    if (!g0) { g0 = gridFor((const void*)k_shade_volume<false>); g1 = gridFor((const void*)k_shade_volume<true>); }
+    const int g0 = gridFor((const void*)k_shade_volume<false>), g1 = gridFor((const void*)k_shade_volume<true>);
     if (count) k_shade_volume<true><<<g1, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
     else k_shade_volume<false><<<g0, kBlock, 0, st>>>(sc, q, w, src, bounce, brute, stats);
 }
 inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, int threshold, int stepsPerVote, bool count,
                               unsigned long long* stats)
 {
-    static thread_local int g0 = 0, g1 = 0, g2 = 0, sel = 0;
-    if (!g0) {
-        g0 = gridFor((const void*)k_volume_paths<false, 5>); g1 = gridFor((const void*)k_volume_paths<true, 4>);
-        g2 = gridFor((const void*)k_volume_paths<false, 4>);
-        const char* e = std::getenv("XRT_VOLUME_MINB");
-        sel = e ? std::atoi(e) : 4;
-    }
-    if (count) k_volume_paths<true, 4><<<g1, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
-    else if (sel == 4) k_volume_paths<false, 4><<<g2, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
-    else k_volume_paths<false, 5><<<g0, kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    if (count) k_volume_paths<true, 4><<<gridFor((const void*)k_volume_paths<true, 4>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    else k_volume_paths<false, 4><<<gridFor((const void*)k_volume_paths<false, 4>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
 }
 inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
 {
-    const int grid = int((w.nPixels + kBlock - 1) / kBlock);
+    const int grid = int((w.wavePixels + kBlock - 1) / kBlock);
     k_accumulate<<<grid, kBlock, 0, st>>>(q, w, accum, stats);
 }
 inline void launchFinalize(cudaStream_t st, const float* accum, float* out, size_t n, float divisor)
@@ -163,11 +147,40 @@ inline void launchFinalize(cudaStream_t st, const float* accum, float* out, size
 }
 // parity hook: rays go through the SAME persistent traversal kernel the renderer uses. `out` = n float4 (device):
 // closest -> the hit queue itself is returned by the caller; any hit -> occlusion flags are written to `out`.
+// mode (the production pipeline the hook should exercise, chosen by the caller exactly like renderOnStream chooses it):
+//   0 = k_trace (the resumable traversal of deep BVHs; also the classic exact-instantiation hook)
+//   1 = k_extend_simple / k_connect_simple (shallow BVHs with more than 64 triangles)
+//   2 = k_hook_small over SmallTracer (small scenes: the closest / any-hit code of k_bounce_small)
 inline void launchTraceRays(cudaStream_t st, const DScene& sc, const DQueues& q, const float* org, const float* dir, const float* tmax,
-                            long long n, bool anyhit, bool brute, float4* out, unsigned long long* stats)
+                            long long n, bool anyhit, bool brute, float4* out, unsigned long long* stats, int mode)
 {
     const int grid = int(std::min<long long>((n + kBlock - 1) / kBlock, 148 * 16));
     k_pack_rays<<<grid > 0 ? grid : 1, kBlock, 0, st>>>(q, org, dir, tmax, uint32_t(n), anyhit ? 1 : 0);
-    if (anyhit) launchTrace<true>(st, sc, q, 0, 0, brute, false, stats, out, 16, 1, 8);
+    if (mode == 2) {
+        const bool grouped = !kExact && sc.smallBlockF4 > 0 && sc.nBoxes == 0;
+        if (grouped) k_hook_small<true><<<gridFor((const void*)k_hook_small<true>), kBlock, 0, st>>>(sc, q, uint32_t(n), anyhit ? 1 : 0, out);
+        else k_hook_small<false><<<gridFor((const void*)k_hook_small<false>), kBlock, 0, st>>>(sc, q, uint32_t(n), anyhit ? 1 : 0, out);
+    }
+    else if (mode == 1) {
+        if (anyhit) k_connect_simple<false><<<gridFor((const void*)k_connect_simple<false>), kBlock, 0, st>>>(sc, q, 0, brute ? 1 : 0, stats, out);
+        else k_extend_simple<false><<<gridFor((const void*)k_extend_simple<false>), kBlock, 0, st>>>(sc, q, 0, 0, brute ? 1 : 0, stats);
+    }
+    else if (anyhit) launchTrace<true>(st, sc, q, 0, 0, brute, false, stats, out, 16, 1, 8);
     else launchTrace<false>(st, sc, q, 0, 0, brute, false, stats, nullptr, 16, 1, 8);
+}
+// parity hook: compact bounce-0 queue of k_primary -> one hit record per path id (misses: prim = -1)
+__global__ void __launch_bounds__(kBlock) k_hook_fill_miss(float4* __restrict__ out, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = make_float4(FLT_MAX, 0.f, 0.f, __int_as_float(-1));
+}
+__global__ void __launch_bounds__(kBlock) k_hook_scatter_hits(DQueues q, float4* __restrict__ out)
+{
+    const uint32_t n = q.ctrl[kCtrlRays];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[__float_as_int(q.q2[0][i].y)] = q.hits[i];
+}
+inline void launchScatterPrimaryHits(cudaStream_t st, const DQueues& q, float4* out, uint32_t nPaths)
+{
+    const int grid = int(std::min<uint32_t>((nPaths + kBlock - 1) / kBlock, 148 * 16));
+    k_hook_fill_miss<<<grid > 0 ? grid : 1, kBlock, 0, st>>>(out, nPaths);
+    k_hook_scatter_hits<<<grid > 0 ? grid : 1, kBlock, 0, st>>>(q, out);
 }

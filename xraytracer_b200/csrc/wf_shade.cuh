@@ -492,42 +492,24 @@ __device__ __forceinline__ void groupedClosest(const SmallSection& S, V3 o, V3 d
     }
 }
 
-// GROUPED: the scene carries a plane-paired block (throughput instantiation, no BoxMesh); otherwise the per-triangle lists.
+// Scene::intersect / Scene::occluded on a small scene staged in shared memory — the ONE implementation behind k_bounce_small
+// (production) and k_hook_small (parity hook xrtg_trace_rays with XRTG_FLAG_FAST_HOOK), so the hit ids the hook reports are the
+// ids the timed kernel shades. GROUPED: the scene carries a plane-paired block (throughput instantiation, no BoxMesh) and both
+// functions must be called by all 32 lanes of a converged warp (lanes without a ray pass want = false); otherwise the
+// per-triangle lists.
 template <bool GROUPED>
-__global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
-{
-    constexpr int kListF4 = GROUPED ? 1 : kTriF4 * kSmallSceneTris;
-    __shared__ float4 s_tris[kListF4];
-    __shared__ float4 s_occ[(kExact || GROUPED) ? 1 : kTriF4 * kSmallSceneTris];
-    __shared__ float4 s_block[GROUPED ? kSmallBlockF4 : 1];
-    __shared__ uint32_t s_scratch[kBlock / 32 + 1];
-    __shared__ int s_nOcc;
-    // shading records and lights of a small scene live in shared memory too: the queue traffic streams through L1 and would keep
-    // evicting them (every entry reads 4-5 of these words on its dependency chain)
-    __shared__ float4 s_prims[4 * kSmallPrims];
-    __shared__ DLight s_lights[kSmallLights];
-    for (int k = threadIdx.x; k < 4 * sc.nPrims; k += blockDim.x) s_prims[k] = sc.prims[k];
-    for (int k = threadIdx.x; k < sc.nLights * int(sizeof(DLight) / sizeof(float4)); k += blockDim.x)
-        reinterpret_cast<float4*>(s_lights)[k] = reinterpret_cast<const float4*>(sc.lights)[k];
-    SmallSection secAll{}, secOcc{};
-    const float4* occTris = nullptr;
-    int nOcc = 0;
-    if constexpr (GROUPED) {
-        for (int k = threadIdx.x; k < sc.smallBlockF4; k += blockDim.x) s_block[k] = sc.smallBlock[k];
-        __syncthreads();
-        const int4 hd = *reinterpret_cast<const int4*>(s_block);
-        secAll = smallSection(s_block, hd.x);
-        secOcc = smallSection(s_block, hd.y);
-    }
-    else {
-        stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
-        occTris = kExact ? s_tris : s_occ;
-        nOcc = s_nOcc;
-    }
-    // Scene::occluded / Scene::intersect on the staged scene. GROUPED: executed by the whole (converged) warp.
-    auto occluded = [&](bool want, V3 o, V3 d, float tmax) -> bool {
+struct SmallTracer {
+    SmallSection secAll, secOcc, secOccFull;
+    const float4* tris;    // per-triangle list, primitive-id order (closest hit)
+    const float4* occTris; // occluders (exact: the same list, emitter proxies skipped by flag)
+    int nOcc;
+    // outsideHull (GROUPED only): this lane's ray starts on a primitive flagged kMetaShadowOutside — its origin may lie behind a
+    // hull plane that was pruned from secOcc, so the whole warp tests the unpruned section for this ray batch
+    __device__ __forceinline__ bool occluded(const DScene& sc, bool want, V3 o, V3 d, float tmax, bool outsideHull = false) const
+    {
         if constexpr (GROUPED) {
-            bool occ = groupedAnyHit(secOcc, o, d, want ? tmax : -1.f);
+            const bool full = __any_sync(0xffffffffu, want && outsideHull);
+            bool occ = groupedAnyHit(full ? secOccFull : secOcc, o, d, want ? tmax : -1.f);
             if (want && !occ)
                 for (int k = 0; k < sc.nSpheres; ++k) {
                     const float4 cr = __ldg(sc.spheres + 2 * k);
@@ -538,8 +520,9 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
             return occ;
         }
         else return want && anyHitSmall(sc, o, d, tmax, occTris, nOcc);
-    };
-    auto closest = [&](bool want, V3 o, V3 d, Hit& h) {
+    }
+    __device__ __forceinline__ void closest(const DScene& sc, bool want, V3 o, V3 d, Hit& h) const
+    {
         if constexpr (GROUPED) {
             h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
             groupedClosest(secAll, o, d, want, h);
@@ -554,9 +537,77 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         }
         else if (want) {
             TraceCounters tc;
-            closestHit<false, true>(sc, o, d, false, h, nullptr, tc, s_tris);
+            closestHit<false, true>(sc, o, d, false, h, nullptr, tc, tris);
         }
-    };
+    }
+};
+// Copies the scene's triangles (plane-paired block or per-triangle lists) into the CTA's shared memory; ends with a barrier.
+template <bool GROUPED>
+__device__ __forceinline__ SmallTracer<GROUPED> stageSmallTracer(const DScene& sc)
+{
+    constexpr int kListF4 = GROUPED ? 1 : kTriF4 * kSmallSceneTris;
+    __shared__ float4 s_tris[kListF4];
+    __shared__ float4 s_occ[(kExact || GROUPED) ? 1 : kTriF4 * kSmallSceneTris];
+    __shared__ float4 s_block[GROUPED ? kSmallBlockF4 : 1];
+    __shared__ int s_nOcc;
+    SmallTracer<GROUPED> tr{};
+    if constexpr (GROUPED) {
+        for (int k = threadIdx.x; k < sc.smallBlockF4; k += blockDim.x) s_block[k] = sc.smallBlock[k];
+        __syncthreads();
+        const int4 hd = *reinterpret_cast<const int4*>(s_block);
+        tr.secAll = smallSection(s_block, hd.x);
+        tr.secOcc = smallSection(s_block, hd.y);
+        tr.secOccFull = smallSection(s_block, hd.w);
+    }
+    else {
+        stageSmallScene(sc, s_tris, s_occ, &s_nOcc);
+        tr.tris = s_tris;
+        tr.occTris = kExact ? s_tris : s_occ;
+        tr.nOcc = s_nOcc;
+    }
+    return tr;
+}
+
+// Parity hook (xrtg_trace_rays + XRTG_FLAG_FAST_HOOK on a small scene): caller-supplied rays through the SAME SmallTracer the
+// fused bounce kernel uses. Closest hit: rays in q.q0[0] / q.q1[0] -> q.hits; any hit: q.s0 (origin | tmax) / q.s1 -> out[i].w.
+template <bool GROUPED>
+__global__ void __launch_bounds__(kBlock) k_hook_small(DScene sc, DQueues q, uint32_t n, int anyhit, float4* __restrict__ out)
+{
+    const SmallTracer<GROUPED> tr = stageSmallTracer<GROUPED>(sc);
+    for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x) {
+        const uint32_t i = tile * kBlock + threadIdx.x;
+        const bool live = i < n;
+        const float4 a = live ? (anyhit ? q.s0[i] : q.q0[0][i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = live ? (anyhit ? q.s1[i] : q.q1[0][i]) : make_float4(0.f, 0.f, 1.f, 0.f);
+        if (anyhit) {
+            // out[i].w holds the primitive the ray starts on (or -1): the renderer's flag for origins behind a pruned hull plane
+            const int srcPrim = live ? __float_as_int(out[i].w) : -1;
+            const bool outside = srcPrim >= 0 && srcPrim < sc.nPrims && (__float_as_uint(__ldg(sc.prims + 4 * srcPrim + 3).w) & kMetaShadowOutside) != 0;
+            const bool occ = tr.occluded(sc, live, xyz(a), xyz(b), a.w, outside);
+            if (live) out[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(occ ? 1 : 0));
+        }
+        else {
+            Hit h{FLT_MAX, 0.f, 0.f, -1};
+            tr.closest(sc, live, xyz(a), xyz(b), h);
+            if (live) q.hits[i] = make_float4(h.prim >= 0 ? h.t : FLT_MAX, h.u, h.v, __int_as_float(h.prim));
+        }
+    }
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q, DWave w, int src, int bounce, unsigned long long* stats)
+{
+    __shared__ uint32_t s_scratch[kBlock / 32 + 1];
+    // shading records and lights of a small scene live in shared memory too: the queue traffic streams through L1 and would keep
+    // evicting them (every entry reads 4-5 of these words on its dependency chain)
+    __shared__ float4 s_prims[4 * kSmallPrims];
+    __shared__ DLight s_lights[kSmallLights];
+    for (int k = threadIdx.x; k < 4 * sc.nPrims; k += blockDim.x) s_prims[k] = sc.prims[k];
+    for (int k = threadIdx.x; k < sc.nLights * int(sizeof(DLight) / sizeof(float4)); k += blockDim.x)
+        reinterpret_cast<float4*>(s_lights)[k] = reinterpret_cast<const float4*>(sc.lights)[k];
+    const SmallTracer<GROUPED> tracer = stageSmallTracer<GROUPED>(sc);
+    auto occluded = [&](bool want, V3 o, V3 d, float tmax, bool outsideHull) -> bool { return tracer.occluded(sc, want, o, d, tmax, outsideHull); };
+    auto closest = [&](bool want, V3 o, V3 d, Hit& h) { tracer.closest(sc, want, o, d, h); };
 
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
@@ -646,7 +697,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
                     }
                 }
                 const float bias = 0.01f;
-                if (!occluded(want, s.pos + s.ng * bias, wi, tmax - bias) && want) add(c);
+                if (!occluded(want, s.pos + s.ng * bias, wi, tmax - bias, (s.meta & kMetaShadowOutside) != 0) && want) add(c);
             }
         }
         // ---- Whitted diffuse term over delta lights (integrator.h:328-343; light.cpp:120-142) ----
@@ -666,7 +717,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
                     c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
                     ++nShadow;
                 }
-                if (!occluded(shadeDelta, s.pos + s.ng * float(0.1), wi, tmax) && shadeDelta) add(c);
+                if (!occluded(shadeDelta, s.pos + s.ng * float(0.1), wi, tmax, (s.meta & kMetaShadowOutside) != 0) && shadeDelta) add(c);
             }
         }
         // ---- phase 3: BSDF bounce (integrator.h:271-283), then intersect + RR + emitter test of depth+1 (integrator.h:214-245) ----

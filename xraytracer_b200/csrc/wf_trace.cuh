@@ -36,13 +36,13 @@ __device__ __forceinline__ void cameraRay(const DCamera& c, float u, float v, V3
     o = mk(m[12], m[13], m[14]);
 }
 
-// path id = s * nPixels + pixel, so consecutive threads own consecutive pixels of the same sample.
+// path id = s * wavePixels + (pixel - pixelBase), so consecutive threads own consecutive pixels of the same sample.
 // jitter (optional, device): [(pixel * spp + s) * 2] floats supplied by the parity hook.
 __global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DQueues q, DWave w, const float* __restrict__ jitter)
 {
     const uint32_t n = w.nPaths;
     for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n; pid += gridDim.x * blockDim.x) {
-        const uint32_t pix = pid % w.nPixels, s = pid / w.nPixels;
+        const uint32_t pix = w.pixelBase + pid % w.wavePixels, s = pid / w.wavePixels;
         const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
         float r0, r1;
         uint32_t ctr = 0;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kBlock) k_extend_simple(DScene sc, DQueues q, 
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q, int bounce, int brute, unsigned long long* stats)
+__global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q, int bounce, int brute, unsigned long long* stats, float4* anyOut)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
     __shared__ float4 s_tris[kTriF4 * kSmallSceneTris];
@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q,
         if (i < n) {
             const float4 s0 = q.s0[i], s1 = q.s1[i];
             const bool occ = anyHit<COUNT>(sc, xyz(s0), xyz(s1), s0.w, brute == 1, s_stack + threadIdx.x, tc, smallTris);
-            if (!occ) {
+            if (anyOut) anyOut[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(occ ? 1 : 0)); // parity hook: the flag, no contribution
+            else if (!occ) {
                 const float4 c = q.s2[i];
                 float* r = reinterpret_cast<float*>(q.radiance + __float_as_int(s1.w));
                 atomicAdd(r + 0, c.x); atomicAdd(r + 1, c.y); atomicAdd(r + 2, c.z);
@@ -475,27 +476,37 @@ __device__ __forceinline__ void blockAppend2(uint32_t* counter, bool wantA, bool
 // hits — ray + hit record — to a COMPACT bounce-0 queue (one atomic per CTA per 128 rays). It also initialises the
 // per-path radiance. Static tile partition: CTA b owns path ids [128 b, 128 b + 128), b += grid.
 // ---------------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQueues q, DWave w, int brute, int missMode, unsigned long long* stats)
+// JITTER: the two primary-sample offsets come from `jitter` (parity hook xrtg_trace_primary) instead of the path's RNG — the only
+// difference between the hook's instantiation and the production one.
+template <bool COUNT, bool JITTER>
+__global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQueues q, DWave w, int brute, int missMode, unsigned long long* stats,
+                                                     const float* __restrict__ jitter)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
     __shared__ uint32_t s_scratch[kBlock / 32 + 1];
     const uint32_t n = w.nPaths;
     TraceCounters tc;
-    uint32_t nHits = 0;
+    uint32_t nHits = 0, nScissored = 0;
     // one path: ray generation, scissor, closest hit; misses are resolved here
     auto path = [&](uint32_t pid, V3& d, Hit& h, uint32_t& ctr) -> bool {
         if (pid >= n) return false;
-        const uint32_t pix = pid % w.nPixels;
+        const uint32_t pix = w.pixelBase + pid % w.wavePixels;
         const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
         const bool inView = int(j) >= w.sx0 && int(j) < w.sx1 && int(i) >= w.sy0 && int(i) < w.sy1;
         bool hit = false;
         if (inView) { // (outside: the pixel cannot see the scene's bounding box, every sample is a miss, no ray needed)
-            Rng rng;
-            rng.open(w, pid, 0);
-            const float r0 = rng.next();
-            const float r1 = rng.next();
-            ctr = rng.close();
+            float r0, r1;
+            if constexpr (JITTER) { // parity hook (xrtg_trace_primary): caller-supplied jitter, laid out [(pixel * spp + s) * 2]
+                const size_t k = (size_t(pix) * w.samplesThisWave + pid / w.wavePixels) * 2;
+                r0 = jitter[k]; r1 = jitter[k + 1];
+            }
+            else {
+                Rng rng;
+                rng.open(w, pid, 0);
+                r0 = rng.next();
+                r1 = rng.next();
+                ctr = rng.close();
+            }
             const float u = (float(j) + r0) / float(uint32_t(w.width));
             const float v = (float(i) + r1) / float(uint32_t(w.height));
             V3 o;
@@ -503,6 +514,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
             closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
             hit = h.prim >= 0;
         }
+        else ++nScissored;
         V3 c = mk(0.f);
         if (!hit) {
             if (missMode == 1) c = mk(float(0.18));
@@ -534,5 +546,6 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
     statAdd(stats, kStatPrimaryHits, nHits);
+    statAdd(stats, kStatScissored, nScissored); // reference-equivalent rays that were never traced
     if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
 }

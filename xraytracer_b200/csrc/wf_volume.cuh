@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
     const uint32_t n = ctrl[kCtrlRays];
     const bool nee = (w.integrator == XRTG_INT_VOLUME_NEE);
     const uint32_t lane = laneId();
-    uint32_t steps = 0, nClosest = 0;
+    uint32_t steps = 0, nClosest = 0, nTruncated = 0;
     TraceCounters tc;
     // per-lane path state
     int state = kLaneIdle, depth = 0, it = 0, mi = -1, walkEnd = kTrackContinue;
@@ -456,6 +456,9 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
             const bool cont = volumePost<COUNT>(sc, w, media, nee, brute != 0, d, T, mi, r, depth, rng, s_stack + threadIdx.x, tc, steps, nClosest, no, nd,
                                                 nT, hasContrib, contrib);
             if (hasContrib) add(contrib);
+            // maxIter bounds the medium crossings of one path (4 * maxDepth + 8): the reference's loop (integrator.h:418) has no
+            // such bound, so a cut path is COUNTED (xrtg_stats.truncated_paths) instead of disappearing silently
+            if (cont && it + 1 == maxIter) ++nTruncated;
             if (!cont || ++it == maxIter) finish();
             else {
                 o = no; d = nd; T = nT;
@@ -517,5 +520,6 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
     }
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatSteps, steps);
+    statAdd(stats, kStatTruncated, nTruncated);
     if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
 }

@@ -11,7 +11,7 @@
  *                                                               camera.h:49-60, scene.cpp:190-200
  *   xrtg_trace_rays       <- Scene::intersect / Scene::occluded  scene.cpp:190-211
  *   xrtg_image_to_u8      <- Image::gammaCorrection + writePPM / writeMat quantisation   image.h:80-136
- *   xrtg_scene_create_multi, xrtg_reduce_finalize, xrtg_partial_buffer, xrtg_ipc_*
+ *   xrtg_scene_create_multi, xrtg_reduce_finalize, xrtg_exchange_buffer, xrtg_ipc_*
  *                         <- the "one renderer, every core" role of ParallelRenderer::render (renderer.cpp:83-99) scaled to
  *                            several GPUs: samples split across devices, `image /= n_samples` (renderer.cpp:98) fused into the
  *                            peer-memory reduction of the per-device sums
@@ -322,8 +322,10 @@ int xrtg_scene_device_count(const xrtg_scene* scene);
 int xrtg_scene_set_tuning(xrtg_scene* scene, const xrtg_tuning* tuning);
 
 /* ---- one process per GPU (torchrun / MPI style deployments): the same fused reduce + finalize over CUDA IPC ------------- */
-/* The scene's exportable per-pixel SUM buffer (width*height*3 floats, plain cudaMalloc on the scene's device). */
-int xrtg_partial_buffer(xrtg_scene* scene, int width, int height, float** device_ptr);
+/* An exportable device buffer owned by the scene (plain cudaMalloc on the scene's device, so that cudaIpcGetMemHandle applies to
+ * it; the pointer stays valid until a larger size is requested for the same slot or the scene is destroyed). Slot 0..3; by
+ * convention slot 0 holds the rank's per-pixel SUM and slot 1, on the root rank, the final image. */
+int xrtg_exchange_buffer(xrtg_scene* scene, int slot, size_t bytes, void** device_ptr);
 #define XRTG_IPC_HANDLE_BYTES 64
 int xrtg_ipc_export(const void* device_ptr, unsigned char handle[XRTG_IPC_HANDLE_BYTES]);
 /* Maps a buffer exported by another process on another (peer-accessible) device into this process. */

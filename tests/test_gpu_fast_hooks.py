@@ -65,8 +65,10 @@ def check_closest(fast, ref, what, rate=RATE, sphere_prims=(), rays=None, verts=
         with np.errstate(invalid="ignore", divide="ignore"):
             cosang = np.abs(np.einsum("ij,ij->i", n, rays[1][both])) / np.linalg.norm(n, axis=1)
         cosang = np.where(np.isfinite(cosang), cosang, 1.0)
-        err = dt * cosang / np.maximum(ref["t"][both], 1.0)
-        assert err.max(initial=0.0) < 2e-5, f"{what}: hit points of agreeing hits differ by {err.max()} (relative, across the surface)"
+        # ... to a few ulps of the coordinates involved (origin up to 750 units from the world origin, hits up to ~1500 away)
+        scale = np.maximum(np.maximum(np.abs(rays[0][both]).max(axis=1), ref["t"][both]), 1.0)
+        err = dt * cosang / scale
+        assert err.max(initial=0.0) < 4e-6, f"{what}: hit points of agreeing hits differ by {err.max()} (across the surface, relative to the coordinates)"
     else:
         rel_t = dt / np.maximum(ref["t"][both], 1e-3)
         assert np.quantile(rel_t, 0.9999) < 2e-5 and rel_t.max(initial=0.0) < 2e-3, f"{what}: t of agreeing hits differs by {rel_t.max()}"

@@ -135,3 +135,51 @@ def test_degenerate_views():
     a, _ = gpu.render(scenes.make_camera(96, 54), 96, 54, 6, capi.INT_GI, 3, seed=5, samples_per_wave=1)
     b, _ = gpu.render(scenes.make_camera(96, 54), 96, 54, 6, capi.INT_GI, 3, seed=5, samples_per_wave=4)
     assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_hundreds_of_area_lights_render_in_budgeted_waves():
+    """An emissive mesh = one TriangleLight per triangle. The three-kernel pipeline queues one shadow ray per (path, light): the
+    wave size follows a byte budget (and shrinks to ranges of pixels when even one sample of every pixel does not fit) instead
+    of the allocation failing. Same image whatever the budget; exact mode still reproduces the oracle."""
+    require_gpu()
+    s = scenes.HostScene()
+    s.add_mesh("floor", np.array(_quad((0, 0, 0), (0, 0, 100), (100, 0, 0))), (0.7, 0.7, 0.7))
+    s.add_mesh("slab", np.array(_quad((30, 20, 30), (0, 0, 30), (30, 0, 0))), (0.3, 0.6, 0.9))
+    n_lights = 0
+    for k in range(12):
+        for j in range(12):
+            x, z = 8.0 * k + 2.0, 8.0 * j + 2.0
+            s.add_triangle_light(f"L{k}_{j}", (x + 4.0, 60.0, z), (x, 60.0, z + 4.0), (x, 60.0, z), (30.0, 30.0, 30.0))   # faces down
+            n_lights += 1
+    desc = s.flatten()
+    gpu, orc = api.GpuScene(desc, 0), api.OracleScene(desc)
+    W, H = 96, 72
+    cam = scenes.make_camera(W, H, [-1, 0, 0, 0, 0, 0.8, 0.6, 0, 0, 0.6, -0.8, 0, 50.0, 70.0, -60.0, 1], 60.0)
+    a, sa = gpu.render(cam, W, H, 2, capi.INT_GI, 2, flags=capi.FLAG_EXACT)
+    b, _, sb = orc.render(cam, W, H, 2, capi.INT_GI, 2)
+    assert sa["shadow_rays"] == sb["shadow_rays"] > W * H * n_lights // 8
+    assert np.abs(a - b).max() <= 5e-5 * max(1.0, float(np.abs(b).max()))
+    base, s0 = gpu.render(cam, W, H, 8, capi.INT_GI, 2, seed=4)
+    for mb in (64, 4, 1):   # 4 MB / 1 MB: not even one sample of every pixel fits -> pixel-tiled waves
+        gpu.set_tuning(workspace_mb=mb)
+        alt, s1 = gpu.render(cam, W, H, 8, capi.INT_GI, 2, seed=4)
+        assert s1["shadow_rays"] == s0["shadow_rays"] and s1["closest_rays"] == s0["closest_rays"]
+        assert np.allclose(alt, base, rtol=2e-5, atol=1e-5), mb     # (shadow contributions are added with float atomics)
+        if mb <= 4:
+            assert s1["kernel_launches"] > s0["kernel_launches"]
+    gpu.set_tuning()
+    e, _ = gpu.render(cam, W, H, 2, capi.INT_DIRECT, 1, flags=capi.FLAG_EXACT)
+    gpu.set_tuning(workspace_mb=1)
+    e2, _ = gpu.render(cam, W, H, 2, capi.INT_DIRECT, 1, flags=capi.FLAG_EXACT)   # exact mode, pixel-tiled
+    assert np.allclose(e, e2, rtol=1e-5, atol=1e-6)
+
+
+def test_render_u8_keeps_the_float_image_on_the_device(cornell_scene=None):
+    require_gpu()
+    host = scenes.cornell_box("quad")
+    gpu = api.GpuScene(host.flatten(), 0)
+    cam = scenes.make_camera(96, 64)
+    img, _ = gpu.render(cam, 96, 64, 16, capi.INT_GI, 3, seed=1)
+    for gamma, bgr in ((0.0, False), (1.2, True)):
+        u8, st = gpu.render_u8(cam, 96, 64, 16, capi.INT_GI, 3, gamma=gamma, bgr=bgr, seed=1)
+        assert np.array_equal(u8, api.image_to_u8(img, gamma, bgr)) and st["samples"] == 96 * 64 * 16

@@ -109,3 +109,32 @@ def test_displaced_sphere_generator_is_deterministic():
     a = scenes.displaced_sphere_tris((0, 0, 0), 1.0, 12, 16)
     b = scenes.displaced_sphere_tris((0, 0, 0), 1.0, 12, 16)
     assert a.shape == (2 * 12 * 16, 18) and np.array_equal(a, b) and np.isfinite(a).all()
+
+
+def test_pure_python_scene_description_equals_host_scene():
+    """xraytracer_b200/flatdesc.py restates the benchmark scenes without libxrthost.so (the CPU reference arm of bench.py must not
+    map product libraries). Through the compiled reference both descriptions must render the very same image: the checker
+    re-inserts the objects in insertion order into the reference's own map, so ids, tie-breaks and sample streams agree."""
+    import numpy as np
+    from xraytracer_b200 import api, capi, flatdesc, scenes
+    if not capi.have_reference():
+        pytest.skip("oracle/_ref/libxrtref.so not built")
+    W, H = 48, 36
+    cam_h = scenes.make_camera(W, H)
+    cam_f = flatdesc.make_camera(W, H, scenes.CORNELL_C2W, scenes.CORNELL_FOV)
+    assert list(cam_h.c2w) == list(cam_f.c2w) and cam_h.scale == cam_f.scale and cam_h.aspect == cam_f.aspect
+    host = scenes.cornell_box("quad")
+    flat = flatdesc.cornell_box()
+    a, _, _ = api.ReferenceScene(host.flatten()).render(cam_h, W, H, 4, capi.INT_GI, 3)
+    b, _, _ = api.ReferenceScene(flat.desc()).render(cam_f, W, H, 4, capi.INT_GI, 3)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    hv = scenes.volume_scene(n=24)
+    fv = flatdesc.volume_scene(n=24)
+    a, _, _ = api.ReferenceScene(hv.flatten()).render(cam_h, W, H, 4, capi.INT_VOLUME, 8)
+    b, _, _ = api.ReferenceScene(fv.desc()).render(cam_f, W, H, 4, capi.INT_VOLUME, 8)
+    assert a.max() > 0 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    hm = scenes.cornell_mesh_scene(12, 12)
+    fm = flatdesc.cornell_mesh_scene(12, 12)
+    a, _, _ = api.ReferenceScene(hm.flatten()).render(cam_h, W, H, 2, capi.INT_GI, 3)
+    b, _, _ = api.ReferenceScene(fm.desc()).render(cam_f, W, H, 2, capi.INT_GI, 3)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -62,10 +62,11 @@ class GpuScene:
     def device_count(self) -> int:
         return self.lib.xrtg_scene_device_count(self.h)
 
-    def partial_buffer(self, width, height) -> int:
-        """Device pointer of the scene's exportable per-pixel SUM buffer (one process per GPU + CUDA IPC)."""
+    def exchange_buffer(self, slot: int, nbytes: int) -> int:
+        """Device pointer of an exportable scene-owned buffer (one process per GPU + CUDA IPC): slot 0 = per-pixel SUM,
+        slot 1 = the final image on the root rank."""
         p = C.c_void_p()
-        self._chk(self.lib.xrtg_partial_buffer(self.h, width, height, C.byref(p)), "xrtg_partial_buffer")
+        self._chk(self.lib.xrtg_exchange_buffer(self.h, slot, nbytes, C.byref(p)), "xrtg_exchange_buffer")
         return p.value
 
     def ipc_export(self, device_ptr: int) -> bytes:

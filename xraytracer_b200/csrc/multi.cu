@@ -130,7 +130,7 @@ static bool enablePeerAccess(xrtg_scene* s)
     bool all = true;
     for (xrtg_scene* a : s->replicas)
         for (xrtg_scene* b : s->replicas) {
-            if (a == b) continue;
+            if (a == b || a->device == b->device) continue; // (one device listed twice: plain local memory)
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, a->device, b->device) != cudaSuccess || !can) { all = false; continue; }
             cudaSetDevice(a->device);
@@ -264,7 +264,8 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
     for (int g = 0; g < ngpus; ++g) {
         const int d = devices ? devices[g] : g;
         if (d < 0 || d >= have) return fail(XRTG_ERR_INVALID, "device index " + std::to_string(d) + " out of range (" + std::to_string(have) + " visible)");
-        if (std::find(devs.begin(), devs.end(), d) != devs.end()) return fail(XRTG_ERR_INVALID, "device listed twice");
+        // (a device may be listed more than once: two replicas then share it — useful on a one-GPU box to exercise the very same
+        //  split + fused reduce a multi-GPU box runs)
         devs.push_back(d);
     }
     xrtg_scene* primary = nullptr;
@@ -281,12 +282,12 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
     return 0;
 }
 
-int xrtg_partial_buffer(xrtg_scene* s, int width, int height, float** device_ptr)
+int xrtg_exchange_buffer(xrtg_scene* s, int slot, size_t bytes, void** device_ptr)
 {
-    if (!s || !device_ptr || width <= 0 || height <= 0) return fail(XRTG_ERR_INVALID, "bad argument");
+    if (!s || !device_ptr || slot < 0 || slot >= 4 || bytes == 0) return fail(XRTG_ERR_INVALID, "bad argument");
     CU(cudaSetDevice(s->device));
-    if (int rc = s->partial.ensure(sizeof(float) * 3 * size_t(width) * size_t(height))) return rc;
-    *device_ptr = static_cast<float*>(s->partial.p);
+    if (int rc = s->exchange[slot].ensure(bytes)) return rc;
+    *device_ptr = s->exchange[slot].p;
     return 0;
 }
 

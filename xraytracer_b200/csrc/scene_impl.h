@@ -117,7 +117,7 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     cudaEvent_t pullEvent = nullptr; // ... when its slice of the fused reduce + finalize has been stored into device 0's image
     bool peerChecked = false, peerAll = false;
     xrt::DevBuf multiOut;            // device 0: the final image of a multi-GPU render
-    xrt::DevBuf partial;             // exportable per-pixel SUM buffer (xrtg_partial_buffer; one process per GPU + CUDA IPC)
+    xrt::DevBuf exchange[4];         // exportable buffers (xrtg_exchange_buffer; one process per GPU + CUDA IPC)
     std::vector<std::unique_ptr<xrt::DevBuf>> peerStage; // device 0, topologies without peer mapping: staged copies of the other sums
 
     ~xrtg_scene();

@@ -48,7 +48,7 @@ class GpuScene:
             ids = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
             arr = (C.c_int * len(ids))(*ids)
             rc = self.lib.xrtg_scene_create_multi(desc, len(ids), arr, build_flags, C.byref(h))
-            device = ids[0]
+            device = ids[0] if ids else 0
         if rc != 0:
             raise RuntimeError(f"xrtg_scene_create failed ({rc}): {self.lib.xrtg_last_error().decode()}")
         self.h = h

@@ -220,22 +220,26 @@ def test_full_size_mesh_bvh_matches_brute_force():
 
 # ---- converged images, counter RNG (the throughput path) vs the reference's estimator ---------------------------------
 
-@pytest.mark.parametrize("light,integ,depth,bound", [
-    ("quad", capi.INT_DIRECT, 1, 0.03), ("triangle", capi.INT_DIRECT, 1, 0.04), ("sphere", capi.INT_DIRECT, 1, 0.03),
-    ("quad", capi.INT_GI, 3, 0.06), ("quad", capi.INT_INDIRECT, 3, 0.25)])
-def test_converged_images_match_reference_estimator(light, integ, depth, bound):
-    """Relative RMSE between two independent Monte-Carlo estimates (GPU counter RNG, 1024 spp vs oracle mt19937, 256 spp)
-    of the same image; the bound is the noise floor of the 256-spp oracle image (measured ~half the bound)."""
+@pytest.mark.parametrize("light,integ,depth,gpu_spp,bound", [
+    ("quad", capi.INT_DIRECT, 1, 16384, 0.012), ("triangle", capi.INT_DIRECT, 1, 16384, 0.016), ("sphere", capi.INT_DIRECT, 1, 16384, 0.012),
+    ("quad", capi.INT_GI, 3, 16384, 0.025), ("quad", capi.INT_INDIRECT, 3, 65536, 0.09)])
+def test_converged_images_match_reference_estimator(light, integ, depth, gpu_spp, bound):
+    """The throughput path (counter RNG, plane-paired records, fused bounce kernel) against the reference's estimator: two
+    independent Monte-Carlo estimates of the same image, GPU at 16 k / 64 k spp, oracle (mt19937) at 2048 spp. The image MEAN must
+    agree within 0.5 % (a 1 % energy bias anywhere in the fast path fails); the per-pixel relative RMSE bound is the noise floor
+    of the 2048-spp oracle image (measured values are printed; the bound is ~1.7x the measurement)."""
     require_gpu()
     s = scenes.cornell_box(light)
     desc = s.flatten()
     W, H = 96, 54
     cam = scenes.make_camera(W, H)
     gpu, orc = api.GpuScene(desc, 0), api.OracleScene(desc)
-    a, _ = gpu.render(cam, W, H, 1024, integ, depth, seed=5)
-    b, _, _ = orc.render(cam, W, H, 256, integ, depth)
-    assert rel_rmse(a, b) < bound
-    assert abs(float(a.mean()) - float(b.mean())) < 0.02 * float(b.mean())
+    a, _ = gpu.render(cam, W, H, gpu_spp, integ, depth, seed=5)
+    b, _, _ = orc.render(cam, W, H, 2048, integ, depth)
+    rr, dm = rel_rmse(a, b), abs(float(a.mean()) - float(b.mean())) / float(b.mean())
+    print(f"{light} {capi.INTEGRATOR_NAMES[integ]}: relRMSE {rr:.4f} (bound {bound}), mean differs by {100 * dm:.3f} % (bound 0.5 %)")
+    assert rr < bound
+    assert dm < 0.005
 
 
 def test_converged_volume_matches_reference_estimator():
@@ -244,10 +248,12 @@ def test_converged_volume_matches_reference_estimator():
     desc = host.flatten()
     gpu, orc = api.GpuScene(desc, 0), api.OracleScene(desc)
     for integ in (capi.INT_VOLUME, capi.INT_VOLUME_NEE):
-        a, _ = gpu.render(cam, 32, 32, 4096, integ, 16, seed=2)
-        b, _, _ = orc.render(cam, 32, 32, 1024, integ, 16)
-        assert abs(float(a.mean()) - float(b.mean())) < 0.03 * float(b.mean()), integ
-        assert rel_rmse(a, b) < 0.2, integ
+        a, _ = gpu.render(cam, 32, 32, 65536, integ, 16, seed=2)
+        b, _, _ = orc.render(cam, 32, 32, 16384, integ, 16)
+        rr, dm = rel_rmse(a, b), abs(float(a.mean()) - float(b.mean())) / float(b.mean())
+        print(f"hetero {capi.INTEGRATOR_NAMES[integ]}: relRMSE {rr:.4f}, mean differs by {100 * dm:.3f} %")
+        assert dm < 0.005, integ
+        assert rr < 0.06, integ
 
 
 def test_volume_large_wave_with_mostly_missing_rays():

@@ -27,7 +27,10 @@ protected:
 };
 
 struct GpuOptions {
-    int device = 0;
+    int device = 0;          // first device
+    int ngpus = 1;           // devices device .. device+ngpus-1 behind one handle: the samples of a render() are split across them and
+                             // the per-device sums meet in one fused peer-memory reduce + `image /= spp` kernel (xrtg_scene_create_multi);
+                             // 0 = every visible device. Exact renders (one mt19937 stream per pixel) stay on the first device.
     uint32_t seed = 0;       // counter-RNG seed
     bool exact = false;      // reproduce the reference's per-pixel mt19937 sample stream (slow, for parity)
     bool counters = false;   // collect BVH node / triangle / tracking-step counters

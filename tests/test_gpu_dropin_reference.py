@@ -30,8 +30,8 @@ def test_gpu_renderer_beside_the_reference_cpu_renderer_on_one_reference_scene()
             assert np.array_equal(bits(cpu), bits(gpu)), capi.INTEGRATOR_NAMES[integ]
         else:
             assert np.abs(cpu - gpu).max() < 2e-5, capi.INTEGRATOR_NAMES[integ]
-    fast = ref.render_gpu(cam, W, H, 1024, capi.INT_GI, 3, seed=3)               # throughput path, same Scene object
-    conv, _, _ = ref.render(cam, W, H, 64, capi.INT_GI, 3)
+    fast = ref.render_gpu(cam, W, H, 8192, capi.INT_GI, 3, seed=3)               # throughput path, same Scene object
+    conv, _, _ = ref.render(cam, W, H, 1024, capi.INT_GI, 3)
     assert abs(float(fast.mean()) - float(conv.mean())) < 0.005 * float(conv.mean())
 
 

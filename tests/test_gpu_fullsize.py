@@ -120,9 +120,9 @@ def test_c4_gi_1m_triangles_fast_pipeline_vs_exact_and_oracle():
     d2 = mid.flatten()
     g2, o2 = api.GpuScene(d2, 0), api.OracleScene(d2)
     assert g2.info()["n_bvh_nodes"] > 512
-    cam2 = scenes.make_camera(64, 36)
-    a, _ = g2.render(cam2, 64, 36, 8192, capi.INT_GI, 3, seed=3)
-    b, _, _ = o2.render(cam2, 64, 36, 512, capi.INT_GI, 3)
+    cam2 = scenes.make_camera(48, 27)
+    a, _ = g2.render(cam2, 48, 27, 32768, capi.INT_GI, 3, seed=3)
+    b, _, _ = o2.render(cam2, 48, 27, 4096, capi.INT_GI, 3)
     dm2, rr2 = abs(float(a.mean()) - float(b.mean())) / float(b.mean()), rel_rmse(a, b)
-    print(f"3.2k triangles 64x36: fast (8192 spp) vs oracle (512 spp) mean differs by {100 * dm2:.3f} %, relRMSE {rr2:.4f}")
-    assert dm2 < 0.005 and rr2 < 0.05
+    print(f"3.2k triangles 48x27: fast (32768 spp) vs oracle (4096 spp) mean differs by {100 * dm2:.3f} %, relRMSE {rr2:.4f}")
+    assert dm2 < 0.005 and rr2 < 0.02

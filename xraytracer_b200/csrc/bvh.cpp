@@ -212,6 +212,126 @@ int collapseBvh4(const BvhNode* nodes, size_t nNodes, std::vector<Bvh4Node>& out
     return depth;
 }
 
+int collapseBvh8(const BvhNode* nodes, size_t nNodes, std::vector<Bvh8Node>& out, std::vector<uint32_t>& triOrder8)
+{
+    struct Slot { float lo[3], hi[3]; int32_t child, count; };
+    auto slotsOf = [&](int32_t n, Slot s[2]) {
+        const BvhNode& b = nodes[n];
+        for (int a = 0; a < 3; ++a) { s[0].lo[a] = b.lo0[a]; s[0].hi[a] = b.hi0[a]; s[1].lo[a] = b.lo1[a]; s[1].hi[a] = b.hi1[a]; }
+        s[0].child = b.child0; s[0].count = b.count0; s[1].child = b.child1; s[1].count = b.count1;
+    };
+    auto area = [](const Slot& s) {
+        const float dx = s.hi[0] - s.lo[0], dy = s.hi[1] - s.lo[1], dz = s.hi[2] - s.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    out.clear();
+    triOrder8.clear();
+    if (nNodes == 0) return 0;
+    struct Todo { int32_t bvh2, wide, depth; };
+    std::vector<Todo> stack{{0, 0, 1}};
+    out.emplace_back();
+    int depth = 0;
+    while (!stack.empty()) {
+        const Todo t = stack.back();
+        stack.pop_back();
+        depth = std::max(depth, t.depth);
+        // ---- gather up to eight children: open the largest inner child while there is room ----
+        Slot ch[8];
+        int n = 0;
+        Slot two[2];
+        slotsOf(t.bvh2, two);
+        for (int k = 0; k < 2; ++k) if (two[k].count >= 0) ch[n++] = two[k];
+        while (n < 8) {
+            int best = -1;
+            float bestArea = -1.f;
+            for (int k = 0; k < n; ++k)
+                if (ch[k].count == 0 && area(ch[k]) > bestArea) { bestArea = area(ch[k]); best = k; }
+            if (best < 0) break;
+            slotsOf(ch[best].child, two);
+            int added = 0;
+            Slot repl[2];
+            for (int k = 0; k < 2; ++k) if (two[k].count >= 0) repl[added++] = two[k];
+            if (added == 0) { ch[best] = ch[--n]; continue; }
+            if (n - 1 + added > 8) break;
+            ch[best] = repl[0];
+            if (added == 2) ch[n++] = repl[1];
+        }
+        // a node may hold at most 32 triangles in its leaf children (one 32-bit hit mask): leaves are <= 4 triangles, 8 x 4 = 32
+        // ---- node frame: origin = lower corner, one power-of-two scale per axis ----
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int k = 0; k < n; ++k)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], ch[k].lo[a]); hi[a] = std::max(hi[a], ch[k].hi[a]); }
+        Bvh8Node w{};
+        float scale[3];
+        for (int a = 0; a < 3; ++a) {
+            w.p[a] = lo[a];
+            const float ext = std::max(hi[a] - lo[a], 1e-30f);
+            int ex = int(std::ceil(std::log2(double(ext) / 255.0)));
+            // make sure 255 * 2^ex really covers the extent in the float arithmetic used below
+            while (std::ldexp(255.0, ex) < double(hi[a]) - double(lo[a])) ++ex;
+            ex = std::min(std::max(ex, -126), 127);
+            w.e[a] = uint8_t(ex + 127);
+            scale[a] = std::ldexp(1.0f, ex);
+        }
+        // ---- slot assignment: child k prefers the slot whose octant direction its centre is displaced to (greedy) ----
+        float cen[3];
+        for (int a = 0; a < 3; ++a) cen[a] = 0.5f * (lo[a] + hi[a]);
+        float cost[8][8];
+        for (int k = 0; k < n; ++k)
+            for (int s8 = 0; s8 < 8; ++s8) {
+                float c = 0.f;
+                for (int a = 0; a < 3; ++a) {
+                    const float dirA = ((s8 >> a) & 1) ? 1.f : -1.f; // slot bit a set = the child lies on the + side of axis a
+                    c += dirA * (0.5f * (ch[k].lo[a] + ch[k].hi[a]) - cen[a]);
+                }
+                cost[k][s8] = c;
+            }
+        int slotOf[8], childAt[8];
+        for (int k = 0; k < 8; ++k) { slotOf[k] = -1; childAt[k] = -1; }
+        for (int round = 0; round < n; ++round) {
+            int bk = -1, bs = -1;
+            float bc = -FLT_MAX;
+            for (int k = 0; k < n; ++k) {
+                if (slotOf[k] >= 0) continue;
+                for (int s8 = 0; s8 < 8; ++s8)
+                    if (childAt[s8] < 0 && cost[k][s8] > bc) { bc = cost[k][s8]; bk = k; bs = s8; }
+            }
+            slotOf[bk] = bs;
+            childAt[bs] = bk;
+        }
+        // ---- emit: inner children get consecutive node indices, leaf triangles consecutive triangle slots, both in slot order ----
+        w.childBase = uint32_t(out.size());
+        w.triBase = uint32_t(triOrder8.size());
+        uint32_t triOff = 0;
+        for (int s8 = 0; s8 < 8; ++s8) {
+            for (int a = 0; a < 3; ++a) { w.qlo[a][s8] = 255; w.qhi[a][s8] = 0; } // empty: inverted box
+            const int k = childAt[s8];
+            if (k < 0) continue;
+            const Slot& c = ch[k];
+            for (int a = 0; a < 3; ++a) {
+                const double ql = std::floor((double(c.lo[a]) - double(w.p[a])) / double(scale[a]));
+                const double qh = std::ceil((double(c.hi[a]) - double(w.p[a])) / double(scale[a]));
+                w.qlo[a][s8] = uint8_t(std::min(std::max(ql, 0.0), 255.0));
+                w.qhi[a][s8] = uint8_t(std::min(std::max(qh, 0.0), 255.0));
+            }
+            if (c.count == 0) {
+                w.imask |= uint8_t(1u << s8);
+                w.meta[s8] = 1;
+                const int32_t idx = int32_t(out.size());
+                out.emplace_back();
+                stack.push_back({c.child, idx, t.depth + 1});
+            }
+            else {
+                w.meta[s8] = uint8_t((uint32_t(c.count) << 5) | triOff);
+                for (int i = 0; i < c.count; ++i) triOrder8.push_back(uint32_t(c.child + i));
+                triOff += uint32_t(c.count);
+            }
+        }
+        out[size_t(t.wide)] = w;
+    }
+    return depth;
+}
+
 void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out)
 {
     out = Bvh();

@@ -43,6 +43,31 @@ static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be one 128-byte record");
 // leaves and their (already padded) boxes are taken over unchanged. Returns the depth of the wide tree.
 int collapseBvh4(const BvhNode* nodes, size_t nNodes, std::vector<Bvh4Node>& out);
 
+// Eight-child node with 8-bit QUANTISED child boxes for the throughput instantiation's traversal of deep trees (k_trace8),
+// 80 bytes = 5 x 16 B, after Ylitie, Karras & Laine, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs"
+// (HPG 2017), simplified: child box k, axis a = [p[a] + qlo[a][k] * 2^e[a], p[a] + qhi[a][k] * 2^e[a]] (lo rounded down, hi rounded
+// up: a superset of the padded box of the two-child tree, so the traversal stays conservative and the triangle tests decide).
+// Children sit in SLOTS chosen so that visiting slots in the order of decreasing (slot ^ octant-inverse) approximates front to
+// back for a ray of that direction octant — no per-ray sorting. Inner children are stored consecutively from childBase in slot
+// order (child = childBase + popcount(imask below the slot)); the triangles of all leaf children are stored consecutively from
+// triBase in the node-ordered triangle array (meta = count << 5 | offset from triBase; at most 4 triangles per leaf, 32 per node),
+// so a whole node's triangle hits fit one 32-bit mask. 1 M triangles: ~75 k nodes = 6 MB instead of 25 MB of four-child nodes.
+struct Bvh8Node {
+    float p[3];
+    uint8_t e[3];      // biased exponents: 2^e as a float is (e << 23)
+    uint8_t imask;     // bit k: child k is an inner node
+    uint32_t childBase;
+    uint32_t triBase;
+    uint8_t meta[8];   // 0 = empty slot, inner: 1, leaf: (count << 5) | offset
+    uint8_t qlo[3][8], qhi[3][8];
+};
+static_assert(sizeof(Bvh8Node) == 80, "Bvh8Node must be 80 bytes");
+
+// Collapses a two-child tree into eight-child quantised nodes (largest-area inner child opened first, greedy slot assignment).
+// triOrder8[k] = index into the LEAF-ordered triangle array of the triangle that the wide tree stores at position k.
+// Returns the depth of the wide tree (0 if nNodes == 0).
+int collapseBvh8(const BvhNode* nodes, size_t nNodes, std::vector<Bvh8Node>& out, std::vector<uint32_t>& triOrder8);
+
 // tri = n * 9 floats (v0 v1 v2). Binned SAH (16 bins, 3 axes), leaves of at most `maxLeaf` triangles.
 void buildBvh(const float* tri, uint32_t n, int maxLeaf, Bvh& out);
 

@@ -4,6 +4,7 @@
 #include <xrt/renderer.h>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 GpuRenderer::GpuRenderer(uint32_t spp, Camera* cam, Integrator* inte, GpuOptions opt)
     : Renderer(cam, inte), n_samples(spp), m_opt(opt) {}
@@ -19,8 +20,11 @@ void GpuRenderer::render(const Scene& scene, Sampler::SamplerType st, Image& ima
     if (!m_scene || m_cachedFor != &scene || m_cachedVersion != scene.version()) {
         if (m_scene) { xrtg_scene_destroy(m_scene); m_scene = nullptr; }
         scene.flatten(m_flat);
-        if (xrtg_scene_create(&m_flat.desc, m_opt.device, &m_scene) != XRTG_OK)
-            throw std::runtime_error(std::string("[GpuRenderer] scene upload failed: ") + xrtg_last_error());
+        const int n = m_opt.ngpus > 0 ? m_opt.ngpus : xrtg_device_count() - m_opt.device;
+        std::vector<int> devices;
+        for (int g = 0; g < n; ++g) devices.push_back(m_opt.device + g);
+        const int rc = n > 1 ? xrtg_scene_create_multi(&m_flat.desc, n, devices.data(), 0u, &m_scene) : xrtg_scene_create(&m_flat.desc, m_opt.device, &m_scene);
+        if (rc != XRTG_OK) throw std::runtime_error(std::string("[GpuRenderer] scene upload failed: ") + xrtg_last_error());
         m_cachedFor = &scene;
         m_cachedVersion = scene.version();
     }

@@ -58,7 +58,7 @@ namespace xrt {
 
 int uploadAll(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
     for (Mirror* m : all) {
         if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
@@ -336,6 +336,22 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             s->info.wide_arity = 4;
         }
     }
+    // ---- deep trees, throughput instantiation: eight-child quantised nodes + node-ordered triangle records (bvh.h, k_trace8) ----
+    if (bvh.nodes.size() > 512) {
+        std::vector<Bvh8Node> wide8;
+        std::vector<uint32_t> order8;
+        const int depth8 = collapseBvh8(static_cast<const BvhNode*>(s->nodes.h), bvh.nodes.size(), wide8, order8);
+        if (depth8 + 2 <= 64 && order8.size() == size_t(nMeshTris)) { // one group-stack entry per level (12 shared + 52 local)
+            if (int rc = s->nodes8.alloc(sizeof(Bvh8Node) * wide8.size())) return rc;
+            std::memcpy(s->nodes8.h, wide8.data(), s->nodes8.bytes);
+            if (int rc = s->ftris8.alloc(sizeof(float4) * 4 * order8.size())) return rc;
+            const float4* ftris = static_cast<const float4*>(s->ftris.h);
+            float4* f8 = static_cast<float4*>(s->ftris8.h);
+            for (size_t k = 0; k < order8.size(); ++k) std::memcpy(f8 + 4 * k, ftris + 4 * size_t(order8[k]), 4 * sizeof(float4));
+            s->info.n_wide_nodes = int(wide8.size());
+            s->info.wide_arity = 8;
+        }
+    }
     // ---- small scenes: plane-grouped triangle block for k_bounce_small (small_scene.h) ----
     int smallBlockF4 = 0;
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
@@ -473,6 +489,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
     ds.ftris = static_cast<const float4*>(s->ftris.d);
     ds.ftris_id = static_cast<const float4*>(s->ftrisId.d);
+    ds.ftris8 = static_cast<const float4*>(s->ftris8.d);
     ds.smallBlock = static_cast<const float4*>(s->smallBlock.d);
     ds.smallBlockF4 = smallBlockF4;
     ds.prims = static_cast<const float4*>(s->prims.d);
@@ -715,6 +732,16 @@ Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, b
     return P;
 }
 
+// Which form of a deep tree the traversal kernel walks: 8 (default; throughput instantiation only), 4 or 2 children per node
+DScene sceneForTraversal(const xrtg_scene* s)
+{
+    DScene ds = s->ds;
+    const int arity = tv(s->tuning.t.wide_bvh, 8);
+    if (arity < 8) { ds.nodes8 = nullptr; ds.ftris8 = nullptr; }
+    if (arity < 4) ds.nodes4 = nullptr;
+    return ds;
+}
+
 } // namespace
 
 namespace xrt {
@@ -755,6 +782,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     while (uint64_t(S) * tile > (1ull << 31) - 64) --S;
 
     if (int rc = ensureWorkspace(s, nPixels, S * tile, size_t(S) * tile * shadowPerPath, nIter, exact)) return rc;
+    const DScene ds = sceneForTraversal(s);
     DQueues q = makeQueues(s);
     const DCamera dc = makeCamera(cam);
     float* accum = static_cast<float*>(s->accum.p);
@@ -800,37 +828,37 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             const int src = b & 1;
             if (P.volumePaths) { // volume integrators on a shallow BVH: primary, then every path to completion in one launch
                 tm.begin(kStageExtend);
-                K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
+                K.primary(st, ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
                 tm.end();
                 tm.begin(kStageShade);
-                K.volumePaths(st, s->ds, q, w, brute, nIter, P.thrVol, P.spvVol, count, dstats); ++launches; ++nShade;
+                K.volumePaths(st, ds, q, w, brute, nIter, P.thrVol, P.spvVol, count, dstats); ++launches; ++nShade;
                 tm.end();
                 break;
             }
             if (P.fusedBounce) { // small scene: primary, then one fused shade + connect + extend kernel per bounce
                 if (b == 0) {
                     tm.begin(kStageExtend);
-                    K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
+                    K.primary(st, ds, dc, q, w, brute, missMode, count, dstats, nullptr); ++launches; ++nExtend;
                     tm.end();
                 }
                 tm.begin(kStageShade);
-                K.bounceSmall(st, s->ds, q, w, src, b, dstats); ++launches; ++nShade; ++nBounce;
+                K.bounceSmall(st, ds, q, w, src, b, dstats); ++launches; ++nShade; ++nBounce;
                 tm.end();
                 continue;
             }
             tm.begin(kStageExtend);
-            if (b == 0 && P.fusedPrimary) K.primary(st, s->ds, dc, q, w, brute, missMode, count, dstats, nullptr);
-            else K.extend(st, s->ds, q, src, b, brute ? 1 : ((P.bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? P.thrExt0 : P.thrExt, P.spv, P.leafThr);
+            if (b == 0 && P.fusedPrimary) K.primary(st, ds, dc, q, w, brute, missMode, count, dstats, nullptr);
+            else K.extend(st, ds, q, src, b, brute ? 1 : ((P.bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? P.thrExt0 : P.thrExt, P.spv, P.leafThr);
             ++launches; ++nExtend;
             tm.end();
             tm.begin(kStageShade);
-            if (volume) K.shadeVolume(st, s->ds, q, w, src, b, brute, count, dstats);
-            else K.shadeSurface(st, s->ds, q, w, src, b);
+            if (volume) K.shadeVolume(st, ds, q, w, src, b, brute, count, dstats);
+            else K.shadeSurface(st, ds, q, w, src, b);
             ++launches; ++nShade;
             tm.end();
             if (hasShadow) {
                 tm.begin(kStageConnect);
-                K.connect(st, s->ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
+                K.connect(st, ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
                 tm.end();
             }
             if (volume) {
@@ -1161,7 +1189,7 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
             w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
         }
         if (int rc = s->rayTmp[3].ensure(sizeof(float4) * nPaths)) return rc;
-        K.primary(st, s->ds, makeCamera(cam), q, w, brute, 0, false, dstats, dj);
+        K.primary(st, sceneForTraversal(s), makeCamera(cam), q, w, brute, 0, false, dstats, dj);
         K.scatterPrimaryHits(st, q, static_cast<float4*>(s->rayTmp[3].p), uint32_t(nPaths));
         hitsByPath = static_cast<const float4*>(s->rayTmp[3].p);
     }
@@ -1169,9 +1197,9 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
         K.raygen(st, makeCamera(cam), q, w, dj);
         if (fastHook) { // deep BVH: the renderer's own bounce-0 launch (k_trace on the wide tree, production refill settings)
             const Pipeline P = choosePipeline(s, XRTG_INT_GI, 3, false, brute);
-            K.extend(st, s->ds, q, 0, 0, brute ? 1 : 0, false, dstats, P.thrExt0, P.spv, P.leafThr);
+            K.extend(st, sceneForTraversal(s), q, 0, 0, brute ? 1 : 0, false, dstats, P.thrExt0, P.spv, P.leafThr);
         }
-        else K.extend(st, s->ds, q, 0, 0, brute ? 1 : 0, false, dstats, 16, 1, 8);
+        else K.extend(st, sceneForTraversal(s), q, 0, 0, brute ? 1 : 0, false, dstats, 16, 1, 8);
     }
     CU(cudaGetLastError());
     // hits are indexed by path id = s * nPixels + pixel; the ABI wants [(pixel * spp) + s]
@@ -1217,7 +1245,7 @@ int xrtg_trace_rays(xrtg_scene* s, int64_t n, const float* org, const float* dir
     // default: the no-FMA instantiation through k_trace; XRTG_FLAG_FAST_HOOK: the throughput instantiation through the
     // production entry points of this scene (hookMode)
     const KernelTable& K = (flags & XRTG_FLAG_FAST_HOOK) ? fastKernels() : exactKernels();
-    K.traceRays(st, s->ds, q, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
+    K.traceRays(st, sceneForTraversal(s), q, static_cast<const float*>(s->rayTmp[0].p), static_cast<const float*>(s->rayTmp[1].p),
                 tmax ? static_cast<const float*>(s->rayTmp[2].p) : nullptr, n, any_hit != 0, (flags & XRTG_FLAG_BRUTE_FORCE) != 0,
                 static_cast<float4*>(s->rayTmp[3].p), static_cast<unsigned long long*>(s->stats.p), hookMode(s, flags));
     CU(cudaGetLastError());

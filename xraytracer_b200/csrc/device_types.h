@@ -56,6 +56,7 @@ struct DScene {
     // triangleRecord() in wavefront.cuh; leaf order / primitive-id order like tris / tris_id
     const float4* ftris;
     const float4* ftris_id;
+    const float4* ftris8;  // the same records in the order the eight-child tree stores them (triBase + offset), or nullptr
     const float4* smallBlock; // plane-paired triangles of a small scene (small_scene.h) or nullptr
     int smallBlockF4;         // its size in float4 (0 = not available)
     const float4* prims;   // 4 float4 per primitive id: shading record

@@ -57,6 +57,7 @@ void rebindPointers(xrtg_scene* s)
     ds.tris_id = static_cast<const float4*>(s->trisId.d);
     ds.ftris = static_cast<const float4*>(s->ftris.d);
     ds.ftris_id = static_cast<const float4*>(s->ftrisId.d);
+    ds.ftris8 = static_cast<const float4*>(s->ftris8.d);
     ds.smallBlock = static_cast<const float4*>(s->smallBlock.d);
     ds.prims = static_cast<const float4*>(s->prims.d);
     ds.spheres = static_cast<const float4*>(s->spheres.d);
@@ -92,9 +93,9 @@ int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out)
     for (auto& e : r->ev) CU(cudaEventCreate(&e));
     CU(cudaMallocHost(&r->statsHost, sizeof(unsigned long long) * kStatCount));
     CU(cudaMallocHost(&r->ctrlHost, sizeof(uint32_t) * 16));
-    const Mirror* src[] = {&primary->nodes, &primary->nodes4, &primary->nodes8, &primary->tris, &primary->trisId, &primary->ftris, &primary->ftrisId,
+    const Mirror* src[] = {&primary->nodes, &primary->nodes4, &primary->nodes8, &primary->tris, &primary->trisId, &primary->ftris, &primary->ftrisId, &primary->ftris8,
                            &primary->smallBlock, &primary->prims, &primary->spheres, &primary->boxes, &primary->lights, &primary->dlights, &primary->media};
-    Mirror* dst[] = {&r->nodes, &r->nodes4, &r->nodes8, &r->tris, &r->trisId, &r->ftris, &r->ftrisId,
+    Mirror* dst[] = {&r->nodes, &r->nodes4, &r->nodes8, &r->tris, &r->trisId, &r->ftris, &r->ftrisId, &r->ftris8,
                      &r->smallBlock, &r->prims, &r->spheres, &r->boxes, &r->lights, &r->dlights, &r->media};
     for (size_t k = 0; k < sizeof(src) / sizeof(src[0]); ++k)
         if (int rc = dst[k]->mirrorOf(*src[k])) return rc;

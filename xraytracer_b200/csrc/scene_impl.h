@@ -96,7 +96,7 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     int device = 0;
     cudaStream_t stream = nullptr; // uploads + host-buffer renders
     // scene arrays (pinned host copy + device copy)
-    xrt::Mirror nodes, nodes4, nodes8, tris, trisId, ftris, ftrisId, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
+    xrt::Mirror nodes, nodes4, nodes8, tris, trisId, ftris, ftrisId, ftris8, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
     std::vector<std::unique_ptr<xrt::Mirror>> gridData;
     xrt::DScene ds{};
     xrtg_scene_info info{};

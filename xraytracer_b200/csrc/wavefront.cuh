@@ -45,6 +45,7 @@ constexpr float kRayEps = 1e-3f;     // geometry.h:23
 #include "wf_math_rng.cuh"
 #include "wf_intersect.cuh"
 #include "wf_trace.cuh"
+#include "wf_trace8.cuh"
 #include "wf_shade.cuh"
 #include "wf_volume.cuh"
 #include "wf_launch.cuh"

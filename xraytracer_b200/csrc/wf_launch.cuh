@@ -77,6 +77,14 @@ template <bool ANY>
 inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,
                         float4* anyOut, int thr, int spv, int leafThr)
 {
+    if constexpr (!kExact) {
+        // throughput instantiation, deep scene: the eight-child quantised tree (k_trace8); brute force stays with k_trace
+        if (sc.nodes8 != nullptr && sc.ftris8 != nullptr && brute == 0) {
+            if (count) k_trace8<ANY, true><<<gridFor((const void*)k_trace8<ANY, true>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
+            else k_trace8<ANY, false><<<gridFor((const void*)k_trace8<ANY, false>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
+            return;
+        }
+    }
     const int g[4] = {gridFor((const void*)k_trace<ANY, false, false>), gridFor((const void*)k_trace<ANY, true, false>),
                       gridFor((const void*)k_trace<ANY, false, true>), gridFor((const void*)k_trace<ANY, true, true>)};
     const bool wide = sc.nodes4 != nullptr;

@@ -264,14 +264,18 @@ int collapseBvh8(const BvhNode* nodes, size_t nNodes, std::vector<Bvh8Node>& out
         Bvh8Node w{};
         float scale[3];
         for (int a = 0; a < 3; ++a) {
-            w.p[a] = lo[a];
+            // The kernel's slab FMA carries up to half a quantisation step of rounding error (wf_trace8.cuh: byteMagic), so every
+            // child box gets ONE step of margin on each side: the frame starts one step below the children's lower corner and
+            // spans 253 steps, which leaves q in [1, 254] before the margin and [0, 255] after it.
             const float ext = std::max(hi[a] - lo[a], 1e-30f);
-            int ex = int(std::ceil(std::log2(double(ext) / 255.0)));
-            // make sure 255 * 2^ex really covers the extent in the float arithmetic used below
-            while (std::ldexp(255.0, ex) < double(hi[a]) - double(lo[a])) ++ex;
-            ex = std::min(std::max(ex, -126), 127);
+            int ex = int(std::ceil(std::log2(double(ext) / 253.0)));
+            while (std::ldexp(253.0, ex) < double(hi[a]) - double(lo[a])) ++ex;
+            ex = std::min(std::max(ex, -100), 100);
             w.e[a] = uint8_t(ex + 127);
             scale[a] = std::ldexp(1.0f, ex);
+            w.p[a] = lo[a] - scale[a];
+            // (lo - scale rounds in float: make sure the frame origin really lies at least one step below the children)
+            while (!((double(lo[a]) - double(w.p[a])) / double(scale[a]) >= 1.0)) w.p[a] = std::nextafter(w.p[a], -FLT_MAX);
         }
         // ---- slot assignment: child k prefers the slot whose octant direction its centre is displaced to (greedy) ----
         float cen[3];
@@ -302,29 +306,26 @@ int collapseBvh8(const BvhNode* nodes, size_t nNodes, std::vector<Bvh8Node>& out
         // ---- emit: inner children get consecutive node indices, leaf triangles consecutive triangle slots, both in slot order ----
         w.childBase = uint32_t(out.size());
         w.triBase = uint32_t(triOrder8.size());
-        uint32_t triOff = 0;
         for (int s8 = 0; s8 < 8; ++s8) {
             for (int a = 0; a < 3; ++a) { w.qlo[a][s8] = 255; w.qhi[a][s8] = 0; } // empty: inverted box
             const int k = childAt[s8];
             if (k < 0) continue;
             const Slot& c = ch[k];
             for (int a = 0; a < 3; ++a) {
-                const double ql = std::floor((double(c.lo[a]) - double(w.p[a])) / double(scale[a]));
-                const double qh = std::ceil((double(c.hi[a]) - double(w.p[a])) / double(scale[a]));
+                const double ql = std::floor((double(c.lo[a]) - double(w.p[a])) / double(scale[a])) - 1.0; // one step of margin
+                const double qh = std::ceil((double(c.hi[a]) - double(w.p[a])) / double(scale[a])) + 1.0;
                 w.qlo[a][s8] = uint8_t(std::min(std::max(ql, 0.0), 255.0));
                 w.qhi[a][s8] = uint8_t(std::min(std::max(qh, 0.0), 255.0));
             }
             if (c.count == 0) {
                 w.imask |= uint8_t(1u << s8);
-                w.meta[s8] = 1;
                 const int32_t idx = int32_t(out.size());
                 out.emplace_back();
                 stack.push_back({c.child, idx, t.depth + 1});
             }
             else {
-                w.meta[s8] = uint8_t((uint32_t(c.count) << 5) | triOff);
+                w.validTri |= ((1u << c.count) - 1u) << (4 * s8);
                 for (int i = 0; i < c.count; ++i) triOrder8.push_back(uint32_t(c.child + i));
-                triOff += uint32_t(c.count);
             }
         }
         out[size_t(t.wide)] = w;

@@ -50,15 +50,18 @@ int collapseBvh4(const BvhNode* nodes, size_t nNodes, std::vector<Bvh4Node>& out
 // Children sit in SLOTS chosen so that visiting slots in the order of decreasing (slot ^ octant-inverse) approximates front to
 // back for a ray of that direction octant — no per-ray sorting. Inner children are stored consecutively from childBase in slot
 // order (child = childBase + popcount(imask below the slot)); the triangles of all leaf children are stored consecutively from
-// triBase in the node-ordered triangle array (meta = count << 5 | offset from triBase; at most 4 triangles per leaf, 32 per node),
-// so a whole node's triangle hits fit one 32-bit mask. 1 M triangles: ~75 k nodes = 6 MB instead of 25 MB of four-child nodes.
+// triBase in the node-ordered triangle array, in slot order. validTri has one NIBBLE per slot: (1 << count) - 1 for a leaf child
+// (at most 4 triangles per leaf), 0 otherwise — the kernel ANDs it with "0xF per hit slot" to get the node's triangle hits in
+// one instruction, and bit b of that mask is triangle triBase + popcount(validTri below b).
+// 1 M triangles: ~75 k nodes = 6 MB instead of 25 MB of four-child nodes.
 struct Bvh8Node {
     float p[3];
     uint8_t e[3];      // biased exponents: 2^e as a float is (e << 23)
     uint8_t imask;     // bit k: child k is an inner node
     uint32_t childBase;
     uint32_t triBase;
-    uint8_t meta[8];   // 0 = empty slot, inner: 1, leaf: (count << 5) | offset
+    uint32_t validTri; // nibble k: triangle bits of leaf child k
+    uint32_t reserved;
     uint8_t qlo[3][8], qhi[3][8];
 };
 static_assert(sizeof(Bvh8Node) == 80, "Bvh8Node must be 80 bytes");

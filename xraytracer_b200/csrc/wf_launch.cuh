@@ -80,8 +80,12 @@ inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int
     if constexpr (!kExact) {
         // throughput instantiation, deep scene: the eight-child quantised tree (k_trace8); brute force stays with k_trace
         if (sc.nodes8 != nullptr && sc.ftris8 != nullptr && brute == 0) {
-            if (count) k_trace8<ANY, true><<<gridFor((const void*)k_trace8<ANY, true>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
-            else k_trace8<ANY, false><<<gridFor((const void*)k_trace8<ANY, false>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
+            // (leafThr carries the development switch "6 CTAs per SM / 80 registers" in bit 8)
+            const bool six = (leafThr & 256) != 0;
+            leafThr &= 255;
+            if (count) k_trace8<ANY, true, 8><<<gridFor((const void*)k_trace8<ANY, true, 8>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
+            else if (six) k_trace8<ANY, false, 6><<<gridFor((const void*)k_trace8<ANY, false, 6>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
+            else k_trace8<ANY, false, 8><<<gridFor((const void*)k_trace8<ANY, false, 8>), kBlock, 0, st>>>(sc, q, src, bounce, stats, anyOut, thr, spv, leafThr);
             return;
         }
     }

@@ -3,8 +3,8 @@
 // node-ordered plane-equation triangle records (ftris8). Same outer structure as k_trace (persistent warps, per-lane resumable
 // state, idle lanes refilled from a warp-private reservation of queue entries, triangle tests postponed until enough lanes of the
 // warp have some), but the traversal state is the compressed-wide-BVH one (Ylitie, Karras & Laine 2017):
-//   * a lane's stack holds GROUPS, not nodes: (childBase, hit bits | imask) = all children of one node that are still to visit,
-//     or (triBase, triangle hit bits) = all postponed triangles of one node -> at most two entries per tree level;
+//   * a lane's stack holds GROUPS, not nodes: (childBase, hit bits | imask) = all children of one node that are still to visit
+//     -> at most one entry per tree level;
 //   * children are visited in the fixed order "decreasing (slot ^ octant-inverse)" the builder arranged the slots for: no
 //     per-ray distance sort, the 8 slab tests produce one 8-bit mask;
 //   * a node test costs ONE dependent 80-byte fetch (five 16 B loads) for eight children: ~4.5 dependent node fetches per ray
@@ -20,7 +20,7 @@ struct Ray8State {
     Hit h;           // closest: current best; any: h.t = tmax, h.prim = occluded flag
     int minId;
     uint32_t gBase, gBits; // current node group: first child node | (hit bits in visiting priority, bits 0..7) | imask << 8
-    uint32_t tBase, tBits; // current triangle group: first triangle | hit bits
+    uint32_t tBase, tBits, tValid; // current triangle group: first triangle | hit bits | the node's validTri (bit -> triangle index)
     uint32_t octinv;       // 7 - direction octant (bit a set <=> d[a] >= 0)
     int sp;
     uint32_t qidx;
@@ -39,52 +39,66 @@ __device__ __forceinline__ uint2 pop8(const uint2* sstack, const uint2* lstack, 
     return (sp < kStack8Smem) ? sstack[sp * kBlock] : lstack[sp - kStack8Smem];
 }
 
-// byte k of `w` as a float: one PRMT builds the bit pattern of 2^23 + b, the subtraction is exact
-__device__ __forceinline__ float byteF(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k)) - 8388608.0f; }
+// Byte k of `w` as the float 2^23 + b: ONE PRMT builds the bit pattern. The "- 2^23" is not executed per byte: it is folded into
+// the additive term of the slab FMA, t = (2^23 + b) * s + (c - 2^23 * s). The product 2^23 * s is exact (power of two) and the
+// FMA rounds once, so the only extra error is the rounding of c - 2^23 * s: at most half a quantisation step (s / 2) in t. The
+// builder pays for it with one step of margin on each side of every child box (bvh.cpp: collapseBvh8), which keeps the test
+// conservative; 48 FADD per node disappear.
+__device__ __forceinline__ float byteMagic(uint32_t w, int k) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k)); }
 
-// One node: the eight quantised slab tests. Writes the node's groups into r (gBase/gBits, tBase/tBits).
+// One node: the eight quantised slab tests, two children per packed fp32x2 FMA. Writes the node's groups into r.
 template <bool COUNT>
 __device__ __forceinline__ void nodeStep8(const DScene& sc, Ray8State& r, uint32_t nodeIdx, TraceCounters& tc)
 {
     const uint4* __restrict__ nd = sc.nodes8 + 5 * size_t(nodeIdx);
     const uint4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3), n4 = __ldg(nd + 4);
     if (COUNT) tc.nodes++;
-    // per-axis scale 2^e folded into the reciprocal direction; origin of the node frame relative to the ray
+    // per-axis scale 2^e folded into the reciprocal direction; origin of the node frame relative to the ray, minus 2^23 steps
     const float sx = r.idir.x * __uint_as_float((n0.w & 0xffu) << 23), sy = r.idir.y * __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                 sz = r.idir.z * __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-    const float cx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x, cy = (__uint_as_float(n0.y) - r.o.y) * r.idir.y, cz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
+    const float cx = fmaf(-8388608.0f, sx, (__uint_as_float(n0.x) - r.o.x) * r.idir.x), cy = fmaf(-8388608.0f, sy, (__uint_as_float(n0.y) - r.o.y) * r.idir.y),
+                cz = fmaf(-8388608.0f, sz, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
+    const float2 SX = make_float2(sx, sx), SY = make_float2(sy, sy), SZ = make_float2(sz, sz);
+    const float2 CX = make_float2(cx, cx), CY = make_float2(cy, cy), CZ = make_float2(cz, cz);
     const uint32_t imask = n0.w >> 24;
     // near / far planes by the sign of the direction: lo is near where d >= 0
     const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
-    const uint32_t nx0 = px ? n2.x : n3.z, nx1 = px ? n2.y : n3.w, fx0 = px ? n3.z : n2.x, fx1 = px ? n3.w : n2.y; // qlo.x = n2.xy, qhi.x = n3.zw
-    const uint32_t ny0 = py ? n2.z : n4.x, ny1 = py ? n2.w : n4.y, fy0 = py ? n4.x : n2.z, fy1 = py ? n4.y : n2.w; // qlo.y = n2.zw, qhi.y = n4.xy
-    const uint32_t nz0 = pz ? n3.x : n4.z, nz1 = pz ? n3.y : n4.w, fz0 = pz ? n4.z : n3.x, fz1 = pz ? n4.w : n3.y; // qlo.z = n3.xy, qhi.z = n4.zw
-    uint32_t nodeHits = 0, triHits = 0;
+    const uint32_t nx[2] = {px ? n2.x : n3.z, px ? n2.y : n3.w}, fx[2] = {px ? n3.z : n2.x, px ? n3.w : n2.y}; // qlo.x = n2.xy, qhi.x = n3.zw
+    const uint32_t ny[2] = {py ? n2.z : n4.x, py ? n2.w : n4.y}, fy[2] = {py ? n4.x : n2.z, py ? n4.y : n2.w}; // qlo.y = n2.zw, qhi.y = n4.xy
+    const uint32_t nz[2] = {pz ? n3.x : n4.z, pz ? n3.y : n4.w}, fz[2] = {pz ? n4.z : n3.x, pz ? n4.w : n3.y}; // qlo.z = n3.xy, qhi.z = n4.zw
+    // H: 0xF in nibble k for every child k whose box the ray enters before the current best (empty slots carry inverted boxes)
+    uint32_t H = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int b = k & 3;
-        const uint32_t wnx = k < 4 ? nx0 : nx1, wfx = k < 4 ? fx0 : fx1, wny = k < 4 ? ny0 : ny1, wfy = k < 4 ? fy0 : fy1, wnz = k < 4 ? nz0 : nz1,
-                       wfz = k < 4 ? fz0 : fz1;
-        const float tnx = fmaf(byteF(wnx, b), sx, cx), tfx = fmaf(byteF(wfx, b), sx, cx);
-        const float tny = fmaf(byteF(wny, b), sy, cy), tfy = fmaf(byteF(wfy, b), sy, cy);
-        const float tnz = fmaf(byteF(wnz, b), sz, cz), tfz = fmaf(byteF(wfz, b), sz, cz);
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.h.t));
-        const uint32_t meta = ((k < 4 ? n1.z : n1.w) >> (8 * b)) & 0xffu;
-        const bool hit = tn <= tf && meta != 0u; // (an empty slot carries an inverted box as well)
-        if (hit) {
-            if ((imask >> k) & 1u) nodeHits |= 1u << (uint32_t(k) ^ r.octinv); // bit index = visiting priority
-            else triHits |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
-        }
+    for (int k = 0; k < 8; k += 2) {
+        const int w = k >> 2, b = k & 3;
+        const float2 tnx = __ffma2_rn(make_float2(byteMagic(nx[w], b), byteMagic(nx[w], b + 1)), SX, CX);
+        const float2 tfx = __ffma2_rn(make_float2(byteMagic(fx[w], b), byteMagic(fx[w], b + 1)), SX, CX);
+        const float2 tny = __ffma2_rn(make_float2(byteMagic(ny[w], b), byteMagic(ny[w], b + 1)), SY, CY);
+        const float2 tfy = __ffma2_rn(make_float2(byteMagic(fy[w], b), byteMagic(fy[w], b + 1)), SY, CY);
+        const float2 tnz = __ffma2_rn(make_float2(byteMagic(nz[w], b), byteMagic(nz[w], b + 1)), SZ, CZ);
+        const float2 tfz = __ffma2_rn(make_float2(byteMagic(fz[w], b), byteMagic(fz[w], b + 1)), SZ, CZ);
+        const float tn0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, 0.0f)), tf0 = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, r.h.t));
+        const float tn1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, 0.0f)), tf1 = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, r.h.t));
+        H |= (tn0 <= tf0 ? (0xFu << (4 * k)) : 0u) | (tn1 <= tf1 ? (0xFu << (4 * k + 4)) : 0u);
     }
+    // triangle hits: the hit slots' nibbles of validTri. Node hits: bit 0 of every hit nibble, compressed to one bit per slot,
+    // restricted to inner children, then permuted to visiting priority (bit k -> bit k ^ octinv) with three masked swaps.
+    uint32_t y = H & 0x11111111u;
+    y = (y | (y >> 3)) & 0x03030303u;
+    y = (y | (y >> 6)) & 0x000F000Fu;
+    y = (y | (y >> 12)) & imask;
+    y = (r.octinv & 1u) ? (((y >> 1) & 0x55u) | ((y << 1) & 0xAAu)) : y;
+    y = (r.octinv & 2u) ? (((y >> 2) & 0x33u) | ((y << 2) & 0xCCu)) : y;
+    y = (r.octinv & 4u) ? (((y >> 4) & 0x0Fu) | ((y << 4) & 0xF0u)) : y;
     r.gBase = n1.x;
-    r.gBits = nodeHits | (imask << 8);
+    r.gBits = y | (imask << 8);
     r.tBase = n1.y;
-    r.tBits = triHits;
+    r.tBits = H & n1.z;
+    r.tValid = n1.z;
 }
 
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kBlock, 6) k_trace8(DScene sc, DQueues q, int src, int bounce, unsigned long long* stats, float4* anyOut, int refillThreshold,
+template <bool ANY, bool COUNT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_trace8(DScene sc, DQueues q, int src, int bounce, unsigned long long* stats, float4* anyOut, int refillThreshold,
                                                       int stepsPerVote, int leafThreshold)
 {
     __shared__ uint2 s_stack[kStack8Smem * kBlock];
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_trace8(DScene sc, DQueues q, int 
     const float4* __restrict__ tris = sc.ftris8;
     TraceCounters tc;
     Ray8State r;
-    r.gBits = r.tBits = 0u; r.gBase = r.tBase = 0u; r.sp = 0; r.qidx = 0; r.minId = -1; r.done = false; r.octinv = 0u;
+    r.gBits = r.tBits = 0u; r.gBase = r.tBase = 0u; r.tValid = 0u; r.sp = 0; r.qidx = 0; r.minId = -1; r.done = false; r.octinv = 0u;
     bool active = false, exhausted = false;
     uint32_t resNext = 0, resEnd = 0; // the warp's current reservation of queue entries
     while (true) {
@@ -170,19 +184,25 @@ __global__ void __launch_bounds__(kBlock, 6) k_trace8(DScene sc, DQueues q, int 
                 const uint32_t triMask = __ballot_sync(0xffffffffu, hasTri);
                 const uint32_t advancing = __ballot_sync(0xffffffffu, active && r.tBits == 0u && (r.gBits & 0xffu) != 0u);
                 if (triMask != 0u && (__popc(triMask) >= leafThreshold || advancing == 0u)) {
-                    if (hasTri) {
-                        const uint32_t k = __ffs(r.tBits) - 1u;
-                        r.tBits &= r.tBits - 1u;
-                        if (COUNT) tc.tris++;
-                        if (triangleRecord<ANY, true>(tris + 4 * size_t(r.tBase + k), r.o, r.d, r.h, r.minId)) { r.h.prim = 1; r.done = true; r.tBits = 0u; r.gBits = 0u; r.sp = 0; }
-                    }
+                    // one triangle per lane and round, rounds while at least half of the lanes that started still have one
+                    uint32_t left = triMask;
+                    const int stop = __popc(triMask) / 2;
+                    do {
+                        if (r.tBits != 0u) {
+                            const uint32_t bit = __ffs(r.tBits) - 1u;
+                            r.tBits &= r.tBits - 1u;
+                            const uint32_t k = __popc(r.tValid & ((1u << bit) - 1u)); // triangles of this node stored before it
+                            if (COUNT) tc.tris++;
+                            if (triangleRecord<ANY, true>(tris + 4 * size_t(r.tBase + k), r.o, r.d, r.h, r.minId)) { r.h.prim = 1; r.done = true; r.tBits = 0u; r.gBits = 0u; r.sp = 0; }
+                        }
+                        left = __ballot_sync(0xffffffffu, r.tBits != 0u);
+                    } while (__popc(left) > stop);
                 }
                 // ---- group exhausted: next group from the stack, or the ray is finished ----
                 if (active && r.tBits == 0u && (r.gBits & 0xffu) == 0u) {
                     if (r.sp > 0 && !r.done) {
                         const uint2 e = pop8(sstack, lstack, r.sp);
-                        if (e.x & 0x80000000u) { r.tBase = e.x & 0x7fffffffu; r.tBits = e.y; }
-                        else { r.gBase = e.x; r.gBits = e.y; }
+                        r.gBase = e.x; r.gBits = e.y;
                     }
                     else r.done = true;
                 }

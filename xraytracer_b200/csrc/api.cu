@@ -709,10 +709,13 @@ Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, b
     const xrtg_tuning& t = s->tuning.t;
     Pipeline P{};
     P.deep = s->info.n_bvh_nodes > 512;
+    // refill thresholds / steps per vote of the resumable traversal kernels, measured on the 1 M-triangle scene
+    // (profiles/r02_notes.md): eight-child tree 24 / 24 / 2, four-child tree 16 / 16 / 4
+    const bool eight = !exact && s->ds.nodes8 != nullptr && tv(t.wide_bvh, 8) >= 8;
     P.thrExt0 = tv(t.thr_ext0, P.deep ? 1 : 0);
-    P.thrExt = tv(t.thr_ext, P.deep ? 16 : 0);
-    P.thrCon = tv(t.thr_con, P.deep ? 16 : 0);
-    P.spv = tv(t.steps_per_vote, P.deep ? 4 : 1);
+    P.thrExt = tv(t.thr_ext, P.deep ? (eight ? 24 : 16) : 0);
+    P.thrCon = tv(t.thr_con, P.deep ? (eight ? 24 : 16) : 0);
+    P.spv = tv(t.steps_per_vote, P.deep ? (eight ? 2 : 4) : 1);
     P.leafThr = tv(t.leaf_threshold, 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
     P.thrVol = tv(t.thr_vol, 16);
     P.spvVol = tv(t.spv_vol, 2);
@@ -1045,6 +1048,49 @@ int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* 
     if (!visit4(0, 0, all)) return fail(XRTG_ERR_INVALID, err);
     for (int t = 0; t < n; ++t)
         if (seen[size_t(t)] != 1) return fail(XRTG_ERR_INVALID, "selftest: the collapsed tree references a triangle " + std::to_string(seen[size_t(t)]) + " times");
+    // ---- the eight-child quantised form: same triangles exactly once, every DEQUANTISED child box (minus its one step of margin
+    //      per side, which the kernel's folded slab arithmetic may eat) contains the child's subtree ----
+    std::vector<Bvh8Node> w8;
+    std::vector<uint32_t> order8;
+    const int depth8 = collapseBvh8(bvh.nodes.data(), bvh.nodes.size(), w8, order8);
+    if (depth8 > bvh.depth || order8.size() != size_t(n)) return fail(XRTG_ERR_INVALID, "selftest: eight-child tree has the wrong depth / triangle count");
+    std::fill(seen.begin(), seen.end(), 0);
+    std::function<bool(uint32_t, Range&)> visit8 = [&](uint32_t ni, Range& out) -> bool {
+        for (int a = 0; a < 3; ++a) { out.lo[a] = FLT_MAX; out.hi[a] = -FLT_MAX; }
+        if (ni >= w8.size()) { err = "selftest: eight-child node index out of range"; return false; }
+        const Bvh8Node& nd = w8[ni];
+        uint32_t triNext = nd.triBase, childNext = nd.childBase;
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t nib = (nd.validTri >> (4 * k)) & 0xfu;
+            const bool inner = (nd.imask >> k) & 1u;
+            if (inner && nib) { err = "selftest: slot is both inner and leaf"; return false; }
+            if (!inner && !nib) continue; // empty
+            Range r;
+            if (inner) { if (!visit8(childNext++, r)) return false; }
+            else {
+                for (int a = 0; a < 3; ++a) { r.lo[a] = FLT_MAX; r.hi[a] = -FLT_MAX; }
+                if (nib != 1u && nib != 3u && nib != 7u && nib != 15u) { err = "selftest: malformed triangle nibble"; return false; }
+                for (uint32_t b = nib; b; b >>= 1) {
+                    if (triNext >= order8.size()) { err = "selftest: eight-child triangle index out of range"; return false; }
+                    const uint32_t t = bvh.triOrder[order8[triNext++]];
+                    seen[t]++;
+                    for (int v = 0; v < 3; ++v)
+                        for (int a = 0; a < 3; ++a) { r.lo[a] = std::min(r.lo[a], tri[9 * size_t(t) + 3 * v + a]); r.hi[a] = std::max(r.hi[a], tri[9 * size_t(t) + 3 * v + a]); }
+                }
+            }
+            for (int a = 0; a < 3; ++a) {
+                const double sc = std::ldexp(1.0, int(nd.e[a]) - 127);
+                const double qlo = double(nd.p[a]) + (double(nd.qlo[a][k]) + 1.0) * sc, qhi = double(nd.p[a]) + (double(nd.qhi[a][k]) - 1.0) * sc;
+                if (!(qlo <= double(r.lo[a]) - 0.5 * bvh.pad) || !(qhi >= double(r.hi[a]) + 0.5 * bvh.pad)) { err = "selftest: quantised child box (without its margin) does not contain its subtree"; return false; }
+                out.lo[a] = std::min(out.lo[a], r.lo[a]);
+                out.hi[a] = std::max(out.hi[a], r.hi[a]);
+            }
+        }
+        return true;
+    };
+    if (!visit8(0, all)) return fail(XRTG_ERR_INVALID, err);
+    for (int t = 0; t < n; ++t)
+        if (seen[size_t(t)] != 1) return fail(XRTG_ERR_INVALID, "selftest: the eight-child tree references a triangle " + std::to_string(seen[size_t(t)]) + " times");
     return 0;
 }
 

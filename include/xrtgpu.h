@@ -291,7 +291,8 @@ typedef struct xrtg_tuning {
     int32_t max_leaf;        /* creation time only (XRT_TUNING): triangles per leaf of the host SAH builder, 1..4             */
     int32_t workspace_mb;    /* byte budget of the per-wave queues (default 6144); small values force pixel-tiled waves       */
     int32_t stage_dump;      /* print every stage's CUDA-event time to stderr (with XRTG_FLAG_STAGE_TIMES)                    */
-    int32_t reserved[4];
+    int32_t primary_masks;   /* small scenes: screen-space candidate masks for the primary rays (1) or the BVH walk (0)       */
+    int32_t reserved[3];
 } xrtg_tuning;
 
 int xrtg_abi_version(void);

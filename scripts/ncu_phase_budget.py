@@ -7,7 +7,8 @@ set of (file, first line, last line) ranges given in a small JSON file:
 
     {"node step": [["wf_trace8.cuh", 49, 96]], "triangle test": [["wf_intersect.cuh", 50, 74]], ...}
 
-Lines that match no range go to "other". Inlined code is attributed to the innermost function's lines (what nvdisasm prints).
+Lines that match no range go to "other". `nvdisasm -gi` gives the whole inlining chain of every instruction; an instruction belongs
+to the phase of the innermost frame that some range lists (so helpers shared by two phases are simply left out of the ranges).
 
 usage: python scripts/ncu_phase_budget.py <file.ncu-rep> <kernel regex> <launch index among matches> <mangled-name substring> <phases.json> [units per launch]
 Writes a markdown table to stdout. Needs no GPU.
@@ -57,22 +58,26 @@ def line_table(so_path, symbol_part):
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", str(so_path)], cwd=td, capture_output=True)
         for cubin in sorted(Path(td).glob("*.cubin")):
-            txt = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True).stdout
+            txt = subprocess.run(["nvdisasm", "-gi", "-c", str(cubin)], capture_output=True, text=True).stdout
             m = re.search(r"^\.text\.(\S*" + re.escape(symbol_part) + r"\S*):\n", txt, re.M)
             if not m:
                 continue
             body = txt[m.end():]
             end = re.search(r"^//-+ \.", body, re.M)
             body = body[:end.start()] if end else body
-            cur = ("?", 0)
+            # -gi prints, before an instruction, the chain of inlined frames (innermost first); it stays valid until the next chain
+            chain, fresh = [("?", 0)], True
             lines = []
             for ln in body.splitlines():
                 f = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
                 if f:
-                    cur = (Path(f.group(1)).name, int(f.group(2)))
+                    if fresh:
+                        chain, fresh = [], False
+                    chain.append((Path(f.group(1)).name, int(f.group(2))))
                     continue
                 if re.match(r"\s*/\*[0-9a-f]{4,}\*/", ln):
-                    lines.append((cur, ln.split("*/", 1)[1].strip()))
+                    fresh = True
+                    lines.append((list(chain), ln.split("*/", 1)[1].strip()))
             return m.group(1), lines
     raise SystemExit(f"no function matching {symbol_part!r} in {so_path}")
 
@@ -87,18 +92,20 @@ def main():
         print(f"warning: {len(rows)} instructions in the capture, {len(lines)} in the library (rebuilt since the capture?)", file=sys.stderr)
     n = min(len(rows), len(lines))
 
-    def phase_of(file, line):
-        for label, ranges in phases.items():
-            for f, lo, hi in ranges:
-                if file == f and lo <= line <= hi:
-                    return label
+    def phase_of(chain):
+        # innermost frame first: code inlined from a shared helper belongs to the phase of the nearest caller that is listed
+        for file, line in chain:
+            for label, ranges in phases.items():
+                for f, lo, hi in ranges:
+                    if file == f and lo <= line <= hi:
+                        return label
         return "other"
 
     agg = {}
     for k in range(n):
-        (file, line), _ = lines[k]
+        chain, _ = lines[k]
         _, inst, tinst, samples = rows[k]
-        a = agg.setdefault(phase_of(file, line), [0, 0, 0, 0])
+        a = agg.setdefault(phase_of(chain), [0, 0, 0, 0])
         a[0] += inst; a[1] += tinst; a[2] += samples; a[3] += 1
     tot = [sum(a[i] for a in agg.values()) for i in range(4)]
     print(f"kernel `{name.split('(')[0]}` (launch {index} of /{regex}/ in {Path(rep).name}): {tot[0] / 1e6:.1f} M warp instructions, "

@@ -516,3 +516,40 @@ def test_gpu_lbvh_full_size_scene():
     assert np.array_equal(lbvh.trace_rays(org, d), sah.trace_rays(org, d))
     assert np.array_equal(lbvh.trace_rays(org, d, tmax, any_hit=True)["prim"], sah.trace_rays(org, d, tmax, any_hit=True)["prim"])
     assert lbvh.info()["bvh_depth"] <= 60
+
+
+def test_primary_candidate_masks_change_nothing():
+    """Small scenes: the primary kernel tests only the triangles whose screen-space bounding box touches the warp's 32 pixels
+    (k_primary_masks) instead of walking the BVH. A superset of what the rays can hit, so hits, images and counters must be
+    BIT-identical with the masks on and off — for the reference camera, a camera inside the box (vertices behind the camera:
+    those triangles are candidates everywhere), an off-centre one, ragged image sizes (segments straddle rows) and pixel-tiled
+    waves; exact and throughput instantiation."""
+    require_gpu()
+    host = scenes.cornell_box("quad+sphere")
+    gpu = api.GpuScene(host.flatten(), 0)
+    views = [(320, 180, scenes.CORNELL_C2W, 60.0), (157, 93, scenes.CORNELL_C2W, 60.0),
+             (200, 120, [-1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 278.0, 274.4, 200.0, 1], 60.0),
+             (31, 17, [-1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 1400.0, 900.0, -2000.0, 1], 50.0)]
+    for W, H, c2w, fov in views:
+        cam = scenes.make_camera(W, H, c2w, fov)
+        for integ, depth, flags in ((capi.INT_GI, 3, 0), (capi.INT_NORMAL, 1, capi.FLAG_EXACT), (capi.INT_DIRECT, 1, capi.FLAG_EXACT), (capi.INT_GI, 2, 0)):
+            gpu.set_tuning(primary_masks=1, workspace_mb=1 if (integ == capi.INT_GI and depth == 2) else -1)
+            a, sa = gpu.render(cam, W, H, 4, integ, depth, seed=9, flags=flags)
+            gpu.set_tuning(primary_masks=0, workspace_mb=1 if (integ == capi.INT_GI and depth == 2) else -1)
+            b, sb = gpu.render(cam, W, H, 4, integ, depth, seed=9, flags=flags)
+            assert np.array_equal(bits(a), bits(b)), (W, H, integ)
+            assert sa["closest_rays"] == sb["closest_rays"] and sa["primary_hits"] == sb["primary_hits"] and sa["shadow_rays"] == sb["shadow_rays"]
+        gpu.set_tuning(primary_masks=1)
+        h1 = gpu.trace_primary(cam, W, H, 2, flags=capi.FLAG_FAST_HOOK)
+        gpu.set_tuning(primary_masks=0)
+        h0 = gpu.trace_primary(cam, W, H, 2, flags=capi.FLAG_FAST_HOOK)
+        assert np.array_equal(h1, h0)
+    gpu.set_tuning()
+    vol = scenes.volume_scene(n=16, light="quad")   # two light triangles + the medium box
+    g2 = api.GpuScene(vol.flatten(), 0)
+    cam = scenes.make_camera(320, 180)
+    g2.set_tuning(primary_masks=1)
+    a, sa = g2.render(cam, 320, 180, 4, capi.INT_VOLUME, 8, seed=9)
+    g2.set_tuning(primary_masks=0)
+    b, sb = g2.render(cam, 320, 180, 4, capi.INT_VOLUME, 8, seed=9)
+    assert np.array_equal(bits(a), bits(b)) and sa["tracking_steps"] == sb["tracking_steps"]

@@ -110,18 +110,18 @@ class SceneInfo(C.Structure):
 
 
 TUNING_KEYS = ["fused_bounce", "volume_paths", "scissor", "brute_secondary", "brute_shadow", "thr_ext0", "thr_ext", "thr_con",
-               "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump"]
+               "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump", "primary_masks"]
 
 
 class Tuning(C.Structure):
     """xrtg_tuning: development / test switches of the pipeline selection; -1 = the measured default."""
-    _fields_ = [(k, C.c_int32) for k in TUNING_KEYS] + [("reserved", C.c_int32 * 4)]
+    _fields_ = [(k, C.c_int32) for k in TUNING_KEYS] + [("reserved", C.c_int32 * 3)]
 
     def __init__(self, **kw):
         super().__init__()
         for k in TUNING_KEYS:
             setattr(self, k, int(kw.pop(k, -1)))
-        for i in range(4):
+        for i in range(3):
             self.reserved[i] = -1
         if kw:
             raise TypeError(f"unknown tuning keys: {sorted(kw)}")

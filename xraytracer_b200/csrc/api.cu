@@ -105,7 +105,7 @@ const TuningKey kTuningKeys[] = {
     {"brute_secondary", &xrtg_tuning::brute_secondary}, {"brute_shadow", &xrtg_tuning::brute_shadow}, {"thr_ext0", &xrtg_tuning::thr_ext0},
     {"thr_ext", &xrtg_tuning::thr_ext}, {"thr_con", &xrtg_tuning::thr_con}, {"steps_per_vote", &xrtg_tuning::steps_per_vote},
     {"leaf_threshold", &xrtg_tuning::leaf_threshold}, {"thr_vol", &xrtg_tuning::thr_vol}, {"spv_vol", &xrtg_tuning::spv_vol},
-    {"wide_bvh", &xrtg_tuning::wide_bvh}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
+    {"wide_bvh", &xrtg_tuning::wide_bvh}, {"primary_masks", &xrtg_tuning::primary_masks}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
     {"stage_dump", &xrtg_tuning::stage_dump}};
 
 void tuningFromEnvironment(Tuning& tu)
@@ -273,6 +273,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         s->hasBounds = finite;
         if (finite) { std::memcpy(s->boundsLo, lo, 12); std::memcpy(s->boundsHi, hi, 12); }
     }
+    if (nMeshTris >= 1 && nMeshTris <= 64) s->smallTriVerts = buildTris; // screen-space candidate masks of the primary rays
     // ---- BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
     Bvh bvh;
     bool builtOnGpu = false;
@@ -693,6 +694,63 @@ void computeScissor(const xrtg_scene* s, const xrtg_camera* cam, int W, int H, i
     if (out[3] < out[1]) out[3] = out[1];
 }
 
+// Pixel bounding boxes of the mesh triangles of a small scene as seen through PinholeCamera::sampleRay (camera.h:49-60), for the
+// candidate masks of the primary kernel. Same inverse projection as computeScissor (double precision), one pixel of margin. A
+// triangle with a vertex beside or behind the camera has no bounded projection: x0 > x1 marks "every pixel". Returns false if
+// the camera matrix cannot be inverted (no masks then).
+bool computeTriBoxes(const xrtg_scene* s, const xrtg_camera* cam, int W, int H, TriBoxes& out)
+{
+    const float* m = cam->c2w;
+    const double R[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}};
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    if (!(std::fabs(det) > 1e-12) || !(cam->scale > 0.f) || !(cam->aspect > 0.f)) return false;
+    double inv[3][3];
+    inv[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det; inv[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det;
+    inv[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det; inv[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det;
+    inv[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det; inv[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+    inv[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det; inv[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det;
+    inv[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+    const int n = int(s->smallTriVerts.size() / 9);
+    for (int t = 0; t < n; ++t) {
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        bool bounded = true;
+        for (int v = 0; v < 3 && bounded; ++v) {
+            const float* p = &s->smallTriVerts[size_t(t) * 9 + 3 * v];
+            const double P[3] = {double(p[0]) - m[12], double(p[1]) - m[13], double(p[2]) - m[14]};
+            const double qx = P[0] * inv[0][0] + P[1] * inv[1][0] + P[2] * inv[2][0]; // row vector * R^-1
+            const double qy = P[0] * inv[0][1] + P[1] * inv[1][1] + P[2] * inv[2][1];
+            const double qz = P[0] * inv[0][2] + P[1] * inv[1][2] + P[2] * inv[2][2];
+            const double len = std::sqrt(qx * qx + qy * qy + qz * qz);
+            if (!(qz < -1e-4 * len)) { bounded = false; break; } // beside / behind the camera (or NaN)
+            const double lam = -qz;
+            const double u = 0.5 * (qx / (lam * cam->scale) + 1.0), v2 = 0.5 * (1.0 - qy * cam->aspect / (lam * cam->scale));
+            x0 = std::min(x0, u * W); x1 = std::max(x1, u * W);
+            y0 = std::min(y0, v2 * H); y1 = std::max(y1, v2 * H);
+        }
+        bounded = bounded && std::isfinite(x0) && std::isfinite(x1) && std::isfinite(y0) && std::isfinite(y1);
+        if (!bounded) { out.b[t] = make_int4(1, 0, 0, 0); continue; }
+        auto clampi = [](double v, int lo, int hi) { return int(std::min(double(hi), std::max(double(lo), v))); };
+        // pixel j holds the samples u in [j / W, (j + 1) / W): floor / ceil, then one more pixel on every side
+        out.b[t] = make_int4(clampi(std::floor(x0) - 1.0, 0, W), clampi(std::floor(y0) - 1.0, 0, H), clampi(std::ceil(x1) + 1.0, 0, W), clampi(std::ceil(y1) + 1.0, 0, H));
+        if (out.b[t].x > out.b[t].z) out.b[t].z = out.b[t].x; // (off-screen: empty box, never "every pixel")
+    }
+    return true;
+}
+
+// Builds the candidate masks of the primary rays on `st` and returns the device pointer (nullptr = no masks for this scene / camera).
+const unsigned long long* preparePrimaryMasks(xrtg_scene* s, const KernelTable& K, const xrtg_camera* cam, int W, int H, cudaStream_t st)
+{
+    const int n = int(s->smallTriVerts.size() / 9);
+    if (n < 1 || n > 64 || n != s->ds.nBruteTris) return nullptr;
+    TriBoxes tb;
+    if (!computeTriBoxes(s, cam, W, H, tb)) return nullptr;
+    const uint32_t nPixels = uint32_t(W) * uint32_t(H);
+    if (s->primMask.ensure(sizeof(unsigned long long) * ((size_t(nPixels) + 31) / 32)) != 0) return nullptr;
+    K.primaryMasks(st, tb, n, W, nPixels, static_cast<unsigned long long*>(s->primMask.p));
+    return static_cast<const unsigned long long*>(s->primMask.p);
+}
+
 // Which kernels render this scene. Chosen per (scene, integrator); the parity hooks with XRTG_FLAG_FAST_HOOK ask the same
 // function, so they exercise exactly the entry points a render would.
 //   deep    : > 512 BVH nodes -> raygen + k_trace (refillable state machine over the wide tree) + shade + k_trace<any>
@@ -812,6 +870,10 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     CU(cudaMemsetAsync(accum, 0, sizeof(float) * 3 * size_t(nPixels), st));
     CU(cudaMemsetAsync(dstats, 0, sizeof(unsigned long long) * kStatCount, st));
     if (exact) { K.seedMt(st, w); ++launches; }
+    if (P.fusedPrimary && tv(s->tuning.t.primary_masks, 1) != 0) { // small scenes: screen-space candidate masks of the primary rays
+        w.primMask = preparePrimaryMasks(s, K, cam, p->width, p->height, st);
+        if (w.primMask) ++launches;
+    }
 
     for (uint32_t pix0 = 0; pix0 < nPixels; pix0 += tile)
     for (uint32_t done = 0; done < uint32_t(p->spp); done += S) {
@@ -1235,6 +1297,7 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
             w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
         }
         if (int rc = s->rayTmp[3].ensure(sizeof(float4) * nPaths)) return rc;
+        if (tv(s->tuning.t.primary_masks, 1) != 0) w.primMask = preparePrimaryMasks(s, K, cam, width, height, st);
         K.primary(st, sceneForTraversal(s), makeCamera(cam), q, w, brute, 0, false, dstats, dj);
         K.scatterPrimaryHits(st, q, static_cast<float4*>(s->rayTmp[3].p), uint32_t(nPaths));
         hitsByPath = static_cast<const float4*>(s->rayTmp[3].p);

@@ -71,6 +71,11 @@ struct DScene {
     int nTris, nSpheres, nBoxes, nLights, nDelta, nPrims, nBruteTris, nMedia, nGrids;
 };
 
+// pixel bounding boxes of the (at most 64) mesh triangles of a small scene, passed to k_primary_masks by value
+struct TriBoxes {
+    int4 b[64];
+};
+
 struct DCamera {
     float c2w[16];
     float scale, aspect;
@@ -109,6 +114,11 @@ struct DWave {
     // Screen-space scissor [sx0, sx1) x [sy0, sy1): pixels outside it cannot see the scene's bounding box (every sample of such a
     // pixel is a miss), so the primary kernel resolves them without generating a ray. Full image when unknown.
     int sx0, sy0, sx1, sy1;
+    // Small scenes (<= 64 mesh triangles): per 32 consecutive pixels (linear index >> 5) a 64-bit mask of the triangles whose
+    // screen-space bounding box touches them (k_primary_masks, rebuilt per render from the camera). The primary kernel tests only
+    // those candidates instead of walking the BVH: a superset of what any ray through these pixels can hit, so the closest hit is
+    // unchanged. nullptr = not available (more triangles, or a vertex beside / behind the camera: those set every bit instead).
+    const unsigned long long* primMask;
     // exact mode: per-pixel mt19937 state, word-major [624][nPixels], and the per-pixel cursor
     uint32_t* mt;
     uint32_t* mti;

@@ -11,6 +11,8 @@ struct KernelTable {
     // jitter: nullptr (production: the RNG draws it) or the parity hook's supplied samples
     void (*primary)(cudaStream_t, const DScene&, const DCamera&, const DQueues&, const DWave&, bool brute, int missMode, bool count,
                     unsigned long long* stats, const float* jitter);
+    // small scenes: per-32-pixel candidate masks of the primary rays (k_primary_masks)
+    void (*primaryMasks)(cudaStream_t, const TriBoxes&, int nTris, int width, uint32_t nPixels, unsigned long long* masks);
     void (*extend)(cudaStream_t, const DScene&, const DQueues&, int src, int bounce, int brute /*0 BVH, 1 brute force, 2 small-scene smem*/, bool count, unsigned long long* stats,
                    int refillThreshold, int stepsPerVote, int leafThreshold);
     void (*connect)(cudaStream_t, const DScene&, const DQueues&, int bounce, int brute, bool count, unsigned long long* stats,

@@ -9,7 +9,7 @@ namespace xrt {
 const KernelTable& exactKernels()
 {
     using namespace exact;
-    static const KernelTable t = {launchSeedMt, launchRaygen, launchPrimary, launchExtend, launchConnect, launchShadeSurface, launchBounceSmall, launchShadeVolume, launchVolumePaths,
+    static const KernelTable t = {launchSeedMt, launchRaygen, launchPrimary, launchPrimaryMasks, launchExtend, launchConnect, launchShadeSurface, launchBounceSmall, launchShadeVolume, launchVolumePaths,
                                   launchAccumulate, launchFinalize, launchTraceRays, launchScatterPrimaryHits, launchGenJitter};
     return t;
 }

@@ -116,6 +116,7 @@ int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out)
     r->info = primary->info;
     r->tuning = primary->tuning;
     r->maxShadowPerPath = primary->maxShadowPerPath;
+    r->smallTriVerts = primary->smallTriVerts;
     std::memcpy(r->boundsLo, primary->boundsLo, sizeof(r->boundsLo));
     std::memcpy(r->boundsHi, primary->boundsHi, sizeof(r->boundsHi));
     r->hasBounds = primary->hasBounds;

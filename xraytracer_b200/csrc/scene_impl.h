@@ -102,10 +102,11 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     xrtg_scene_info info{};
     xrt::Tuning tuning;
     int maxShadowPerPath = 1;
+    std::vector<float> smallTriVerts; // small scenes (<= 64 mesh triangles): 9 floats per triangle, primitive-id order (primary-ray masks)
     float boundsLo[3] = {0, 0, 0}, boundsHi[3] = {0, 0, 0}; // world bounds of every primitive (valid if hasBounds)
     bool hasBounds = false;
     // workspace
-    xrt::DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4];
+    xrt::DevBuf q0[2], q1[2], q2[2], hits, s0, s1, s2, radiance, ctrl, accum, outDev, mt, mti, stats, jitter, rayTmp[4], primMask;
     unsigned long long* statsHost = nullptr; // pinned
     uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
     cudaEvent_t ev[4] = {};

@@ -72,6 +72,11 @@ inline void launchPrimary(cudaStream_t st, const DScene& sc, const DCamera& cam,
     else if (count) k_primary<true, false><<<gridFor((const void*)k_primary<true, false>), kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats, nullptr);
     else k_primary<false, false><<<gridFor((const void*)k_primary<false, false>), kBlock, 0, st>>>(sc, cam, q, w, brute, missMode, stats, nullptr);
 }
+inline void launchPrimaryMasks(cudaStream_t st, const TriBoxes& boxes, int nTris, int width, uint32_t nPixels, unsigned long long* masks)
+{
+    const uint32_t nSeg = (nPixels + 31u) / 32u;
+    k_primary_masks<<<int(std::min<uint32_t>((nSeg + kBlock - 1) / kBlock, 148u * 8u)), kBlock, 0, st>>>(boxes, nTris, width, nPixels, masks);
+}
 // k_trace instantiation for (closest / any hit, counters, two- / four-child tree)
 template <bool ANY>
 inline void launchTrace(cudaStream_t st, const DScene& sc, const DQueues& q, int src, int bounce, int brute, bool count, unsigned long long* stats,

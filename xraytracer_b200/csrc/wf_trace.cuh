@@ -476,6 +476,60 @@ __device__ __forceinline__ void blockAppend2(uint32_t* counter, bool wantA, bool
 // hits — ray + hit record — to a COMPACT bounce-0 queue (one atomic per CTA per 128 rays). It also initialises the
 // per-path radiance. Static tile partition: CTA b owns path ids [128 b, 128 b + 128), b += grid.
 // ---------------------------------------------------------------------------------------------------------
+// Screen-space candidate masks of the primary rays (small scenes): bit t of segment s (= 32 consecutive pixels in linear index)
+// is set when the pixel bounding box of mesh triangle t, bbox[t] = (x0, y0, x1, y1) with exclusive upper bounds, computed on
+// the host by projecting its vertices through PinholeCamera::sampleRay's inverse (camera.h:49-60) with a pixel of margin, touches
+// the segment; x0 > x1 marks a triangle with a vertex beside / behind the camera (no valid projection): every segment gets it.
+__global__ void __launch_bounds__(kBlock) k_primary_masks(const TriBoxes boxes, int nTris, int width, uint32_t nPixels, unsigned long long* __restrict__ masks)
+{
+    const int4* bbox = boxes.b;
+    const uint32_t nSeg = (nPixels + 31u) / 32u;
+    for (uint32_t sgm = blockIdx.x * blockDim.x + threadIdx.x; sgm < nSeg; sgm += gridDim.x * blockDim.x) {
+        const uint32_t p0 = 32u * sgm, p1 = min(p0 + 31u, nPixels - 1u);
+        const int r0 = int(p0 / uint32_t(width)), r1 = int(p1 / uint32_t(width));
+        unsigned long long m = 0ull;
+        for (int t = 0; t < nTris; ++t) {
+            const int4 b = bbox[t];
+            bool hit = b.x > b.z;
+            for (int r = max(r0, b.y); r <= r1 && r < b.w && !hit; ++r) { // rows of the segment inside the box's rows
+                const int c0 = r == r0 ? int(p0 - uint32_t(r0) * uint32_t(width)) : 0;
+                const int c1 = r == r1 ? int(p1 - uint32_t(r1) * uint32_t(width)) : width - 1;
+                hit = c0 < b.z && c1 >= b.x;
+            }
+            if (hit) m |= 1ull << t;
+        }
+        masks[sgm] = m;
+    }
+}
+
+// Scene::intersect (scene.cpp:190-200) restricted to the mesh triangles in `mask` (bit = index in primitive-id order): boxes and
+// spheres as in closestHit(). The mask is made warp-uniform by the caller so that the warp stays converged.
+template <bool COUNT>
+__device__ __forceinline__ void closestHitMasked(const DScene& sc, V3 o, V3 d, Hit& h, unsigned long long mask, TraceCounters& tc)
+{
+    h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
+    int minId = -1;
+    for (int b = 0; b < sc.nBoxes; ++b) { // boxes[] are in object order
+        const float4 bl = __ldg(sc.boxes + 2 * b), bh = __ldg(sc.boxes + 2 * b + 1);
+        float t0, t1;
+        if (boxSlabs(xyz(bl), xyz(bh), o, d, t0, t1)) { h.t = t0; h.u = t1; h.v = 0.f; h.prim = __float_as_int(bl.w); minId = h.prim; }
+    }
+    const float4* __restrict__ tris = triArray(sc, true);
+    while (mask) {
+        const int t = __ffsll((long long)mask) - 1;
+        mask &= mask - 1ull;
+        if (COUNT) tc.tris++;
+        triangleRecord<false, true>(tris + kTriF4 * t, o, d, h, minId);
+    }
+    for (int s = 0; s < sc.nSpheres; ++s) {
+        const float4 cr = __ldg(sc.spheres + 2 * s);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(sc.spheres + 2 * s + 1));
+        float t;
+        if (meta.x > minId && sphereT(cr, o, d, t)) consider(h, t, 0.f, 0.f, meta.x);
+    }
+    if (h.prim == 0x7fffffff) h.prim = -1;
+}
+
 // JITTER: the two primary-sample offsets come from `jitter` (parity hook xrtg_trace_primary) instead of the path's RNG — the only
 // difference between the hook's instantiation and the production one.
 template <bool COUNT, bool JITTER>
@@ -494,6 +548,14 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
         const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
         const bool inView = int(j) >= w.sx0 && int(j) < w.sx1 && int(i) >= w.sy0 && int(i) < w.sy1;
         bool hit = false;
+        // small scenes: the triangles that can be seen through this warp's pixels (one mask per 32 pixels; OR over the warp's
+        // lanes, which may straddle two segments, keeps the candidate loop converged)
+        unsigned long long cand = 0ull;
+        if (w.primMask != nullptr && !brute) {
+            const unsigned long long mine = inView ? __ldg(w.primMask + (pix >> 5)) : 0ull;
+            const uint32_t act = __activemask();
+            cand = (unsigned long long)__reduce_or_sync(act, uint32_t(mine)) | ((unsigned long long)__reduce_or_sync(act, uint32_t(mine >> 32)) << 32);
+        }
         if (inView) { // (outside: the pixel cannot see the scene's bounding box, every sample is a miss, no ray needed)
             float r0, r1;
             if constexpr (JITTER) { // parity hook (xrtg_trace_primary): caller-supplied jitter, laid out [(pixel * spp + s) * 2]
@@ -511,7 +573,8 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
             const float v = (float(i) + r1) / float(uint32_t(w.height));
             V3 o;
             cameraRay(cam, u, v, o, d);
-            closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
+            if (w.primMask != nullptr && !brute) closestHitMasked<COUNT>(sc, o, d, h, cand, tc);
+            else closestHit<COUNT>(sc, o, d, brute != 0, h, s_stack + threadIdx.x, tc);
             hit = h.prim >= 0;
         }
         else ++nScissored;

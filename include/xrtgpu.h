@@ -321,6 +321,10 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
 /* Number of devices behind a handle (1 for xrtg_scene_create). */
 int xrtg_scene_device_count(const xrtg_scene* scene);
 int xrtg_scene_set_tuning(xrtg_scene* scene, const xrtg_tuning* tuning);
+/* Every workspace buffer of the handle (ray / hit / shadow queues, radiance, counters, ...) is allocated with 256-byte guard bands
+ * of a known pattern on both sides; this counts the guard bytes that were overwritten since allocation (0 = no kernel wrote out
+ * of bounds). Synchronises the scene's stream(s). The GPU tests call it after every render (tests/conftest.py). */
+int xrtg_scene_check_guards(xrtg_scene* scene, int* violations);
 
 /* ---- one process per GPU (torchrun / MPI style deployments): the same fused reduce + finalize over CUDA IPC ------------- */
 /* An exportable device buffer owned by the scene (plain cudaMalloc on the scene's device, so that cudaIpcGetMemHandle applies to

@@ -37,3 +37,24 @@ def require_gpu():
     from xraytracer_b200 import capi
     if capi.gpu().xrtg_device_count() < 1:
         pytest.fail("GPU test selected but no CUDA device is visible (the render path has no CPU fallback)")
+
+
+@pytest.fixture(autouse=True)
+def guard_bands(monkeypatch):
+    """Every workspace buffer of a GPU scene carries guard bands (csrc/scene_impl.h: DevBuf). After every render / trace call of
+    a GPU test the guards are verified: a kernel that wrote past a queue fails the test that ran it (compute-sanitizer is
+    closed on this pool). No-op for tests that never create a GpuScene."""
+    from xraytracer_b200 import api
+
+    def wrap(name):
+        orig = getattr(api.GpuScene, name)
+
+        def checked(self, *a, **kw):
+            out = orig(self, *a, **kw)
+            bad = self.check_guards()
+            assert bad == 0, f"{name}: {bad} guard bytes around the workspace buffers were overwritten"
+            return out
+        monkeypatch.setattr(api.GpuScene, name, checked)
+    for n in ("render", "render_device", "trace_primary", "trace_rays", "render_u8"):
+        wrap(n)
+    yield

@@ -59,6 +59,12 @@ class GpuScene:
         t = capi.Tuning(**kw)
         self._chk(self.lib.xrtg_scene_set_tuning(self.h, C.byref(t)), "xrtg_scene_set_tuning")
 
+    def check_guards(self) -> int:
+        """Guard bytes around the workspace buffers that a kernel overwrote (0 = no out-of-bounds write)."""
+        n = C.c_int()
+        self._chk(self.lib.xrtg_scene_check_guards(self.h, C.byref(n)), "xrtg_scene_check_guards")
+        return n.value
+
     def device_count(self) -> int:
         return self.lib.xrtg_scene_device_count(self.h)
 

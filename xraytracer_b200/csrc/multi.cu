@@ -47,6 +47,14 @@ __global__ void __launch_bounds__(256) k_reduce_finalize(PartList parts, int nPa
     }
 }
 
+// counts the guard bytes (scene_impl.h: DevBuf) that no longer hold the pattern
+__global__ void __launch_bounds__(256) k_check_guard(const unsigned char* __restrict__ lo, const unsigned char* __restrict__ hi, int* bad)
+{
+    const int i = threadIdx.x;
+    if (lo[i] != kGuardPattern) atomicAdd(bad, 1);
+    if (hi[i] != kGuardPattern) atomicAdd(bad, 1);
+}
+
 void rebindPointers(xrtg_scene* s)
 {
     DScene& ds = s->ds;
@@ -79,6 +87,30 @@ void launchReduceFinalize(cudaStream_t st, const float* const* parts, int nParts
     for (int k = 0; k < nParts; ++k) pl.p[k] = parts[k];
     const int grid = int(std::min<size_t>((count / 4 + 255) / 256 + 1, 148 * 8));
     k_reduce_finalize<<<grid, 256, 0, st>>>(pl, nParts, out, first, count, divisor);
+}
+
+int checkGuards(xrtg_scene* s, int* violations)
+{
+    static_assert(kGuardBytes == 256, "k_check_guard runs one thread per guard byte");
+    *violations = 0;
+    const std::vector<xrtg_scene*> all = s->replicas.empty() ? std::vector<xrtg_scene*>{s} : s->replicas;
+    for (xrtg_scene* r : all) {
+        CU(cudaSetDevice(r->device));
+        DevBuf* bufs[] = {&r->q0[0], &r->q0[1], &r->q1[0], &r->q1[1], &r->q2[0], &r->q2[1], &r->hits, &r->s0, &r->s1, &r->s2, &r->radiance, &r->ctrl, &r->accum,
+                          &r->outDev, &r->mt, &r->mti, &r->stats, &r->jitter, &r->rayTmp[0], &r->rayTmp[1], &r->rayTmp[2], &r->rayTmp[3], &r->primMask, &r->multiOut};
+        int* bad = nullptr;
+        CU(cudaMalloc(&bad, sizeof(int)));
+        CU(cudaMemsetAsync(bad, 0, sizeof(int), r->stream));
+        for (DevBuf* b : bufs)
+            if (b->raw) k_check_guard<<<1, 256, 0, r->stream>>>(static_cast<const unsigned char*>(b->raw), static_cast<const unsigned char*>(b->p) + b->bytes, bad);
+        int h = 0;
+        const cudaError_t e = cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, r->stream);
+        const cudaError_t e2 = cudaStreamSynchronize(r->stream);
+        cudaFree(bad);
+        if (e != cudaSuccess || e2 != cudaSuccess) return fail(XRTG_ERR_CUDA, std::string("guard check: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+        *violations += h;
+    }
+    return 0;
 }
 
 // A replica of `primary` on `device`: shares the primary's pinned host arrays (scene data is built ONCE), owns its device
@@ -282,6 +314,12 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
     primary->info.device_bytes *= uint64_t(ngpus);
     *out = primary;
     return 0;
+}
+
+int xrtg_scene_check_guards(xrtg_scene* s, int* violations)
+{
+    if (!s || !violations) return fail(XRTG_ERR_INVALID, "NULL argument");
+    return checkGuards(s, violations);
 }
 
 int xrtg_exchange_buffer(xrtg_scene* s, int slot, size_t bytes, void** device_ptr)

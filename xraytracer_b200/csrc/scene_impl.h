@@ -60,7 +60,35 @@ struct Mirror {
     ~Mirror() { release(); }
 };
 
+// Device workspace buffer with GUARD BANDS: kGuardBytes of a known pattern before and after the usable range, verified on demand
+// (xrtg_scene_check_guards; the GPU tests check them after every render). compute-sanitizer is closed on this pool, so an
+// out-of-bounds queue write is caught by its footprint instead: every queue / counter / radiance buffer of the wave scheduler
+// is one of these, and neighbouring cudaMalloc blocks are not adjacent, so a stray store lands in a guard or faults.
+constexpr size_t kGuardBytes = 256;
+constexpr unsigned char kGuardPattern = 0xA5;
 struct DevBuf {
+    void* p = nullptr;   // usable range
+    void* raw = nullptr; // allocation = guard | usable | guard
+    size_t bytes = 0;
+    int ensure(size_t n)
+    {
+        if (n <= bytes) return 0;
+        if (raw) cudaFree(raw);
+        p = raw = nullptr;
+        bytes = 0;
+        const size_t padded = (n + 255) & ~size_t(255);
+        CU(cudaMalloc(&raw, padded + 2 * kGuardBytes));
+        CU(cudaMemset(raw, kGuardPattern, kGuardBytes));
+        CU(cudaMemset(static_cast<char*>(raw) + kGuardBytes + padded, kGuardPattern, kGuardBytes));
+        p = static_cast<char*>(raw) + kGuardBytes;
+        bytes = padded;
+        return 0;
+    }
+    ~DevBuf() { if (raw) cudaFree(raw); }
+};
+
+// plain allocation (no guard bands): exportable through CUDA IPC, where the handle names the allocation's BASE address
+struct PlainBuf {
     void* p = nullptr;
     size_t bytes = 0;
     int ensure(size_t n)
@@ -73,7 +101,7 @@ struct DevBuf {
         bytes = n;
         return 0;
     }
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~PlainBuf() { if (p) cudaFree(p); }
 };
 
 struct Timer {
@@ -118,7 +146,7 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     cudaEvent_t pullEvent = nullptr; // ... when its slice of the fused reduce + finalize has been stored into device 0's image
     bool peerChecked = false, peerAll = false;
     xrt::DevBuf multiOut;            // device 0: the final image of a multi-GPU render
-    xrt::DevBuf exchange[4];         // exportable buffers (xrtg_exchange_buffer; one process per GPU + CUDA IPC)
+    xrt::PlainBuf exchange[4];         // exportable buffers (xrtg_exchange_buffer; one process per GPU + CUDA IPC)
     std::vector<std::unique_ptr<xrt::DevBuf>> peerStage; // device 0, topologies without peer mapping: staged copies of the other sums
 
     ~xrtg_scene();
@@ -130,6 +158,7 @@ int uploadAll(xrtg_scene* s);
 int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats);
 int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p);
 // multi.cu
+int checkGuards(xrtg_scene* s, int* violations);
 int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out);
 int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgbHost, xrtg_stats* stats);
 void launchReduceFinalize(cudaStream_t st, const float* const* parts, int nParts, float* out, size_t n0, size_t n1, float divisor);

@@ -173,6 +173,12 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     CU(cudaMallocHost(&s->ctrlHost, sizeof(uint32_t) * 16));
 
     Timer tb;
+    const bool dumpCreate = tv(s->tuning.t.stage_dump, 0) != 0;
+    Timer tphase;
+    auto lap = [&](const char* what) {
+        if (dumpCreate) std::fprintf(stderr, "scene_create: %-28s %8.2f ms\n", what, tphase.ms());
+        tphase = Timer();
+    };
     // ---- global primitive ids in object (= reference iteration) order ----
     int nPrims = 0;
     std::vector<int> firstPrim(d->n_objects);
@@ -194,6 +200,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     if (int rc = s->ftrisId.alloc(sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
     if (int rc = s->spheres.alloc(sizeof(float4) * 2 * size_t(std::max(nSph, 1)))) return rc;
     if (int rc = s->boxes.alloc(sizeof(float4) * 2 * size_t(std::max(nBox, 1)))) return rc;
+    lap("pinned + device allocation");
     std::memset(s->prims.h, 0, s->prims.bytes);
     float4* prims = static_cast<float4*>(s->prims.h);
     float4* trisId = static_cast<float4*>(s->trisId.h);
@@ -214,9 +221,14 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         meta |= uint32_t(o.medium + 1) << kMetaMediumShift;
         const float4 rec3 = make_float4(alb[0], alb[1], alb[2], asF(meta));
         if (o.kind == XRTG_OBJ_MESH) {
-            for (int k = 0; k < o.count; ++k, ++ti) {
-                const xrtg_triangle& t = d->triangles[o.first + k];
-                const int id = firstPrim[i] + k;
+            const int ti0 = ti, id0 = firstPrim[i], emitter = o.area_light >= 0 ? 1 : 0;
+            const xrtg_triangle* src = d->triangles + o.first;
+            // (a 1 M-triangle mesh is one object: the per-triangle work runs on all host cores)
+#pragma omp parallel for schedule(static) if (o.count > 4096)
+            for (int k = 0; k < o.count; ++k) {
+                const xrtg_triangle& t = src[k];
+                const int id = id0 + k;
+                const size_t tk = size_t(ti0) + size_t(k);
                 // e1 = v1 - v0, e2 = v2 - v0 (primitive.cpp:142-143) and ng = normalize(e1 x e2)
                 // (primitive.cpp:105) with the reference's fp32 operation order (host code, no FMA)
                 float e1[3], e2[3], c[3];
@@ -226,19 +238,20 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
                 c[2] = e1[0] * e2[1] - e1[1] * e2[0];
                 const float len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
                 const float ng[3] = {c[0] / len, c[1] / len, c[2] / len};
-                trisId[3 * ti] = f4(t.v0, asF(id));
-                trisId[3 * ti + 1] = f4(e1, asF(int(o.area_light >= 0 ? 1 : 0)));
-                trisId[3 * ti + 2] = f4(e2, 0.f);
+                trisId[3 * tk] = f4(t.v0, asF(id));
+                trisId[3 * tk + 1] = f4(e1, asF(emitter));
+                trisId[3 * tk + 2] = f4(e2, 0.f);
                 // plane-equation record of the throughput instantiation (wavefront.cuh: triangleRecord), built in double
-                makePlaneRecord(t.v0, t.v1, t.v2, id, o.area_light >= 0 ? 1 : 0, reinterpret_cast<float*>(ftrisId + 4 * ti));
-                prims[4 * id] = f4(t.n0, ng[0]);
-                prims[4 * id + 1] = f4(t.n1, ng[1]);
-                prims[4 * id + 2] = f4(t.n2, ng[2]);
-                prims[4 * id + 3] = rec3;
-                std::memcpy(&buildTris[size_t(ti) * 9], t.v0, 12);
-                std::memcpy(&buildTris[size_t(ti) * 9 + 3], t.v1, 12);
-                std::memcpy(&buildTris[size_t(ti) * 9 + 6], t.v2, 12);
+                makePlaneRecord(t.v0, t.v1, t.v2, id, emitter, reinterpret_cast<float*>(ftrisId + 4 * tk));
+                prims[4 * size_t(id)] = f4(t.n0, ng[0]);
+                prims[4 * size_t(id) + 1] = f4(t.n1, ng[1]);
+                prims[4 * size_t(id) + 2] = f4(t.n2, ng[2]);
+                prims[4 * size_t(id) + 3] = rec3;
+                std::memcpy(&buildTris[tk * 9], t.v0, 12);
+                std::memcpy(&buildTris[tk * 9 + 3], t.v1, 12);
+                std::memcpy(&buildTris[tk * 9 + 6], t.v2, 12);
             }
+            ti += o.count;
         }
         else if (o.kind == XRTG_OBJ_SPHERE) {
             const xrtg_sphere& sp = d->spheres[o.first];
@@ -258,6 +271,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             ++bi;
         }
     }
+    lap("triangle / shading records");
     // ---- world bounds of everything a ray can hit (screen-space scissor of the primary kernel) ----
     {
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -316,16 +330,18 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         if (int rc = s->nodes.alloc(sizeof(BvhNode) * bvh.nodes.size())) return rc;
         std::memcpy(s->nodes.h, bvh.nodes.data(), s->nodes.bytes);
         float4* tris = static_cast<float4*>(s->tris.h);
-        for (size_t k = 0; k < bvh.triOrder.size(); ++k) {
-            const uint32_t src = bvh.triOrder[k];
+        float4* ftris = static_cast<float4*>(s->ftris.h);
+        const int64_t nOrder = int64_t(bvh.triOrder.size());
+#pragma omp parallel for schedule(static) if (nOrder > 4096)
+        for (int64_t k = 0; k < nOrder; ++k) {
+            const uint32_t src = bvh.triOrder[size_t(k)];
             tris[3 * k] = trisId[3 * src];
             tris[3 * k + 1] = trisId[3 * src + 1];
             tris[3 * k + 2] = trisId[3 * src + 2];
+            std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(src), 4 * sizeof(float4));
         }
-        float4* ftris = static_cast<float4*>(s->ftris.h);
-        for (size_t k = 0; k < bvh.triOrder.size(); ++k)
-            std::memcpy(ftris + 4 * k, ftrisId + 4 * size_t(bvh.triOrder[k]), 4 * sizeof(float4));
     }
+    lap("bounds + BVH build + reorder");
     // ---- deep trees: four-child form for the resumable traversal kernel (bvh.h) ----
     if (bvh.nodes.size() > 512 && tv(s->tuning.t.wide_bvh, 4) >= 4) {
         std::vector<Bvh4Node> wide;
@@ -337,6 +353,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             s->info.wide_arity = 4;
         }
     }
+    lap("four-child collapse");
     // ---- deep trees, throughput instantiation: eight-child quantised nodes + node-ordered triangle records (bvh.h, k_trace8) ----
     if (bvh.nodes.size() > 512) {
         std::vector<Bvh8Node> wide8;
@@ -348,11 +365,14 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             if (int rc = s->ftris8.alloc(sizeof(float4) * 4 * order8.size())) return rc;
             const float4* ftris = static_cast<const float4*>(s->ftris.h);
             float4* f8 = static_cast<float4*>(s->ftris8.h);
-            for (size_t k = 0; k < order8.size(); ++k) std::memcpy(f8 + 4 * k, ftris + 4 * size_t(order8[k]), 4 * sizeof(float4));
+            const int64_t n8 = int64_t(order8.size());
+#pragma omp parallel for schedule(static) if (n8 > 4096)
+            for (int64_t k = 0; k < n8; ++k) std::memcpy(f8 + 4 * k, ftris + 4 * size_t(order8[size_t(k)]), 4 * sizeof(float4));
             s->info.n_wide_nodes = int(wide8.size());
             s->info.wide_arity = 8;
         }
     }
+    lap("eight-child collapse + ftris8");
     // ---- small scenes: plane-grouped triangle block for k_bounce_small (small_scene.h) ----
     int smallBlockF4 = 0;
     if (nMeshTris >= 1 && nMeshTris <= 64 && nBox == 0) {
@@ -376,7 +396,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             else distant = true;
         }
         std::vector<int> pruned;
-        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi, distant ? nullptr : hull.data(), int(hull.size() / 3), &pruned)) {
+        if (buildSmallBlock(reinterpret_cast<const float*>(ftrisId), nMeshTris, block, &sbi, distant ? nullptr : hull.data(), int(hull.size() / 3), &pruned, buildTris.data())) {
             // Shadow rays do not start ON the surfaces: the origin is hit + bias * ng with ng never flipped towards the ray
             // (SURVEY §9-T3). On a triangle whose normal points OUT of the hull the origin lies behind a hull plane and the
             // reference lets that plane shadow it. An origin p + b * ng (b <= kMaxBias) is a convex combination of the
@@ -475,6 +495,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             M[i].invMajorant = 1.0f / M[i].majorant;
         }
     }
+    lap("small block, lights, media");
     s->info.build_ms = tb.ms();
 
     Timer tu;

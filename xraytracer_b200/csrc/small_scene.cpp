@@ -1,6 +1,7 @@
 // small_scene.cpp — groups the triangles of a small scene by supporting plane (see small_scene.h).
 #include "small_scene.h"
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 
@@ -112,7 +113,94 @@ size_t emitSection(const float* rec, const std::vector<int>& tris, const std::ve
     return end - at;
 }
 
+// ---- coplanar duplicates that can never matter (the Cornell floor shape carries both block footprints) ----
+// 2-D convex polygon clipping in the plane's dominant projection, double precision.
+struct P2 { double x, y; };
+double polyArea(const std::vector<P2>& p)
+{
+    double a = 0.0;
+    for (size_t i = 0; i < p.size(); ++i) { const P2& u = p[i]; const P2& v = p[(i + 1) % p.size()]; a += u.x * v.y - v.x * u.y; }
+    return 0.5 * a;
+}
+// splits convex polygon `poly` by the line through a -> b: `in` = the part on the left (inside for a CCW clip polygon), `out` = the rest
+void splitByEdge(const std::vector<P2>& poly, P2 a, P2 b, std::vector<P2>& in, std::vector<P2>& out)
+{
+    in.clear(); out.clear();
+    auto side = [&](const P2& p) { return (b.x - a.x) * (p.y - a.y) - (b.y - a.y) * (p.x - a.x); };
+    for (size_t i = 0; i < poly.size(); ++i) {
+        const P2& p = poly[i]; const P2& q = poly[(i + 1) % poly.size()];
+        const double sp = side(p), sq = side(q);
+        if (sp >= 0) in.push_back(p);
+        if (sp <= 0) out.push_back(p);
+        if ((sp > 0 && sq < 0) || (sp < 0 && sq > 0)) {
+            const double t = sp / (sp - sq);
+            const P2 x{p.x + t * (q.x - p.x), p.y + t * (q.y - p.y)};
+            in.push_back(x); out.push_back(x);
+        }
+    }
+}
+// true if triangle T lies inside the union of the triangles `cover` (all in one plane), up to 1e-9 of T's area
+bool coveredBy(const P2 T[3], const std::vector<std::array<P2, 3>>& cover)
+{
+    std::vector<std::vector<P2>> pieces{{T[0], T[1], T[2]}};
+    if (polyArea(pieces[0]) < 0) std::reverse(pieces[0].begin(), pieces[0].end());
+    const double areaT = std::fabs(polyArea(pieces[0]));
+    if (!(areaT > 0.0)) return false; // degenerate triangles are left alone (their records reject every ray anyway)
+    for (const auto& L0 : cover) {
+        std::array<P2, 3> L = L0;
+        if (polyArea({L[0], L[1], L[2]}) < 0) std::swap(L[1], L[2]); // CCW
+        std::vector<std::vector<P2>> next;
+        for (const auto& piece : pieces) {
+            std::vector<P2> cur = piece, in, out;
+            for (int e = 0; e < 3 && cur.size() >= 3; ++e) { // what leaves through edge e stays a piece; the rest goes on
+                splitByEdge(cur, L[size_t(e)], L[size_t((e + 1) % 3)], in, out);
+                if (out.size() >= 3 && std::fabs(polyArea(out)) > 1e-12 * areaT) next.push_back(out);
+                cur = in;
+            }
+            // `cur` is now the part of the piece inside L: covered, dropped
+        }
+        pieces.swap(next);
+        if (pieces.empty()) return true;
+    }
+    double left = 0.0;
+    for (const auto& piece : pieces) left += std::fabs(polyArea(piece));
+    return left <= 1e-9 * areaT;
+}
+
 } // namespace
+
+// Triangles of `tris` (indices into the record / vertex arrays, ascending ids) that can be DROPPED from a section without
+// changing any result: a triangle that lies inside the union of coplanar triangles of the same section which precede it.
+// Closest hit: the records of one plane share bit-identical plane words, so a point inside both is always credited to the
+// earlier (lower-id) triangle — the reference's own first-wins rule (scene.cpp:193-197) — and the later one never wins. Any hit:
+// a segment that crosses the dropped triangle crosses one of the covering triangles at the same point.
+std::vector<int> coveredCoplanarDuplicates(const float* ftrisId, const float* tris9, const std::vector<int>& tris)
+{
+    std::vector<int> dropped;
+    if (!tris9) return dropped;
+    std::vector<Plane> planes;
+    for (int t : tris) planes.push_back(planeOf(ftrisId + 16 * size_t(t)));
+    for (size_t k = 1; k < tris.size(); ++k) {
+        if (!planes[k].valid) continue;
+        // dominant projection axis of the plane normal
+        int ax = 0;
+        for (int a = 1; a < 3; ++a) if (std::fabs(planes[k].n[a]) > std::fabs(planes[k].n[ax])) ax = a;
+        const int ux = (ax + 1) % 3, uy = (ax + 2) % 3;
+        auto proj = [&](int t, P2 out[3]) { for (int v = 0; v < 3; ++v) out[v] = P2{tris9[9 * size_t(t) + 3 * v + ux], tris9[9 * size_t(t) + 3 * v + uy]}; };
+        std::vector<std::array<P2, 3>> cover;
+        for (size_t j = 0; j < k; ++j) {
+            if (!samePlane(planes[j], planes[k]) || std::find(dropped.begin(), dropped.end(), tris[j]) != dropped.end()) continue;
+            P2 L[3];
+            proj(tris[j], L);
+            cover.push_back({L[0], L[1], L[2]});
+        }
+        if (cover.empty()) continue;
+        P2 T[3];
+        proj(tris[k], T);
+        if (coveredBy(T, cover)) dropped.push_back(tris[k]);
+    }
+    return dropped;
+}
 
 void makePlaneRecord(const float v0[3], const float v1[3], const float v2[3], int id, int flags, float rec[16])
 {
@@ -141,9 +229,38 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
         makePlaneRecord(tris9 + 9 * size_t(t), tris9 + 9 * size_t(t) + 3, tris9 + 9 * size_t(t) + 6, t, emitterFlags ? emitterFlags[t] : 0, &recs[16 * size_t(t)]);
     std::vector<float> block;
     SmallBlockInfo bi;
-    const bool ok = buildSmallBlock(recs.data(), n, block, &bi, tris9, 3 * n); // hull = the triangles' own vertices
+    const bool ok = buildSmallBlock(recs.data(), n, block, &bi, tris9, 3 * n, nullptr, tris9); // hull = the triangles' own vertices
     if (info) *info = bi;
     if (!ok) return 1;
+    // coplanar duplicates the builder may leave out: inside the union of earlier coplanar triangles of the same list. Checked
+    // independently of the clipping code: a few interior sample points of each dropped triangle must lie inside an earlier,
+    // kept, coplanar triangle.
+    std::vector<int> allList, occList;
+    for (int t = 0; t < n; ++t) { allList.push_back(t); if (!(emitterFlags && (emitterFlags[t] & 1))) occList.push_back(t); }
+    const std::vector<int> covAll = coveredCoplanarDuplicates(recs.data(), tris9, allList), covOcc = coveredCoplanarDuplicates(recs.data(), tris9, occList);
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int>& cov = pass ? covOcc : covAll;
+        const std::vector<int>& list = pass ? occList : allList;
+        for (int t : cov) {
+            const float* v = tris9 + 9 * size_t(t);
+            const double w3[4][3] = {{1 / 3.0, 1 / 3.0, 1 / 3.0}, {0.8, 0.1, 0.1}, {0.1, 0.8, 0.1}, {0.1, 0.1, 0.8}};
+            for (const auto& w : w3) {
+                const double P[3] = {w[0] * v[0] + w[1] * v[3] + w[2] * v[6], w[0] * v[1] + w[1] * v[4] + w[2] * v[7], w[0] * v[2] + w[1] * v[5] + w[2] * v[8]};
+                bool inside = false;
+                for (int j : list) {
+                    if (j >= t) break;
+                    if (std::find(cov.begin(), cov.end(), j) != cov.end()) continue;
+                    const float* a = &recs[16 * size_t(j)];
+                    const double u = a[4] * P[0] + a[5] * P[1] + a[6] * P[2] + a[7], vv = a[8] * P[0] + a[9] * P[1] + a[10] * P[2] + a[11];
+                    const double nl = std::sqrt(double(a[0]) * a[0] + double(a[1]) * a[1] + double(a[2]) * a[2]);
+                    const double dist = nl > 0 ? std::fabs(a[0] * P[0] + a[1] * P[1] + a[2] * P[2] - a[3]) / nl : 1e30;
+                    if (u >= -1e-6 && vv >= -1e-6 && u + vv <= 1.0 + 1e-6 && dist <= 1e-3 * std::fmax(1.0, std::fabs(P[0]) + std::fabs(P[1]) + std::fabs(P[2]))) { inside = true; break; }
+                }
+                if (!inside) return -1;
+            }
+        }
+    }
+    if (bi.nCovered != int(covAll.size())) return -1;
     auto asInt = [](float f) { int i; std::memcpy(&i, &f, 4); return i; };
     const int total = asInt(block[2]);
     if (size_t(total) * 4 != block.size() || total > kSmallBlockMaxF4) return -1;
@@ -186,7 +303,9 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
             // a non-emitter may be missing from the occluder section only if the whole scene lies on one side of its plane
             const bool pruned = sec == 1 && !emitter && seen[size_t(t)] == 0 && planeBoundsPoints(&recs[16 * size_t(t)], tris9, 3 * n);
             const bool expect = sec == 0 || !emitter;
-            if (seen[size_t(t)] != (expect ? 1 : 0) && !pruned) return -1;
+            const std::vector<int>& cov = sec == 0 ? covAll : covOcc;
+            const bool covered = seen[size_t(t)] == 0 && std::find(cov.begin(), cov.end(), t) != cov.end();
+            if (seen[size_t(t)] != (expect ? 1 : 0) && !pruned && !covered) return -1;
         }
     }
     return 0;
@@ -218,7 +337,7 @@ bool planeBoundsPoints(const float* rec, const float* points, int nPoints)
 }
 
 bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints, int nHullPoints,
-                     std::vector<int>* pruned)
+                     std::vector<int>* pruned, const float* tris9)
 {
     block.clear();
     if (nTris <= 0 || nTris > 64) return false;
@@ -241,6 +360,15 @@ bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block,
         }
         occ.push_back(t);
     }
+    // coplanar duplicates covered by earlier triangles of the same section can never change a result: leave them out
+    auto dropCovered = [&](std::vector<int>& list) {
+        const std::vector<int> gone = coveredCoplanarDuplicates(ftrisId, tris9, list);
+        for (int t : gone) list.erase(std::find(list.begin(), list.end(), t));
+        return int(gone.size());
+    };
+    bi.nCovered = dropCovered(all);
+    dropCovered(occ);
+    dropCovered(occFull);
     block.assign(4, 0.f);
     const size_t offAll = 1;
     int planesOcc = 0, recordsFull = 0;

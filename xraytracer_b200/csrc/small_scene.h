@@ -30,6 +30,7 @@ constexpr int kSmallBlockMaxF4 = 704; // shared-memory budget of the kernel (11 
 
 struct SmallBlockInfo {
     int nRecordsAll = 0, nRecordsOcc = 0, nPlanesAll = 0, nPruned = 0;
+    int nCovered = 0; // triangles left out of the closest-hit section because earlier coplanar triangles cover them
 };
 
 // Plane-equation record of one triangle (16 floats: N|d, n1|d1, n2|d2, id|flags|0|0 — the last two as int bits), computed in
@@ -48,7 +49,11 @@ int smallBlockSelftest(const float* tris9, const int* emitterFlags, int n, Small
 // closed room: the scene lies inside its half-space) can never be crossed by a segment between two such points, so it is
 // left out of the occluder section. Pass null when a light is infinitely far away (DistantLight) — its shadow rays leave the hull.
 bool buildSmallBlock(const float* ftrisId, int nTris, std::vector<float>& block, SmallBlockInfo* info, const float* hullPoints = nullptr,
-                     int nHullPoints = 0, std::vector<int>* pruned = nullptr);
+                     int nHullPoints = 0, std::vector<int>* pruned = nullptr, const float* tris9 = nullptr);
+// tris9 (9 floats per triangle, same order as ftrisId; may be null): enables the removal of coplanar duplicates that lie inside
+// the union of earlier triangles of the same plane — see coveredCoplanarDuplicates() in small_scene.cpp.
+// the triangles of `tris` (ascending indices into ftrisId / tris9) that lie inside the union of EARLIER coplanar triangles of the list
+std::vector<int> coveredCoplanarDuplicates(const float* ftrisId, const float* tris9, const std::vector<int>& tris);
 // signed distance of `point` to the plane of record `rec` (16 floats), positive on the side the triangle's normal e1 x e2 points to
 double planeSignedDistance(const float* rec, const float* point);
 // true if all points lie on one closed side of the plane of record `rec` (16 floats), within 1e-5 of the points' extent

@@ -79,7 +79,7 @@ inline std::string trim(const std::string& s)
 inline int fixIndex(int idx, int n)
 {
     if (idx > 0) return idx - 1;
-    if (idx < 0) return n + idx;
+    if (idx < 0) return n + idx >= 0 ? n + idx : -2; // relative index before the first element: invalid (-2), not "absent" (-1)
     return -1;
 }
 
@@ -205,6 +205,18 @@ inline bool load(const std::string& path, const std::string& mtlDir, Result& out
             if (face.size() < 3) {
                 out.warning += "degenerate face ignored\n";
                 continue;
+            }
+            // every resolved index must name an existing attribute: a position is mandatory (0, missing or out of range is a
+            // load error, like tinyobj's), texcoord / normal indices are optional (-1) but, when given, must exist too
+            for (const Index& ix : face) {
+                if (ix.vertex_index < 0 || ix.vertex_index >= nv) {
+                    out.error = "face references vertex " + std::to_string(ix.vertex_index + 1) + " but only " + std::to_string(nv) + " are defined: " + line;
+                    return false;
+                }
+                if (ix.texcoord_index >= nvt || ix.texcoord_index < -1 || ix.normal_index >= nvn || ix.normal_index < -1) {
+                    out.error = "face references a texture coordinate / normal that is not defined: " + line;
+                    return false;
+                }
             }
             for (size_t k = 1; k + 1 < face.size(); ++k) {
                 cur.mesh.indices.push_back(face[0]);

@@ -138,3 +138,26 @@ def test_pure_python_scene_description_equals_host_scene():
     a, _, _ = api.ReferenceScene(hm.flatten()).render(cam_h, W, H, 2, capi.INT_GI, 3)
     b, _, _ = api.ReferenceScene(fm.desc()).render(cam_f, W, H, 2, capi.INT_GI, 3)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_malformed_obj_indices_are_load_errors(tmp_path):
+    """Face tokens that are 0, missing, out of range or reach before the first element used to become out-of-bounds reads in
+    Scene::loadObj; they are load errors now (like the tinyobj-based reference, scene.cpp:52-64). Normals on only some vertices
+    of a face fall back to the flat normal."""
+    base = "v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nnewmtl m\n"
+    (tmp_path / "m.mtl").write_text("newmtl m\nKd 1 1 1\n")
+    head = "mtllib m.mtl\no a\nusemtl m\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\n"
+    for k, face in enumerate(["f 1 2 4", "f 0 1 2", "f 1 2 -4", "f 1//2 2//1 3//1", "f 1/5 2 3"]):
+        path = tmp_path / f"bad{k}.obj"
+        path.write_text(head + face + "\n")
+        s = scenes.HostScene()
+        with pytest.raises(RuntimeError, match="face references"):
+            s.load_obj(path)
+    good = tmp_path / "partial.obj"
+    good.write_text(head + "f 1//1 2 3\n")     # a normal on one vertex only -> flat normal for the face
+    s = scenes.HostScene()
+    s.load_obj(good)
+    d = s.flatten().contents
+    assert d.n_triangles == 1
+    t = d.triangles[0]
+    assert list(t.n0) == list(t.n1) == list(t.n2) == [0.0, 0.0, 1.0]

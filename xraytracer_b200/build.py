@@ -62,7 +62,7 @@ def build_gpu(force=False, verbose=False) -> Path:
                 if verbose:
                     print(log)
     if force or jobs or _stale(out, objs):
-        _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-Xcompiler", "-fopenmp", "-o", out] + objs + ["-lgomp"])
+        _run([NVCC] + ARCH + ["-shared", "-ccbin", CXX, "-Xcompiler", "-fopenmp", "-o", out] + objs + ["-lgomp", "-ldl"])
     return out
 
 

@@ -158,6 +158,7 @@ int xrtg_scene_create(const xrtg_scene_desc* d, int device, xrtg_scene** out) { 
 
 int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flags, xrtg_scene** out)
 {
+    NvtxRange nvtx("xrtg_scene_create: ingest + BVH + upload");
     if (!out) return fail(XRTG_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (int rc = checkDesc(d)) return rc;
@@ -831,6 +832,7 @@ namespace xrt {
 // The whole render on `st`, result (mean or sum) written to device buffer `out`.
 int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats)
 {
+    NvtxRange nvtx("xrtg_render: wave scheduler");
     const bool exact = (p->flags & XRTG_FLAG_EXACT) != 0;
     const bool count = (p->flags & XRTG_FLAG_COUNTERS) != 0;
     const bool brute = (p->flags & XRTG_FLAG_BRUTE_FORCE) != 0;
@@ -898,6 +900,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
 
     for (uint32_t pix0 = 0; pix0 < nPixels; pix0 += tile)
     for (uint32_t done = 0; done < uint32_t(p->spp); done += S) {
+        NvtxRange nvtxWave("wave: primary / bounces / accumulate");
         const uint32_t sw = std::min<uint32_t>(S, uint32_t(p->spp) - done);
         w.pixelBase = pix0;
         w.wavePixels = std::min<uint32_t>(tile, nPixels - pix0);

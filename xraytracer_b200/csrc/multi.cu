@@ -218,6 +218,7 @@ int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params*
     for (int g = 0; g < G; ++g)
         if (rcs[size_t(g)]) return fail(rcs[size_t(g)], "device " + std::to_string(s->replicas[size_t(g)]->device) + ": " + errs[size_t(g)]);
 
+    NvtxRange nvtx("multi-GPU: fused peer-memory reduce + finalize");
     // ---- fused reduce + finalize over peer memory ----
     const int divisor = (p->flags & XRTG_FLAG_SUM_ONLY) ? 0 : (p->spp_total > 0 ? p->spp_total : p->spp);
     float* finalImg = static_cast<float*>(s->multiOut.p);

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost a function-pointer test unless a profiler is attached
 #include <xrtgpu.h>
 #include "device_types.h"
 
@@ -102,6 +103,12 @@ struct PlainBuf {
         return 0;
     }
     ~PlainBuf() { if (p) cudaFree(p); }
+};
+
+// NVTX range over a scope (nsys / ncu timelines: scene ingest, every wave of a render, the multi-GPU reduce)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 struct Timer {

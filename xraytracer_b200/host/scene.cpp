@@ -37,11 +37,11 @@ void Scene::loadObj(const std::filesystem::path& filepath)
                     N.emplace_back(A.normals[3 * idx.normal_index], A.normals[3 * idx.normal_index + 1], A.normals[3 * idx.normal_index + 2]);
                 if (idx.texcoord_index >= 0) T.emplace_back(A.texcoords[2 * idx.texcoord_index], A.texcoords[2 * idx.texcoord_index + 1]);
             }
-            if (N.empty()) { // flat normal from the winding (scene.cpp:118-125)
+            if (N.size() != fv) { // no normals (or normals on only some vertices): flat normal from the winding (scene.cpp:118-125)
                 const Vec3f n = normalize(cross(P[1] - P[0], P[2] - P[0]));
                 N = {n, n, n};
             }
-            if (T.empty()) T = {Vec2f(0, 0), Vec2f(1, 0), Vec2f(0, 1)};
+            if (T.size() != fv) T = {Vec2f(0, 0), Vec2f(1, 0), Vec2f(0, 1)};
             if (materialID == -1) materialID = shape.mesh.material_ids[f]; // first face decides (scene.cpp:135-144)
             prims.emplace_back(P, N, T);
             off += fv;

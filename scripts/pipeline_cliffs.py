@@ -1,6 +1,6 @@
 """Throughput on both sides of every limit that switches the render pipeline (api.cu: choosePipeline):
    64 / 66 mesh triangles   fused k_bounce_small  ->  k_primary + shade + connect + extend (simple kernels, shared-memory triangle loops off)
-   8 / 9 area lights        fused k_bounce_small  ->  three-kernel pipeline (one shadow-queue entry per light)
+   16 / 17 area lights      fused k_bounce_small  ->  three-kernel pipeline (one shadow-queue entry per light)
    <= 512 / > 512 BVH nodes simple run-to-completion kernels -> raygen + k_trace8 (resumable traversal of the eight-child tree)
 GI depth 3, 1920x1080, 16 spp, throughput instantiation. usage: python scripts/pipeline_cliffs.py  (prints a markdown table)"""
 import sys
@@ -36,8 +36,8 @@ def room(n_extra_quads, n_lights):
         t += quad(c, (8, 0, 2), (0, 1, 8))
     s.add_mesh("geo", np.array(t), (0.7, 0.7, 0.7))
     for k in range(n_lights):
-        x = 8.0 + 9.0 * k
-        s.add_quad_light(f"L{k}", (x + 6, 99.5, 40), (x + 6, 99.5, 60), (x, 99.5, 40), (30.0, 30.0, 30.0))   # faces down
+        x = 4.0 + 5.4 * k
+        s.add_quad_light(f"L{k}", (x + 4, 99.5, 40), (x + 4, 99.5, 60), (x, 99.5, 40), (30.0, 30.0, 30.0))   # faces down
     return s
 
 
@@ -49,9 +49,9 @@ def sphere_room(nt):
 W, H, SPP = 1920, 1080, 16
 rows = []
 cases = [("27 quads + 1 light (64 triangles incl. light proxy)", room(26, 1), scenes.make_camera(W, H, [-1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 50.0, 50.0, -140.0, 1], 50.0)),
-         ("28 quads + 1 light (66 triangles)", room(27, 1), None), ("12 quads + 8 lights", room(7, 8), None), ("12 quads + 9 lights", room(7, 9), None)]
+         ("28 quads + 1 light (66 triangles)", room(27, 1), None), ("12 quads + 8 lights", room(7, 8), None), ("12 quads + 16 lights", room(7, 16), None), ("12 quads + 17 lights", room(7, 17), None)]
 cam_room = cases[0][2]
-for nt in (14, 15, 16, 17):
+for nt in (19, 20, 21, 22):
     cases.append((f"Cornell box + {2 * nt * nt}-triangle sphere", sphere_room(nt), scenes.make_camera(W, H)))
 for name, host, cam in cases:
     cam = cam or cam_room

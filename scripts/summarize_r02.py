@@ -104,12 +104,16 @@ if rep.exists():
           "Source: `ncu --set full --clock-control none --import-source on` on `scripts/profile_step.py c3 8` (Cornell GI depth 3, 1080p, waves of 4 spp = 8.29 M paths),",
           "joined per SASS instruction with `nvdisasm -gi` line info by `scripts/ncu_phase_budget.py` (phase = source line ranges in `profiles/phases/k_bounce_small.json`).",
           "`warp instr` = `Instructions Executed` summed over the phase's SASS instructions; `per unit` = per warp-tile of 32 queue entries.\n"]
-    for i, (b, entries) in enumerate(((0, None), (1, None), (2, None)), start=1):
+    # (the capture window starts one launch early: launches 2, 3, 4 of the capture are bounce 0, 1, 2 of one wave)
+    for i, (b, entries) in enumerate(((0, None), (1, None), (2, None)), start=2):
         md.append(f"## bounce {b}\n")
         md.append(budget(rep, "k_bounce_small", i, "4fast14k_bounce_smallILb1", "k_bounce_small.json"))
     (P / "r02_budget_bounce_small.md").write_text("\n".join(md))
+rep = G / "r2_prof_c3_primary.ncu-rep"
+if rep.exists():
     md = ["# k_primary — per-phase instruction budget (round 2, final build: screen-space candidate masks)\n",
-          "Same capture as `r02_budget_bounce_small.md`.\n", budget(rep, "k_primary<", 1, "4fast9k_primaryILb0ELb0", "k_primary.json")]
+          "Source: `ncu --set full` on `scripts/profile_step.py c3 8`, one wave of 4 spp = 8.29 M paths (36 % of them outside the scissor).\n",
+          budget(rep, "k_primary<", 1, "4fast9k_primaryILb0ELb0", "k_primary.json")]
     (P / "r02_budget_primary.md").write_text("\n".join(md))
 rep = G / "r2_prof_c4_final.ncu-rep"
 if rep.exists():

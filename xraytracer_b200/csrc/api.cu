@@ -810,7 +810,7 @@ Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, b
     const bool volume = integ == XRTG_INT_VOLUME || integ == XRTG_INT_VOLUME_NEE;
     P.volumePaths = P.fusedPrimary && volume && s->ds.nMedia <= 8 && s->ds.nGrids <= 8 && tv(t.volume_paths, 1) != 0;
     P.fusedBounce = P.fusedPrimary && P.small && !brute && P.bruteSecondary && P.bruteShadow && tv(t.fused_bounce, 1) != 0 &&
-                    s->ds.nPrims <= 96 && s->ds.nLights <= 8 && // what k_bounce_small stages in shared memory (kSmallPrims / kSmallLights)
+                    s->ds.nPrims <= 96 && s->ds.nLights <= 16 && // what k_bounce_small stages in shared memory (kSmallPrims / kSmallLights)
                     (integ == XRTG_INT_DIRECT || integ == XRTG_INT_WHITTED || integ == XRTG_INT_INDIRECT || integ == XRTG_INT_GI);
     return P;
 }

@@ -216,7 +216,7 @@ __device__ __forceinline__ bool bruteTris(const DScene& sc, V3 o, V3 d, Hit& h, 
 constexpr int kSmallSceneTris = 64;
 constexpr int kSmallBlockF4 = 704; // = kSmallBlockMaxF4 (small_scene.h)
 constexpr int kSmallPrims = 96;    // shading records / area lights k_bounce_small stages in shared memory (the host uses that
-constexpr int kSmallLights = 8;    // kernel only below these limits)
+constexpr int kSmallLights = 16;   // kernel only below these limits)
 template <bool ANY, bool OCCLUDERS_ONLY = false>
 __device__ __forceinline__ bool smallSceneTris(const float4* __restrict__ st, int n, V3 o, V3 d, Hit& h, int minId)
 {

@@ -178,12 +178,6 @@ __global__ void __launch_bounds__(kBlock, MINB) k_trace8(DScene sc, DQueues q, i
                     const uint32_t nodeIdx = r.gBase + __popc((r.gBits >> 8) & ((1u << slot) - 1u));
                     if ((rest & 0xffu) != 0u) push8(sstack, lstack, r.sp, r.gBase, rest);   // the siblings wait on the stack as ONE entry
                     nodeStep8<COUNT>(sc, r, nodeIdx, tc);
-                    // the triangle tests of this node wait for the warp's next triangle round: pull the first hit triangle's line
-                    // (two 64 B records) towards L1 now, off the critical path (the triangle fetch was 25 % of the stall samples)
-                    if (r.tBits != 0u) {
-                        const float4* first = tris + 4 * size_t(r.tBase + __popc(r.tValid & ((1u << (__ffs(r.tBits) - 1u)) - 1u)));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(first));
-                    }
                 }
                 // ---- triangle phase: postponed until enough lanes have some (or nobody can advance through nodes) ----
                 const bool hasTri = active && r.tBits != 0u;

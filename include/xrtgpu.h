@@ -265,7 +265,7 @@ typedef struct xrtg_scene_info {
     uint64_t device_bytes; /* scene data resident in HBM      */
     uint64_t upload_bytes; /* bytes copied H2D by an upload    */
     float bvh_build_ms;    /* the BVH builder alone (host SAH, or the GPU LBVH kernels incl. their sort) */
-    int32_t bvh_builder;   /* 0 = host binned SAH, 1 = GPU linear BVH                                    */
+    int32_t bvh_builder;   /* 0 = host binned SAH, 1 = GPU linear BVH, 2 = GPU PLOC (device ingest + build + collapse) */
     int32_t small_records_all, small_records_occ; /* plane-paired triangle records (80 B each) of a small scene's closest-hit /
                                                      occluder sections; 0 = no block (per-triangle lists or BVH only)  */
     int32_t small_flagged;  /* small scenes: primitives whose shadow rays can start behind a hull-pruned plane (they test the
@@ -292,21 +292,36 @@ typedef struct xrtg_tuning {
     int32_t workspace_mb;    /* byte budget of the per-wave queues (default 6144); small values force pixel-tiled waves       */
     int32_t stage_dump;      /* print every stage's CUDA-event time to stderr (with XRTG_FLAG_STAGE_TIMES)                    */
     int32_t primary_masks;   /* small scenes: screen-space candidate masks for the primary rays (1) or the BVH walk (0)       */
-    int32_t reserved[3];
+    int32_t gpu_build;       /* creation time only (XRT_TUNING): 1 = as if XRTG_BUILD_GPU were passed, 0 = never build on the device */
+    int32_t ploc_radius;     /* creation time only: PLOC neighbour-search radius (default 16)                                 */
+    int32_t ploc_ct_x16;     /* creation time only: SAH traversal-step cost of the PLOC leaf decision, in 1/16 (default 16)   */
+    int32_t ploc_top;        /* creation time only: clusters at which PLOC hands over to the top-level sweep SAH (default 1024) */
+    int32_t ploc_weight;     /* creation time only: top-level sweep SAH weighs a side by its triangles (0) or clusters (1, default) */
 } xrtg_tuning;
 
 int xrtg_abi_version(void);
 int xrtg_device_count(void);
 const char* xrtg_last_error(void);
 
-/* Copies the PODs, builds the SAH BVH on the host, uploads everything to `device`. */
+/* Copies the PODs, builds the BVH (host binned SAH; on the device from 65536 mesh triangles on, see XRTG_BUILD_GPU), uploads
+ * everything to `device`. */
 int xrtg_scene_create(const xrtg_scene_desc* desc, int device, xrtg_scene** out);
 
 enum {
     /* Build the BVH ON THE GPU (linear BVH: Morton codes, radix sort, Karras radix tree, bottom-up fit) instead of the
      * host SAH builder: ~100x faster to build, a somewhat slower tree to traverse. Results are identical (any valid BVH
      * returns what the reference's brute-force loops return). */
-    XRTG_BUILD_LBVH_GPU = 1u << 0
+    XRTG_BUILD_LBVH_GPU = 1u << 0,
+    /* Ingest AND build on the device (csrc/gpu_build.cu): the raw triangle array is copied up once; the per-triangle records,
+     * a PLOC tree (parallel locally-ordered clustering over 63-bit Morton order, SAH-decided leaves of up to four triangles) and
+     * its collapse into eight-child quantised nodes are produced in HBM. Tens of milliseconds for a million triangles instead of
+     * the host path's ~0.5-1.3 s, and a tree that traverses like the host SAH one. No pinned staging copies are made until
+     * xrtg_scene_upload or a multi-GPU replica asks for them. This is the DEFAULT for scenes of 65536 mesh triangles or more; the
+     * flag lowers that threshold to 1024 (below it the host path is taken regardless: it is faster there). Inputs the clustering
+     * cannot handle (a tree deeper than the traversal stacks) fall back to the host builder. */
+    XRTG_BUILD_GPU = 1u << 1,
+    /* Force the host binned-SAH builder, whatever the size of the scene. */
+    XRTG_BUILD_HOST = 1u << 2
 };
 /* xrtg_scene_create with build flags. */
 int xrtg_scene_create2(const xrtg_scene_desc* desc, int device, uint32_t build_flags, xrtg_scene** out);
@@ -367,6 +382,13 @@ int xrtg_trace_primary(xrtg_scene* scene, const xrtg_camera* cam, int width, int
  * semantics (emitter proxies skipped) -> out_hits[i].prim = 0/1 occluded flag in prim>=0. */
 int xrtg_trace_rays(xrtg_scene* scene, int64_t n, const float* org, const float* dir, const float* tmax,
                     int any_hit, uint32_t flags, xrtg_hit* out_hits);
+
+/* Structural check of the acceleration structures RESIDENT ON THE DEVICE, whichever builder produced them: the two-child tree, the
+ * leaf-ordered triangles, the eight-child quantised tree and its node-ordered records are copied back and walked on the host —
+ * every triangle in exactly one leaf, every (decoded, margin-shrunk) child box contains the triangles below it, depths fit the
+ * traversal stacks. *n_errors = number of violations (xrtg_last_error() describes the first). Scenes of fewer than two mesh
+ * triangles have nothing to check. */
+int xrtg_scene_selfcheck(xrtg_scene* scene, int* n_errors);
 
 /* Host-only structural check of the SAH BVH builder (no CUDA device needed): builds the tree over n triangles (9 floats each:
  * v0 v1 v2) and verifies that every triangle is referenced by exactly one leaf, that every child box (minus the conservative

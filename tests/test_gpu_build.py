@@ -1,0 +1,185 @@
+"""Device-side ingest + PLOC build + eight-child collapse (csrc/gpu_build.cu, XRTG_BUILD_GPU).
+
+The reference has no acceleration structure (Scene::build() is an empty hook, scene.h:22-24; Scene::intersect / occluded are
+brute-force loops, scene.cpp:190-211), so every builder here is held to "returns exactly what the brute-force loops return", and
+the device ingest to "bit-identical records to the host ingest" (e1 / e2 / ng as primitive.cpp:105,142-143 computes them)."""
+import numpy as np
+import pytest
+
+from conftest import require_gpu
+from xraytracer_b200 import api, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _random_rays(n, lo, hi, seed):
+    rng = np.random.RandomState(seed)
+    org = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    tmax = rng.uniform(5, 700, n).astype(np.float32)
+    return org, d, tmax
+
+
+def _with_flat_normals(tris):
+    """(n, 3, 3) vertices -> (n, 18) = v0 v1 v2 n0 n1 n2 with the flat normal at every vertex."""
+    tris = np.asarray(tris, np.float32)
+    nrm = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.where(ln > 0, nrm / np.maximum(ln, 1e-30), np.array([[0, 1, 0]], np.float32)).astype(np.float32)
+    return np.concatenate([tris.reshape(-1, 9), np.tile(nrm, (1, 3))], 1).astype(np.float32)
+
+
+def _mesh_scene(nt=64, with_sphere=True):
+    def extra(h):
+        h.add_mesh("tess", scenes.displaced_sphere_tris((278, 200, 280), 150, nt, nt), (0.75, 0.75, 0.75))
+        if with_sphere:
+            h.add_sphere("ball", (120.0, 80.0, 400.0), 60.0, (0.5, 0.5, 0.5))
+    return scenes.cornell_box("quad", extra=extra)
+
+
+def test_device_build_equals_host_build_brute_force_and_oracle():
+    """8 k-triangle scene + analytic sphere: hits from the device-built tree == host SAH tree == GPU brute force == oracle;
+    the exact-mode images are bit-identical (same trisId / prims records, ties to the lowest primitive id) and so are the
+    throughput instantiation's primary hits INCLUDING t, u, v (same plane-equation records to the last bit)."""
+    require_gpu()
+    hs = _mesh_scene(64)  # (the description points into the host scene: keep it alive)
+    desc = hs.flatten()
+    host = api.GpuScene(desc, 0, build_flags=capi.BUILD_HOST)
+    dev = api.GpuScene(desc, 0, build_flags=capi.BUILD_GPU)
+    orc = api.OracleScene(desc)
+    di, hi = dev.info(), host.info()
+    assert di["bvh_builder"] == 2 and hi["bvh_builder"] == 0
+    assert di["wide_arity"] == 8 and di["n_wide_nodes"] > 0 and 2 <= di["bvh_depth"] <= 120
+    assert dev.selfcheck() == 0, getattr(dev, "last_selfcheck_error", "")
+    assert host.selfcheck() == 0, getattr(host, "last_selfcheck_error", "")
+    org, d, tmax = _random_rays(50000, 20, 530, 33)
+    a = dev.trace_rays(org, d)
+    assert np.array_equal(a, host.trace_rays(org, d))
+    assert np.array_equal(a, dev.trace_rays(org, d, flags=capi.FLAG_BRUTE_FORCE))
+    assert np.array_equal(a[:20000], orc.trace_rays(org[:20000], d[:20000]))
+    occ = dev.trace_rays(org, d, tmax, any_hit=True)["prim"]
+    assert np.array_equal(occ, host.trace_rays(org, d, tmax, any_hit=True)["prim"])
+    assert np.array_equal(occ[:20000], orc.trace_rays(org[:20000], d[:20000], tmax[:20000], any_hit=True)["prim"])
+    # the throughput instantiation on the eight-child tree: ids AND t/u/v identical between the two builds
+    fa = dev.trace_rays(org, d, flags=capi.FLAG_FAST_HOOK)
+    fb = host.trace_rays(org, d, flags=capi.FLAG_FAST_HOOK)
+    assert np.array_equal(fa, fb)
+    assert np.array_equal(dev.trace_rays(org, d, tmax, any_hit=True, flags=capi.FLAG_FAST_HOOK)["prim"],
+                          host.trace_rays(org, d, tmax, any_hit=True, flags=capi.FLAG_FAST_HOOK)["prim"])
+    assert (fa["prim"] != a["prim"]).mean() < 5e-3  # (edges between the small triangles; held to the oracle in test_gpu_fast_hooks.py)
+    cam = scenes.make_camera(96, 54)
+    for integ, depth in ((capi.INT_NORMAL, 1), (capi.INT_DIRECT, 1), (capi.INT_GI, 3)):
+        x, sx = dev.render(cam, 96, 54, 4, integ, depth, flags=capi.FLAG_EXACT)
+        y, sy = host.render(cam, 96, 54, 4, integ, depth, flags=capi.FLAG_EXACT)
+        assert np.array_equal(bits(x), bits(y))
+        assert (sx["closest_rays"], sx["shadow_rays"]) == (sy["closest_rays"], sy["shadow_rays"])
+    x, _ = dev.render(cam, 96, 54, 16, capi.INT_GI, 3, seed=5)
+    y, _ = host.render(cam, 96, 54, 16, capi.INT_GI, 3, seed=5)
+    assert np.array_equal(bits(x), bits(y)), "throughput path: same records + same RNG -> same image whichever tree is walked"
+    # pinned copies are made on demand: a re-upload must leave the results unchanged
+    dev.upload()
+    assert np.array_equal(dev.trace_rays(org[:4000], d[:4000]), a[:4000])
+    assert np.array_equal(dev.trace_rays(org[:4000], d[:4000], flags=capi.FLAG_FAST_HOOK), fa[:4000])
+    assert dev.check_guards() == 0
+
+
+def test_device_build_is_deterministic():
+    require_gpu()
+    hs = _mesh_scene(48, with_sphere=False)
+    desc = hs.flatten()
+    a = api.GpuScene(desc, 0, build_flags=capi.BUILD_GPU)
+    b = api.GpuScene(desc, 0, build_flags=capi.BUILD_GPU)
+    ia, ib = a.info(), b.info()
+    for k in ("n_bvh_nodes", "bvh_depth", "n_wide_nodes", "bvh_sah_cost"):
+        assert ia[k] == ib[k], k
+    cam = scenes.make_camera(80, 45)
+    x, sx = a.render(cam, 80, 45, 8, capi.INT_GI, 3, seed=11, flags=capi.FLAG_COUNTERS)
+    y, sy = b.render(cam, 80, 45, 8, capi.INT_GI, 3, seed=11, flags=capi.FLAG_COUNTERS)
+    assert np.array_equal(bits(x), bits(y))
+    assert sx["tris_tested"] == sy["tris_tested"], "the two-child tree (and the set of triangles a ray meets) is reproducible"
+
+
+@pytest.mark.parametrize("kind", ["soup", "grid", "duplicates", "sliver"])
+def test_device_build_on_awkward_inputs(kind):
+    """Random triangle soup (overlapping boxes everywhere), a perfectly regular grid and thousands of coincident triangles (every
+    neighbour distance ties: "ties to the lower index" would merge one pair per round, the symmetric pair hash merges a random
+    matching) and long slivers. All must pass the structural check and equal brute force (ties in t -> lowest primitive id)."""
+    require_gpu()
+    rng = np.random.RandomState(7)
+    if kind == "soup":
+        c = rng.uniform(0, 500, (6000, 1, 3))
+        tris = (c + rng.normal(scale=25.0, size=(6000, 3, 3))).astype(np.float32)
+    elif kind == "grid":
+        n = 48
+        xs, zs = np.meshgrid(np.arange(n, dtype=np.float32) * 10, np.arange(n, dtype=np.float32) * 10)
+        p00 = np.stack([xs, np.zeros_like(xs), zs], -1).reshape(-1, 3)
+        dx, dz = np.array([10, 0, 0], np.float32), np.array([0, 0, 10], np.float32)
+        tris = np.concatenate([np.stack([p00, p00 + dx, p00 + dz], 1), np.stack([p00 + dx, p00 + dx + dz, p00 + dz], 1)]).astype(np.float32)
+    elif kind == "duplicates":
+        one = np.array([[[100, 100, 100], [200, 100, 100], [100, 200, 150]]], np.float32)
+        tris = np.concatenate([np.repeat(one, 3000, 0), (rng.uniform(0, 500, (500, 1, 3)) + rng.normal(scale=10, size=(500, 3, 3))).astype(np.float32)])
+    else:
+        a = rng.uniform(0, 500, (3000, 3))
+        dirs = rng.normal(size=(3000, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        tris = np.stack([a, a + 400 * dirs, a + 400 * dirs + rng.normal(scale=0.5, size=(3000, 3))], 1).astype(np.float32)
+    h = scenes.HostScene()
+    h.add_mesh("m", _with_flat_normals(tris), (0.7, 0.7, 0.7))
+    h.add_quad_light("L", (213, 548, 227), (343, 548, 227), (213, 548, 332), (25, 25, 25))
+    g = api.GpuScene(h.flatten(), 0, build_flags=capi.BUILD_GPU)
+    info = g.info()
+    assert info["bvh_builder"] == 2 and info["bvh_depth"] <= 120, info
+    assert g.selfcheck() == 0, getattr(g, "last_selfcheck_error", "")
+    org, d, tmax = _random_rays(20000, -50, 550, 3)
+    a = g.trace_rays(org, d)
+    assert np.array_equal(a, g.trace_rays(org, d, flags=capi.FLAG_BRUTE_FORCE))
+    assert np.array_equal(g.trace_rays(org, d, tmax, any_hit=True)["prim"], g.trace_rays(org, d, tmax, any_hit=True, flags=capi.FLAG_BRUTE_FORCE)["prim"])
+    f = g.trace_rays(org, d, flags=capi.FLAG_FAST_HOOK)
+    hit = a["prim"] >= 0
+    assert hit.mean() > 0.05
+    # throughput records on the eight-child tree: the same triangle except on edges / coplanar overlaps (soup and duplicates overlap a lot)
+    assert ((f["prim"] >= 0) != hit).mean() < 2e-3
+    if kind in ("grid", "sliver"):
+        assert (f["prim"] != a["prim"]).mean() < 2e-3
+
+
+def test_small_meshes_take_the_host_path_even_when_asked_for_the_device_build():
+    require_gpu()
+    hs = scenes.cornell_box("quad")
+    g = api.GpuScene(hs.flatten(), 0, build_flags=capi.BUILD_GPU)
+    assert g.info()["bvh_builder"] == 0 and g.info()["small_records_all"] > 0
+
+
+def test_device_build_full_size_scene_and_replicas():
+    """999,698 triangles: device build == host SAH tree on random rays (exact and throughput instantiations), structural check,
+    creation time; the same handle replicated onto a second 'device' (device 0 listed twice) renders the split + fused reduce."""
+    require_gpu()
+    hs = scenes.cornell_mesh_scene(707, 707)
+    desc = hs.flatten()
+    dev = api.GpuScene(desc, 0, build_flags=capi.BUILD_GPU)
+    host = api.GpuScene(desc, 0, build_flags=capi.BUILD_HOST)
+    di = dev.info()
+    assert di["bvh_builder"] == 2 and di["wide_arity"] == 8 and di["bvh_depth"] <= 120
+    assert di["build_ms"] < 0.5 * host.info()["build_ms"], (di["build_ms"], host.info()["build_ms"])
+    assert dev.selfcheck() == 0, getattr(dev, "last_selfcheck_error", "")
+    org, d, tmax = _random_rays(30000, 30, 520, 8)
+    a = dev.trace_rays(org, d)
+    assert np.array_equal(a, host.trace_rays(org, d))
+    assert np.array_equal(a[:4096], dev.trace_rays(org[:4096], d[:4096], flags=capi.FLAG_BRUTE_FORCE))
+    assert np.array_equal(dev.trace_rays(org, d, tmax, any_hit=True)["prim"], host.trace_rays(org, d, tmax, any_hit=True)["prim"])
+    assert np.array_equal(dev.trace_rays(org, d, flags=capi.FLAG_FAST_HOOK), host.trace_rays(org, d, flags=capi.FLAG_FAST_HOOK))
+    cam = scenes.make_camera(240, 135)
+    x, _ = dev.render(cam, 240, 135, 8, capi.INT_GI, 3, seed=3)
+    y, _ = host.render(cam, 240, 135, 8, capi.INT_GI, 3, seed=3)
+    assert np.array_equal(bits(x), bits(y))
+    del host
+    multi = api.GpuScene(desc, devices=[0, 0], build_flags=capi.BUILD_GPU)
+    assert multi.device_count() == 2 and multi.info()["bvh_builder"] == 2
+    z, st = multi.render(cam, 240, 135, 8, capi.INT_GI, 3, seed=3)
+    assert st["n_devices"] == 2
+    assert np.allclose(z, x, rtol=2e-5, atol=1e-6)

@@ -65,6 +65,14 @@ class GpuScene:
         self._chk(self.lib.xrtg_scene_check_guards(self.h, C.byref(n)), "xrtg_scene_check_guards")
         return n.value
 
+    def selfcheck(self) -> int:
+        """Structural check of the device-resident trees (xrtg_scene_selfcheck); returns the number of violations."""
+        n = C.c_int()
+        self._chk(self.lib.xrtg_scene_selfcheck(self.h, C.byref(n)), "xrtg_scene_selfcheck")
+        if n.value:
+            self.last_selfcheck_error = self.lib.xrtg_last_error().decode()
+        return n.value
+
     def device_count(self) -> int:
         return self.lib.xrtg_scene_device_count(self.h)
 

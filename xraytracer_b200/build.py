@@ -47,7 +47,7 @@ def build_gpu(force=False, verbose=False) -> Path:
     # exact: no FMA contraction, IEEE div/sqrt (parity). fast: FMA + approximate div/sqrt/sin/cos/log/exp — it is an independent
     # Monte-Carlo estimate anyway (counter RNG) and is validated statistically against the oracle.
     fast_flags = os.environ.get("XRT_FAST_FLAGS", "-use_fast_math").split()
-    units = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", fast_flags), ("api.cu", []), ("multi.cu", []), ("lbvh.cu", []), ("bvh.cpp", []), ("small_scene.cpp", [])]
+    units = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", fast_flags), ("api.cu", []), ("multi.cu", []), ("lbvh.cu", []), ("gpu_build.cu", []), ("bvh.cpp", []), ("small_scene.cpp", [])]
     objs = []
     jobs = []
     for src, extra in units:

@@ -110,19 +110,18 @@ class SceneInfo(C.Structure):
 
 
 TUNING_KEYS = ["fused_bounce", "volume_paths", "scissor", "brute_secondary", "brute_shadow", "thr_ext0", "thr_ext", "thr_con",
-               "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump", "primary_masks"]
+               "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump", "primary_masks",
+               "gpu_build", "ploc_radius", "ploc_ct_x16", "ploc_top", "ploc_weight"]
 
 
 class Tuning(C.Structure):
     """xrtg_tuning: development / test switches of the pipeline selection; -1 = the measured default."""
-    _fields_ = [(k, C.c_int32) for k in TUNING_KEYS] + [("reserved", C.c_int32 * 3)]
+    _fields_ = [(k, C.c_int32) for k in TUNING_KEYS]
 
     def __init__(self, **kw):
         super().__init__()
         for k in TUNING_KEYS:
             setattr(self, k, int(kw.pop(k, -1)))
-        for i in range(3):
-            self.reserved[i] = -1
         if kw:
             raise TypeError(f"unknown tuning keys: {sorted(kw)}")
 
@@ -135,14 +134,14 @@ OBJ_MESH, OBJ_SPHERE, OBJ_BOX = 0, 1, 2
 LIGHT_QUAD, LIGHT_TRIANGLE, LIGHT_SPHERE = 0, 1, 2
 MEDIUM_HOMOGENEOUS_MIS, MEDIUM_HOMOGENEOUS_ACHROMATIC, MEDIUM_HOMOGENEOUS_NOMIS, MEDIUM_HETEROGENEOUS = range(4)
 ABI_VERSION = 2
-BUILD_LBVH_GPU = 1
+BUILD_LBVH_GPU, BUILD_GPU, BUILD_HOST = 1, 2, 4
 
 # every symbol include/xrtgpu.h declares (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg_scene_create", "xrtg_scene_create2", "xrtg_scene_upload",
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
                "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest", "xrtg_small_scene_selftest", "xrtg_scene_create_multi",
                "xrtg_scene_device_count", "xrtg_scene_set_tuning", "xrtg_exchange_buffer", "xrtg_ipc_export", "xrtg_ipc_open",
-               "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8", "xrtg_scene_check_guards"]
+               "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8", "xrtg_scene_check_guards", "xrtg_scene_selfcheck"]
 
 GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
 HOST_LIB = PKG / "host" / "libxrthost.so"
@@ -190,6 +189,7 @@ def gpu():
     lib.xrtg_scene_device_count.argtypes = [VP]
     lib.xrtg_scene_set_tuning.argtypes = [VP, P(Tuning)]
     lib.xrtg_scene_check_guards.argtypes = [VP, P(C.c_int)]
+    lib.xrtg_scene_selfcheck.argtypes = [VP, P(C.c_int)]
     lib.xrtg_exchange_buffer.argtypes = [VP, C.c_int, C.c_size_t, P(VP)]
     lib.xrtg_ipc_export.argtypes = [VP, VP]
     lib.xrtg_ipc_open.argtypes = [VP, VP, P(VP)]

@@ -19,6 +19,7 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "lbvh.h"
+#include "gpu_build.h"
 #include "scene_impl.h"
 
 using namespace xrt;
@@ -56,12 +57,24 @@ xrtg_scene::~xrtg_scene()
 
 namespace xrt {
 
-int uploadAll(xrtg_scene* s)
+int materializeHost(xrtg_scene* s)
+{
+    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    CU(cudaSetDevice(s->device));
+    for (Mirror* m : all)
+        if (int rc = m->ensureHost()) return rc;
+    return 0;
+}
+
+int uploadAll(xrtg_scene* s, bool materialize)
 {
     Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
     size_t total = 0;
+    if (materialize)
+        if (int rc = materializeHost(s)) return rc;
     for (Mirror* m : all) {
-        if (m->bytes) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
+        // (arrays produced on the device have no host copy until someone asks for a re-upload or a replica)
+        if (m->bytes && m->h) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
         total += m->bytes;
     }
     for (auto& g : s->gridData) {
@@ -106,7 +119,10 @@ const TuningKey kTuningKeys[] = {
     {"thr_ext", &xrtg_tuning::thr_ext}, {"thr_con", &xrtg_tuning::thr_con}, {"steps_per_vote", &xrtg_tuning::steps_per_vote},
     {"leaf_threshold", &xrtg_tuning::leaf_threshold}, {"thr_vol", &xrtg_tuning::thr_vol}, {"spv_vol", &xrtg_tuning::spv_vol},
     {"wide_bvh", &xrtg_tuning::wide_bvh}, {"primary_masks", &xrtg_tuning::primary_masks}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
-    {"stage_dump", &xrtg_tuning::stage_dump}};
+    {"stage_dump", &xrtg_tuning::stage_dump}, {"gpu_build", &xrtg_tuning::gpu_build}, {"ploc_radius", &xrtg_tuning::ploc_radius},
+    {"ploc_ct_x16", &xrtg_tuning::ploc_ct_x16}, {"ploc_top", &xrtg_tuning::ploc_top}, {"ploc_weight", &xrtg_tuning::ploc_weight}};
+constexpr int kGpuBuildMinTris = 1024;   // below this the device build is refused: the host path is faster than its launches and synchronisations
+constexpr int kGpuBuildAutoTris = 65536; // from here on the device build is the default
 
 void tuningFromEnvironment(Tuning& tu)
 {
@@ -194,21 +210,34 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         else if (o.kind == XRTG_OBJ_SPHERE) nSph++;
         else nBox++;
     }
-    if (int rc = s->prims.alloc(sizeof(float4) * 4 * size_t(std::max(nPrims, 1)))) return rc;
-    if (int rc = s->trisId.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
-    if (int rc = s->tris.alloc(sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
-    if (int rc = s->ftris.alloc(sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
-    if (int rc = s->ftrisId.alloc(sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
+    // Device-side ingest + build (gpu_build.cu) for meshes large enough to pay for it: the raw triangles go up once and every
+    // derived array is produced in HBM — no pinned staging copies (they are materialised lazily, on the first xrtg_scene_upload
+    // or replica), no host loops over the triangles.
+    // Default: meshes of kGpuBuildAutoTris triangles or more are built on the device (faster to build AND to traverse, measured
+    // on the 1 M-triangle workload); XRTG_BUILD_GPU lowers the threshold to kGpuBuildMinTris, XRTG_BUILD_HOST / _LBVH_GPU or the
+    // tuning switch gpu_build=0 keep the other builders.
+    const bool otherBuilder = (build_flags & (XRTG_BUILD_HOST | XRTG_BUILD_LBVH_GPU)) != 0;
+    const bool askedGpu = (build_flags & XRTG_BUILD_GPU) != 0 || s->tuning.t.gpu_build > 0;
+    const bool gpuBuild = !otherBuilder && ((askedGpu && nMeshTris >= kGpuBuildMinTris) || (s->tuning.t.gpu_build != 0 && nMeshTris >= kGpuBuildAutoTris));
+    auto allocArr = [&](Mirror& m, size_t bytes) { return gpuBuild ? m.allocDevice(bytes) : m.alloc(bytes); };
+    if (int rc = allocArr(s->prims, sizeof(float4) * 4 * size_t(std::max(nPrims, 1)))) return rc;
+    if (int rc = allocArr(s->trisId, sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = allocArr(s->tris, sizeof(float4) * 3 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = allocArr(s->ftris, sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
+    if (int rc = allocArr(s->ftrisId, sizeof(float4) * 4 * size_t(std::max(nMeshTris, 1)))) return rc;
     if (int rc = s->spheres.alloc(sizeof(float4) * 2 * size_t(std::max(nSph, 1)))) return rc;
     if (int rc = s->boxes.alloc(sizeof(float4) * 2 * size_t(std::max(nBox, 1)))) return rc;
-    lap("pinned + device allocation");
-    std::memset(s->prims.h, 0, s->prims.bytes);
-    float4* prims = static_cast<float4*>(s->prims.h);
+    lap(gpuBuild ? "device allocation" : "pinned + device allocation");
+    if (!gpuBuild) std::memset(s->prims.h, 0, s->prims.bytes);
+    float4* prims = static_cast<float4*>(s->prims.h); // (host-side arrays: NULL in the device-build path)
     float4* trisId = static_cast<float4*>(s->trisId.h);
     float4* ftrisId = static_cast<float4*>(s->ftrisId.h);
     float4* sph = static_cast<float4*>(s->spheres.h);
     float4* box = static_cast<float4*>(s->boxes.h);
-    std::vector<float> buildTris(size_t(nMeshTris) * 9);
+    std::vector<float> buildTris(gpuBuild ? 0 : size_t(nMeshTris) * 9);
+    std::vector<MeshRange> meshRanges;          // device-build path: one entry per mesh object
+    std::vector<int> extraIds;                   // ... shading records of the spheres / boxes, scattered after the ingest kernel
+    std::vector<float4> extraRecs;
     int ti = 0, si = 0, bi = 0;
     for (int i = 0; i < d->n_objects; ++i) {
         const xrtg_object& o = d->objects[i];
@@ -221,7 +250,17 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         meta |= uint32_t(o.area_light + 1) << kMetaLightShift;
         meta |= uint32_t(o.medium + 1) << kMetaMediumShift;
         const float4 rec3 = make_float4(alb[0], alb[1], alb[2], asF(meta));
-        if (o.kind == XRTG_OBJ_MESH) {
+        if (o.kind == XRTG_OBJ_MESH && gpuBuild) {
+            if (o.count > 0) {
+                MeshRange mr{};
+                mr.srcFirst = o.first; mr.triStart = ti; mr.id0 = firstPrim[i]; mr.emitter = o.area_light >= 0 ? 1 : 0;
+                std::memcpy(mr.albedo, alb, 12);
+                mr.meta = meta;
+                meshRanges.push_back(mr);
+            }
+            ti += o.count;
+        }
+        else if (o.kind == XRTG_OBJ_MESH) {
             const int ti0 = ti, id0 = firstPrim[i], emitter = o.area_light >= 0 ? 1 : 0;
             const xrtg_triangle* src = d->triangles + o.first;
             // (a 1 M-triangle mesh is one object: the per-triangle work runs on all host cores)
@@ -259,8 +298,14 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             const int id = firstPrim[i];
             sph[2 * si] = f4(sp.center, sp.radius);
             sph[2 * si + 1] = make_float4(asF(id), asF(int(o.area_light >= 0 ? 1 : 0)), 0.f, 0.f);
-            prims[4 * id] = f4(sp.center, sp.radius);
-            prims[4 * id + 3] = rec3;
+            if (gpuBuild) {
+                extraIds.push_back(id);
+                extraRecs.insert(extraRecs.end(), {f4(sp.center, sp.radius), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), rec3});
+            }
+            else {
+                prims[4 * id] = f4(sp.center, sp.radius);
+                prims[4 * id + 3] = rec3;
+            }
             ++si;
         }
         else {
@@ -268,16 +313,88 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
             const int id = firstPrim[i];
             box[2 * bi] = f4(b.pmin, asF(id));
             box[2 * bi + 1] = f4(b.pmax, 0.f);
-            prims[4 * id + 3] = rec3;
+            if (gpuBuild) {
+                extraIds.push_back(id);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                extraRecs.insert(extraRecs.end(), {z, z, z, rec3});
+            }
+            else prims[4 * id + 3] = rec3;
             ++bi;
         }
     }
     lap("triangle / shading records");
+    // ---- device-side ingest, PLOC build and eight-child collapse (gpu_build.cu) ----
+    Bvh bvh;
+    bool builtOnGpu = false, wideOnGpu = false;
+    GpuBuildInfo gbi;
+    if (gpuBuild) {
+        Timer tbv;
+        const size_t nRaw = size_t(d->n_triangles);
+        xrtg_triangle* dRaw = nullptr;
+        MeshRange* dRanges = nullptr;
+        int* dExtraIds = nullptr;
+        float4* dExtraRecs = nullptr;
+        struct Temp { void** p; ~Temp() { if (*p) cudaFree(*p); } };
+        Temp t0{reinterpret_cast<void**>(&dRaw)}, t1{reinterpret_cast<void**>(&dRanges)}, t2{reinterpret_cast<void**>(&dExtraIds)}, t3{reinterpret_cast<void**>(&dExtraRecs)};
+        CU(cudaMalloc(reinterpret_cast<void**>(&dRaw), sizeof(xrtg_triangle) * nRaw));
+        CU(cudaMalloc(reinterpret_cast<void**>(&dRanges), sizeof(MeshRange) * meshRanges.size()));
+        CU(cudaMemcpyAsync(dRaw, d->triangles, sizeof(xrtg_triangle) * nRaw, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaMemcpyAsync(dRanges, meshRanges.data(), sizeof(MeshRange) * meshRanges.size(), cudaMemcpyHostToDevice, s->stream));
+        launchIngest(dRaw, dRanges, int(meshRanges.size()), nMeshTris, static_cast<float4*>(s->trisId.d), static_cast<float4*>(s->ftrisId.d),
+                     static_cast<float4*>(s->prims.d), s->stream);
+        if (!extraIds.empty()) {
+            CU(cudaMalloc(reinterpret_cast<void**>(&dExtraIds), sizeof(int) * extraIds.size()));
+            CU(cudaMalloc(reinterpret_cast<void**>(&dExtraRecs), sizeof(float4) * extraRecs.size()));
+            CU(cudaMemcpyAsync(dExtraIds, extraIds.data(), sizeof(int) * extraIds.size(), cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(dExtraRecs, extraRecs.data(), sizeof(float4) * extraRecs.size(), cudaMemcpyHostToDevice, s->stream));
+            launchScatterPrims(dExtraRecs, dExtraIds, int(extraIds.size()), static_cast<float4*>(s->prims.d), s->stream);
+        }
+        CU(cudaStreamSynchronize(s->stream));
+        lap("raw upload + ingest kernel");
+        if (int rc = s->nodes.allocDevice(sizeof(BvhNode) * size_t(nMeshTris - 1))) return rc;
+        if (int rc = s->ftris8.allocDevice(sizeof(float4) * 4 * size_t(nMeshTris))) return rc;
+        PlocParams pp;
+        pp.radius = tv(s->tuning.t.ploc_radius, pp.radius);
+        pp.maxLeaf = std::min(4, std::max(1, tv(s->tuning.t.max_leaf, 4)));
+        if (s->tuning.t.ploc_ct_x16 >= 0) pp.traversalCost = float(s->tuning.t.ploc_ct_x16) / 16.f;
+        pp.topClusters = tv(s->tuning.t.ploc_top, pp.topClusters);
+        pp.topByClusters = tv(s->tuning.t.ploc_weight, 1) != 0;
+        pp.verbose = dumpCreate;
+        cudaError_t e = buildPlocDevice(static_cast<const float4*>(s->trisId.d), uint32_t(nMeshTris), static_cast<float4*>(s->tris.d),
+                                        static_cast<BvhNode*>(s->nodes.d), s->stream, &gbi, static_cast<const float4*>(s->ftrisId.d),
+                                        static_cast<float4*>(s->ftris.d), pp);
+        lap("sort + PLOC + node records");
+        Bvh8Node* d8 = nullptr;
+        uint32_t n8 = 0;
+        int depth8 = 0;
+        if (e == cudaSuccess)
+            e = collapseBvh8Device(static_cast<const BvhNode*>(s->nodes.d), uint32_t(nMeshTris), static_cast<const float4*>(s->ftris.d), &d8, &n8,
+                                   static_cast<float4*>(s->ftris8.d), &depth8, s->stream);
+        if (dumpCreate) std::fprintf(stderr, "scene_create: device build: %s, %u wide nodes, wide depth %d\n", cudaGetErrorString(e), n8, depth8);
+        if (e == cudaErrorNotSupported || (e == cudaSuccess && depth8 + 2 > 64)) {
+            // degenerate input (clustering without progress, or a tree deeper than the traversal stacks): the host builder decides
+            if (d8) cudaFree(d8);
+            cudaGetLastError();
+            s.reset();
+            return xrtg_scene_create2(d, device, (build_flags & ~uint32_t(XRTG_BUILD_GPU)) | XRTG_BUILD_HOST, out);
+        }
+        if (e != cudaSuccess) { if (d8) cudaFree(d8); return fail(XRTG_ERR_CUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e)); }
+        s->nodes8.adoptDevice(d8, sizeof(Bvh8Node) * size_t(n8));
+        s->info.n_wide_nodes = int(n8);
+        s->info.wide_arity = 8;
+        bvh.depth = gbi.depth; bvh.pad = gbi.pad; bvh.sahCost = gbi.sahCost;
+        bvh.nodes.resize(size_t(std::max(gbi.nNodes, 1))); // size bookkeeping only
+        builtOnGpu = wideOnGpu = true;
+        s->info.bvh_build_ms = tbv.ms();
+        s->info.bvh_builder = 2;
+        lap("eight-child collapse (device)");
+    }
     // ---- world bounds of everything a ray can hit (screen-space scissor of the primary kernel) ----
     {
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         auto grow = [&](const float* p, float r) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a] - r); hi[a] = std::max(hi[a], p[a] + r); } };
         for (size_t k = 0; k < buildTris.size(); k += 3) grow(&buildTris[k], 0.f);
+        if (gpuBuild) { grow(gbi.lo, 0.f); grow(gbi.hi, 0.f); }
         for (int i = 0; i < d->n_objects; ++i) {
             const xrtg_object& o = d->objects[i];
             if (o.kind == XRTG_OBJ_SPHERE) grow(d->spheres[o.first].center, std::fabs(d->spheres[o.first].radius));
@@ -290,9 +407,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     }
     if (nMeshTris >= 1 && nMeshTris <= 64) s->smallTriVerts = buildTris; // screen-space candidate masks of the primary rays
     // ---- BVH over all mesh triangles (emitter proxies included; any-hit skips them by flag) ----
-    Bvh bvh;
-    bool builtOnGpu = false;
-    if ((build_flags & XRTG_BUILD_LBVH_GPU) && nMeshTris >= 2) {
+    if (!builtOnGpu && (build_flags & XRTG_BUILD_LBVH_GPU) && nMeshTris >= 2) {
         // GPU build: triangles go up first, the tree and the leaf-ordered triangles are produced on the device and
         // mirrored back into the pinned host copies (xrtg_scene_upload re-sends them)
         if (int rc = s->nodes.alloc(sizeof(BvhNode) * size_t(nMeshTris - 1))) return rc;
@@ -344,7 +459,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     }
     lap("bounds + BVH build + reorder");
     // ---- deep trees: four-child form for the resumable traversal kernel (bvh.h) ----
-    if (bvh.nodes.size() > 512 && tv(s->tuning.t.wide_bvh, 4) >= 4) {
+    if (!wideOnGpu && bvh.nodes.size() > 512 && tv(s->tuning.t.wide_bvh, 4) >= 4) {
         std::vector<Bvh4Node> wide;
         const int depth4 = collapseBvh4(static_cast<const BvhNode*>(s->nodes.h), bvh.nodes.size(), wide);
         if (3 * depth4 + 1 <= 64) { // a four-child node pushes up to three entries: must fit the traversal stack (24 shared + 40 local)
@@ -356,7 +471,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     }
     lap("four-child collapse");
     // ---- deep trees, throughput instantiation: eight-child quantised nodes + node-ordered triangle records (bvh.h, k_trace8) ----
-    if (bvh.nodes.size() > 512) {
+    if (!wideOnGpu && bvh.nodes.size() > 512) {
         std::vector<Bvh8Node> wide8;
         std::vector<uint32_t> order8;
         const int depth8 = collapseBvh8(static_cast<const BvhNode*>(s->nodes.h), bvh.nodes.size(), wide8, order8);
@@ -500,7 +615,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
     s->info.build_ms = tb.ms();
 
     Timer tu;
-    if (int rc = uploadAll(s.get())) return rc;
+    if (int rc = uploadAll(s.get(), false)) return rc;
     CU(cudaStreamSynchronize(s->stream));
     s->info.upload_ms = tu.ms();
 
@@ -545,7 +660,7 @@ int xrtg_scene_upload(xrtg_scene* s)
     const std::vector<xrtg_scene*> all = s->replicas.empty() ? std::vector<xrtg_scene*>{s} : s->replicas;
     for (xrtg_scene* r : all) { // every replica's copies are enqueued before the first one is waited for
         CU(cudaSetDevice(r->device));
-        if (int rc = uploadAll(r)) return rc;
+        if (int rc = uploadAll(r, true)) return rc;
     }
     size_t total = 0;
     for (xrtg_scene* r : all) {
@@ -795,6 +910,9 @@ Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, b
     P.thrExt0 = tv(t.thr_ext0, P.deep ? 1 : 0);
     P.thrExt = tv(t.thr_ext, P.deep ? (eight ? 24 : 16) : 0);
     P.thrCon = tv(t.thr_con, P.deep ? (eight ? 24 : 16) : 0);
+    if (s->info.bvh_depth > 60) { // only k_trace's stack holds a tree this deep: the run-to-completion kernels cannot be forced onto it
+        P.thrExt0 = std::max(P.thrExt0, 1); P.thrExt = std::max(P.thrExt, 1); P.thrCon = std::max(P.thrCon, 1);
+    }
     P.spv = tv(t.steps_per_vote, P.deep ? (eight ? 2 : 4) : 1);
     P.leafThr = tv(t.leaf_threshold, 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
     P.thrVol = tv(t.thr_vol, 16);
@@ -1032,6 +1150,141 @@ int xrtg_small_scene_selftest(const float* tris9, const int* emitter_flags, int 
     if (n_planes) *n_planes = bi.nPlanesAll;
     if (rc < 0) return fail(XRTG_ERR_INVALID, "small-scene block is inconsistent with its triangles");
     return rc;
+}
+
+// Structural check of the trees RESIDENT ON THE DEVICE (whichever builder made them): the arrays are copied back and walked on the
+// host. Two-child tree: every leaf-ordered triangle in exactly one leaf, every child box contains the triangles below it. Eight-child
+// tree: the same with the DECODED quantised boxes shrunk by the one step of margin the traversal kernel's folded FMA relies on
+// (wf_trace8.cuh: byteMagic), every primitive id exactly once in the node-ordered records, leaf children of at most four triangles.
+int xrtg_scene_selfcheck(xrtg_scene* s, int* n_errors)
+{
+    if (!s || !n_errors) return fail(XRTG_ERR_INVALID, "NULL argument");
+    *n_errors = 0;
+    const int n = s->info.n_triangles;
+    if (n < 2 || s->nodes.bytes == 0) return 0;
+    if (int rc = materializeHost(s)) return rc;
+    const float4* trisId = static_cast<const float4*>(s->trisId.h);
+    const float4* tris = static_cast<const float4*>(s->tris.h);
+    const BvhNode* nodes = static_cast<const BvhNode*>(s->nodes.h);
+    const size_t nNodes = s->nodes.bytes / sizeof(BvhNode);
+    int errors = 0;
+    std::string firstMsg;
+    auto err = [&](const std::string& m) { if (errors++ == 0) firstMsg = m; };
+    struct Bounds { float lo[3], hi[3]; };
+    auto triBounds = [](const float4* rec, Bounds& b) { // v0, v0 + e1, v0 + e2
+        const float v[3][3] = {{rec[0].x, rec[0].y, rec[0].z}, {rec[0].x + rec[1].x, rec[0].y + rec[1].y, rec[0].z + rec[1].z}, {rec[0].x + rec[2].x, rec[0].y + rec[2].y, rec[0].z + rec[2].z}};
+        for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a])); b.hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a])); }
+    };
+    auto grow = [](Bounds& a, const Bounds& b) { for (int k = 0; k < 3; ++k) { a.lo[k] = std::min(a.lo[k], b.lo[k]); a.hi[k] = std::max(a.hi[k], b.hi[k]); } };
+    const Bounds kEmpty{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}};
+    // ---- two-child tree ----
+    {
+        std::vector<int> seen(size_t(n), 0), seenId(size_t(s->info.n_prims), 0);
+        int maxDepth = 0;
+        std::function<Bounds(int, int)> walk = [&](int node, int depth) -> Bounds {
+            Bounds all = kEmpty;
+            maxDepth = std::max(maxDepth, depth + 1);
+            if (node < 0 || size_t(node) >= nNodes || depth > 130) { err("two-child tree: node index out of range or runaway depth"); return all; }
+            const BvhNode& b = nodes[node];
+            for (int c = 0; c < 2; ++c) {
+                const float* lo = c ? b.lo1 : b.lo0;
+                const float* hi = c ? b.hi1 : b.hi0;
+                const int child = c ? b.child1 : b.child0, count = c ? b.count1 : b.count0;
+                if (count < 0) continue;
+                Bounds sub = kEmpty;
+                if (count > 0) {
+                    if (count > 4 || child < 0 || child + count > n) { err("two-child tree: bad leaf range"); continue; }
+                    for (int k = 0; k < count; ++k) {
+                        Bounds tb;
+                        triBounds(tris + 3 * size_t(child + k), tb);
+                        grow(sub, tb);
+                        seen[size_t(child + k)]++;
+                        int id;
+                        std::memcpy(&id, &tris[3 * size_t(child + k)].w, 4);
+                        if (id < 0 || id >= s->info.n_prims) err("two-child tree: primitive id out of range");
+                        else seenId[size_t(id)]++;
+                    }
+                }
+                else sub = walk(child, depth + 1);
+                for (int a = 0; a < 3; ++a)
+                    if (!(lo[a] <= sub.lo[a] && sub.hi[a] <= hi[a])) { err("two-child tree: child box does not contain its subtree (node " + std::to_string(node) + ")"); break; }
+                grow(all, sub);
+            }
+            return all;
+        };
+        walk(0, 0);
+        for (int k = 0; k < n; ++k)
+            if (seen[size_t(k)] != 1) { err("two-child tree: leaf-ordered triangle " + std::to_string(k) + " referenced " + std::to_string(seen[size_t(k)]) + " times"); break; }
+        for (int k = 0; k < n; ++k) {
+            int id;
+            std::memcpy(&id, &trisId[3 * size_t(k)].w, 4);
+            if (id < 0 || id >= s->info.n_prims || seenId[size_t(id)] != 1) { err("two-child tree: primitive " + std::to_string(id) + " not exactly once in the leaf order"); break; }
+        }
+        if (maxDepth > 124) err("two-child tree deeper than the traversal stack of k_trace");
+    }
+    // ---- eight-child tree ----
+    if (s->nodes8.bytes && s->ftris8.bytes) {
+        const Bvh8Node* n8 = static_cast<const Bvh8Node*>(s->nodes8.h);
+        const size_t nWide = s->nodes8.bytes / sizeof(Bvh8Node);
+        const float4* f8 = static_cast<const float4*>(s->ftris8.h);
+        std::vector<int> tkOfId(size_t(s->info.n_prims), -1), seenId(size_t(s->info.n_prims), 0), seenNode(nWide, 0);
+        for (int k = 0; k < n; ++k) {
+            int id;
+            std::memcpy(&id, &trisId[3 * size_t(k)].w, 4);
+            if (id >= 0 && id < s->info.n_prims) tkOfId[size_t(id)] = k;
+        }
+        int maxDepth = 0;
+        std::function<Bounds(uint32_t, int)> walk = [&](uint32_t node, int depth) -> Bounds {
+            Bounds all = kEmpty;
+            maxDepth = std::max(maxDepth, depth + 1);
+            if (size_t(node) >= nWide || depth > 70) { err("eight-child tree: node index out of range or runaway depth"); return all; }
+            if (seenNode[node]++) { err("eight-child tree: node referenced twice"); return all; }
+            const Bvh8Node& w = n8[node];
+            uint32_t nextChild = 0, nextTri = 0;
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const bool inner = (w.imask >> s8) & 1u;
+                const uint32_t nib = (w.validTri >> (4 * s8)) & 0xFu;
+                if (inner && nib) { err("eight-child tree: slot is both inner and leaf"); continue; }
+                if (!inner && !nib) continue;
+                Bounds sub = kEmpty;
+                if (inner) sub = walk(w.childBase + nextChild++, depth + 1);
+                else {
+                    if (nib != 1u && nib != 3u && nib != 7u && nib != 15u) { err("eight-child tree: malformed triangle nibble"); continue; }
+                    const int count = __builtin_popcount(nib);
+                    for (int k = 0; k < count; ++k) {
+                        const size_t t = size_t(w.triBase) + nextTri++;
+                        if (t >= size_t(n)) { err("eight-child tree: triangle index out of range"); continue; }
+                        int id;
+                        std::memcpy(&id, &f8[4 * t + 3].x, 4);
+                        if (id < 0 || id >= s->info.n_prims || tkOfId[size_t(id)] < 0) { err("eight-child tree: bad primitive id in ftris8"); continue; }
+                        seenId[size_t(id)]++;
+                        Bounds tb;
+                        triBounds(trisId + 3 * size_t(tkOfId[size_t(id)]), tb);
+                        grow(sub, tb);
+                    }
+                }
+                for (int a = 0; a < 3; ++a) {
+                    const double step = std::ldexp(1.0, int(w.e[a]) - 127);
+                    const double lo = double(w.p[a]) + (double(w.qlo[a][s8]) + 1.0) * step, hi = double(w.p[a]) + (double(w.qhi[a][s8]) - 1.0) * step;
+                    if (!(lo <= double(sub.lo[a]) && double(sub.hi[a]) <= hi)) { err("eight-child tree: quantised child box (minus its margin) does not contain its subtree (node " + std::to_string(node) + ", slot " + std::to_string(s8) + ")"); break; }
+                }
+                grow(all, sub);
+            }
+            return all;
+        };
+        walk(0u, 0);
+        for (int k = 0; k < n; ++k) {
+            int id;
+            std::memcpy(&id, &trisId[3 * size_t(k)].w, 4);
+            if (id < 0 || id >= s->info.n_prims || seenId[size_t(id)] != 1) { err("eight-child tree: primitive " + std::to_string(id) + " not exactly once in ftris8"); break; }
+        }
+        for (size_t k = 0; k < nWide; ++k)
+            if (seenNode[k] != 1) { err("eight-child tree: node " + std::to_string(k) + " unreachable"); break; }
+        if (maxDepth + 2 > 64) err("eight-child tree deeper than the group stack");
+    }
+    *n_errors = errors;
+    if (errors) fail(XRTG_ERR_INVALID, "selfcheck: " + firstMsg);
+    return 0;
 }
 
 int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost)

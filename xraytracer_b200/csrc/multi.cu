@@ -152,7 +152,7 @@ int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out)
     std::memcpy(r->boundsLo, primary->boundsLo, sizeof(r->boundsLo));
     std::memcpy(r->boundsHi, primary->boundsHi, sizeof(r->boundsHi));
     r->hasBounds = primary->hasBounds;
-    if (int rc = uploadAll(r.get())) return rc;
+    if (int rc = uploadAll(r.get(), false)) return rc;
     CU(cudaStreamSynchronize(r->stream));
     *out = r.release();
     return 0;
@@ -306,6 +306,9 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
     xrtg_scene* primary = nullptr;
     if (int rc = xrtg_scene_create2(desc, devs[0], build_flags, &primary)) return rc;
     primary->replicas.push_back(primary);
+    // replicas are filled from the primary's pinned arrays: a device-built scene makes those copies now
+    if (ngpus > 1)
+        if (int rc = materializeHost(primary)) { xrtg_scene_destroy(primary); return rc; }
     for (int g = 1; g < ngpus; ++g) {
         xrtg_scene* r = nullptr;
         if (int rc = createReplica(primary, devs[size_t(g)], &r)) { xrtg_scene_destroy(primary); return rc; }

@@ -40,6 +40,27 @@ struct Mirror {
         CU(cudaMalloc(&d, n));
         return 0;
     }
+    int allocDevice(size_t n) // device array only: produced by kernels (gpu_build.cu); the pinned copy is made on demand
+    {
+        release();
+        bytes = n;
+        if (n == 0) return 0;
+        CU(cudaMalloc(&d, n));
+        return 0;
+    }
+    void adoptDevice(void* dev, size_t n) // takes ownership of a cudaMalloc'ed array
+    {
+        release();
+        d = dev;
+        bytes = n;
+    }
+    int ensureHost() // pinned copy of a device-produced array (re-uploads, replicas on other devices)
+    {
+        if (h || bytes == 0) return 0;
+        CU(cudaMallocHost(&h, bytes));
+        CU(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     int mirrorOf(const Mirror& src) // device copy on the CURRENT device of src's host array
     {
         release();
@@ -161,7 +182,8 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
 
 namespace xrt {
 // api.cu
-int uploadAll(xrtg_scene* s);
+int uploadAll(xrtg_scene* s, bool materialize = false);
+int materializeHost(xrtg_scene* s); // pinned copies of the arrays a device-side build produced
 int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* out, cudaStream_t st, xrtg_stats* stats);
 int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p);
 // multi.cu

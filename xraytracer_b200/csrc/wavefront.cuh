@@ -38,7 +38,9 @@ namespace XRT_NS {
 constexpr bool kExact = (XRT_EXACT != 0);
 constexpr int kBlock = 128;          // threads per CTA of the traversal kernels (the surface shade kernel uses kShadeBlock)
 constexpr int kStackSmem = 24;       // traversal stack entries kept in shared memory per thread
-constexpr int kStackLocal = 40;      // overflow entries (local memory); builder depth limit is 56
+constexpr int kStackLocal = 40;      // overflow entries (local memory) of the run-to-completion walks; host builder depth limit is 56
+constexpr int kStackLocalDeep = 104; // ... of k_trace, the kernel of deep trees: two-child trees of up to 120 levels (device-built
+                                     // PLOC trees are deeper than top-down SAH ones: 41-53 levels on the 1 M-triangle scene)
 constexpr float kPI = 3.14159265359; // geometry.h:10
 constexpr float kRayEps = 1e-3f;     // geometry.h:23
 

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace(DScene sc, DQueues q, int s
                                                   int refillThreshold, int stepsPerVote, int leafThreshold)
 {
     __shared__ int s_stack[kStackSmem * kBlock];
-    int lstack[kStackLocal];
+    int lstack[kStackLocalDeep]; // (local memory, touched only as deep as a ray's stack actually grows)
     int* sstack = s_stack + threadIdx.x;
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ANY ? ctrl[kCtrlShadow] : ctrl[kCtrlRays];

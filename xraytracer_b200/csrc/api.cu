@@ -59,7 +59,8 @@ namespace xrt {
 
 int materializeHost(xrtg_scene* s)
 {
-    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[kSceneArrays];
+    sceneArrays(s, all);
     CU(cudaSetDevice(s->device));
     for (Mirror* m : all)
         if (int rc = m->ensureHost()) return rc;
@@ -68,12 +69,13 @@ int materializeHost(xrtg_scene* s)
 
 int uploadAll(xrtg_scene* s, bool materialize)
 {
-    Mirror* all[] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8, &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    Mirror* all[kSceneArrays];
+    sceneArrays(s, all);
     size_t total = 0;
     if (materialize)
         if (int rc = materializeHost(s)) return rc;
     for (Mirror* m : all) {
-        // (arrays produced on the device have no host copy until someone asks for a re-upload or a replica)
+        // (arrays produced on the device have no host copy until someone asks for a re-upload)
         if (m->bytes && m->h) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
         total += m->bytes;
     }
@@ -658,9 +660,19 @@ int xrtg_scene_upload(xrtg_scene* s)
     if (!s) return fail(XRTG_ERR_INVALID, "scene is NULL");
     Timer t;
     const std::vector<xrtg_scene*> all = s->replicas.empty() ? std::vector<xrtg_scene*>{s} : s->replicas;
+    // a device-built scene makes its pinned copies now (once); the replicas on other devices re-upload from the same copies
+    if (int rc = materializeHost(s)) return rc;
+    for (xrtg_scene* r : all) {
+        if (r == s) continue;
+        Mirror *src[kSceneArrays], *dst[kSceneArrays];
+        sceneArrays(s, src);
+        sceneArrays(r, dst);
+        for (int k = 0; k < kSceneArrays; ++k)
+            if (dst[k] != &r->grids) dst[k]->shareHost(*src[k]); // (every replica owns its table of grid descriptors: device pointers)
+    }
     for (xrtg_scene* r : all) { // every replica's copies are enqueued before the first one is waited for
         CU(cudaSetDevice(r->device));
-        if (int rc = uploadAll(r, true)) return rc;
+        if (int rc = uploadAll(r, false)) return rc;
     }
     size_t total = 0;
     for (xrtg_scene* r : all) {

@@ -125,12 +125,19 @@ int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out)
     for (auto& e : r->ev) CU(cudaEventCreate(&e));
     CU(cudaMallocHost(&r->statsHost, sizeof(unsigned long long) * kStatCount));
     CU(cudaMallocHost(&r->ctrlHost, sizeof(uint32_t) * 16));
-    const Mirror* src[] = {&primary->nodes, &primary->nodes4, &primary->nodes8, &primary->tris, &primary->trisId, &primary->ftris, &primary->ftrisId, &primary->ftris8,
-                           &primary->smallBlock, &primary->prims, &primary->spheres, &primary->boxes, &primary->lights, &primary->dlights, &primary->media};
-    Mirror* dst[] = {&r->nodes, &r->nodes4, &r->nodes8, &r->tris, &r->trisId, &r->ftris, &r->ftrisId, &r->ftris8,
-                     &r->smallBlock, &r->prims, &r->spheres, &r->boxes, &r->lights, &r->dlights, &r->media};
-    for (size_t k = 0; k < sizeof(src) / sizeof(src[0]); ++k)
-        if (int rc = dst[k]->mirrorOf(*src[k])) return rc;
+    // Arrays with a pinned host copy are uploaded from it (shared with the primary); arrays a device-side build produced exist in
+    // the primary's HBM only and are copied device to device — over NVLink when the devices are peers — with no host staging.
+    Mirror *src[kSceneArrays], *dst[kSceneArrays];
+    sceneArrays(const_cast<xrtg_scene*>(primary), src);
+    sceneArrays(r.get(), dst);
+    for (int k = 0; k < kSceneArrays; ++k) {
+        if (dst[k] == &r->grids) continue; // (its own table, below)
+        if (src[k]->h || src[k]->bytes == 0) { if (int rc = dst[k]->mirrorOf(*src[k])) return rc; }
+        else {
+            if (int rc = dst[k]->allocDevice(src[k]->bytes)) return rc;
+            CU(cudaMemcpyPeerAsync(dst[k]->d, device, src[k]->d, primary->device, src[k]->bytes, r->stream));
+        }
+    }
     for (const auto& g : primary->gridData) {
         auto m = std::make_unique<Mirror>();
         if (int rc = m->mirrorOf(*g)) return rc;
@@ -306,9 +313,6 @@ int xrtg_scene_create_multi(const xrtg_scene_desc* desc, int ngpus, const int* d
     xrtg_scene* primary = nullptr;
     if (int rc = xrtg_scene_create2(desc, devs[0], build_flags, &primary)) return rc;
     primary->replicas.push_back(primary);
-    // replicas are filled from the primary's pinned arrays: a device-built scene makes those copies now
-    if (ngpus > 1)
-        if (int rc = materializeHost(primary)) { xrtg_scene_destroy(primary); return rc; }
     for (int g = 1; g < ngpus; ++g) {
         xrtg_scene* r = nullptr;
         if (int rc = createReplica(primary, devs[size_t(g)], &r)) { xrtg_scene_destroy(primary); return rc; }

@@ -61,6 +61,10 @@ struct Mirror {
         CU(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
         return 0;
     }
+    void shareHost(const Mirror& src) // a replica adopts the primary's (lazily made) pinned copy
+    {
+        if (!h && src.h && src.bytes == bytes) { h = src.h; ownsHost = false; }
+    }
     int mirrorOf(const Mirror& src) // device copy on the CURRENT device of src's host array
     {
         release();
@@ -181,6 +185,14 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
 };
 
 namespace xrt {
+// every scene array of a handle, in one fixed order (uploads, replicas, lazily made pinned copies)
+constexpr int kSceneArrays = 16;
+inline void sceneArrays(xrtg_scene* s, Mirror* out[kSceneArrays])
+{
+    Mirror* all[kSceneArrays] = {&s->nodes, &s->nodes4, &s->nodes8, &s->tris, &s->trisId, &s->ftris, &s->ftrisId, &s->ftris8,
+                                 &s->smallBlock, &s->prims, &s->spheres, &s->boxes, &s->lights, &s->dlights, &s->media, &s->grids};
+    for (int k = 0; k < kSceneArrays; ++k) out[k] = all[k];
+}
 // api.cu
 int uploadAll(xrtg_scene* s, bool materialize = false);
 int materializeHost(xrtg_scene* s); // pinned copies of the arrays a device-side build produced

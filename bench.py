@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the GPU path tracer (BASELINE.json: Msamples/s & Mrays/s, GIIntegrator 1080p).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c3|c4|c5] [--side c4,c5,exact] [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c4|c5] [--side c4,c5,c1,c2,exact] [--impl ours|reference]
 
 One "step" = one full render of the workload (every pixel x every sample) through the wavefront kernels.
 
@@ -43,6 +43,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
+    "c1": dict(scene="cornell", integrator="normal", max_depth=1, width=512, height=512, spp=16, cpu_spp=16, cpu_stride=1,
+               desc="Cornell box, NormalIntegrator visibility, 512x512, 16 spp"),
+    "c2": dict(scene="cornell_tri", integrator="direct", max_depth=1, width=1920, height=1080, spp=64, cpu_spp=2, cpu_stride=1,
+               desc="Cornell box, DirectIntegrator with a TriangleLight (half of the quad), 1920x1080, 64 spp"),
     "c3": dict(scene="cornell", integrator="gi", max_depth=3, width=1920, height=1080, spp=1024, cpu_spp=4, cpu_stride=1,
                desc="Cornell box (34 tris + quad light), GIIntegrator depth 3, 1920x1080, 1024 spp"),
     "c4": dict(scene="mesh1m", integrator="gi", max_depth=3, width=1920, height=1080, spp=64, cpu_spp=1, cpu_stride=30,
@@ -59,6 +63,8 @@ def build_scene(kind):
     from xraytracer_b200 import scenes
     if kind == "cornell":
         return scenes.cornell_box("quad")
+    if kind == "cornell_tri":
+        return scenes.cornell_box("triangle")
     if kind == "mesh1m":
         return scenes.cornell_mesh_scene(707, 707)
     if kind == "volume":
@@ -72,6 +78,8 @@ def build_flat_scene(kind):
     from xraytracer_b200 import flatdesc
     if kind == "cornell":
         return flatdesc.cornell_box()
+    if kind == "cornell_tri":
+        return flatdesc.cornell_box("triangle")
     if kind == "mesh1m":
         return flatdesc.cornell_mesh_scene(707, 707)
     if kind == "volume":
@@ -601,7 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="headline workload (top level of the JSON line)")
-    ap.add_argument("--side", default="c4,c5,exact", help="comma list of side measurements reported under 'workloads' / 'exact_mode_c3' ('' = none)")
+    ap.add_argument("--side", default="c4,c5,c1,c2,exact", help="comma list of side measurements reported under 'workloads' / 'exact_mode_c3' ('' = none)")
     ap.add_argument("--spp", type=int, default=0, help="override the headline workload's spp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

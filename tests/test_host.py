@@ -128,6 +128,10 @@ def test_pure_python_scene_description_equals_host_scene():
     a, _, _ = api.ReferenceScene(host.flatten()).render(cam_h, W, H, 4, capi.INT_GI, 3)
     b, _, _ = api.ReferenceScene(flat.desc()).render(cam_f, W, H, 4, capi.INT_GI, 3)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    ht, ft = scenes.cornell_box("triangle"), flatdesc.cornell_box("triangle")   # bench.py workload c2
+    a, _, _ = api.ReferenceScene(ht.flatten()).render(cam_h, W, H, 4, capi.INT_DIRECT, 1)
+    b, _, _ = api.ReferenceScene(ft.desc()).render(cam_f, W, H, 4, capi.INT_DIRECT, 1)
+    assert a.max() > 0 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     hv = scenes.volume_scene(n=24)
     fv = flatdesc.volume_scene(n=24)
     a, _, _ = api.ReferenceScene(hv.flatten()).render(cam_h, W, H, 4, capi.INT_VOLUME, 8)

@@ -66,6 +66,14 @@ class FlatScene:
         self.area_lights.append((capi.LIGHT_QUAD, v0, v1, v2, 0.0, tuple(float(x) for x in Le)))
         self.add_mesh(name, np.array([np.concatenate([v0, v1, v2, n, n, n]), np.concatenate([v1, v3, v2, n, n, n])], np.float32), None, area_light=li)
 
+    def add_triangle_light(self, name, v0, v1, v2, Le):
+        """TriangleLight + its one-triangle proxy mesh (light.cpp:32-47)."""
+        v0, v1, v2 = (np.asarray(v, np.float32) for v in (v0, v1, v2))
+        n = _flat_normal(v0, v1, v2)
+        li = len(self.area_lights)
+        self.area_lights.append((capi.LIGHT_TRIANGLE, v0, v1, v2, 0.0, tuple(float(x) for x in Le)))
+        self.add_mesh(name, np.array([np.concatenate([v0, v1, v2, n, n, n])], np.float32), None, area_light=li)
+
     def add_heterogeneous_medium(self, name, g, voxels, origin, voxel_size, abs_color, scat_color, mul=1.0):
         """HeterogeneousMedium over a dense grid + its BoxMesh proxy over the active-voxel bounds (grid.h:58-69, medium.h)."""
         v = np.ascontiguousarray(voxels, dtype=np.float32)
@@ -140,15 +148,19 @@ def make_camera(width, height, c2w, fov) -> capi.Camera:
     return cam
 
 
-def cornell_box() -> FlatScene:
-    """scenes.cornell_box("quad") without the host library: shapes in OBJ order (face-less shapes dropped), then the light."""
+def cornell_box(light: str = "quad") -> FlatScene:
+    """scenes.cornell_box(light) without the host library: shapes in OBJ order (face-less shapes dropped), then the light
+    ("quad", or "triangle" = half of the quad)."""
     from . import scenes
     s = FlatScene()
     for shape, mat, quads in scenes.CORNELL_SHAPES:
         if quads:
             s.add_quads(shape, quads, scenes.CORNELL_MATERIALS[mat])
     q = scenes.CORNELL_QUAD_LIGHT
-    s.add_quad_light("QuadLight", q["v0"], q["v1"], q["v2"], q["Le"])
+    if light == "triangle":
+        s.add_triangle_light("TriangleLight", q["v0"], q["v1"], q["v2"], q["Le"])
+    else:
+        s.add_quad_light("QuadLight", q["v0"], q["v1"], q["v2"], q["Le"])
     return s
 
 

@@ -143,7 +143,7 @@ GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg
                "xrtg_scene_device_count", "xrtg_scene_set_tuning", "xrtg_exchange_buffer", "xrtg_ipc_export", "xrtg_ipc_open",
                "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8", "xrtg_scene_check_guards", "xrtg_scene_selfcheck"]
 
-GPU_LIB = PKG / "csrc" / "libxrtgpu.so"
+GPU_LIB = Path(os.environ["XRT_GPU_LIB"]) if os.environ.get("XRT_GPU_LIB") else PKG / "csrc" / "libxrtgpu.so"   # (override: A/B builds)
 HOST_LIB = PKG / "host" / "libxrthost.so"
 ORACLE_LIB = ROOT / "oracle" / "libxrtoracle.so"
 REF_LIB = ROOT / "oracle" / "_ref" / "libxrtref.so"          # CPU checker / reference arm: no product library behind it

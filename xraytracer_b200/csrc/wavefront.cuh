@@ -33,6 +33,14 @@
 #endif
 
 namespace xrt {
+#ifndef XRT_TMA_STAGE
+// k_bounce_small: queue tiles staged per thread with cp.async (0, default) or by bulk copies of the TMA unit completing on an
+// mbarrier (1; SASS: UBLKCP + SYNCS.ARRIVE.TRANS64). Measured on c3 (profiles/r02_notes.md): 9 241 vs 9 053 Msamples/s — with
+// cp.async every warp waits for its OWN 4 x 16 B, with the bulk copy all warps of the CTA wake on the same barrier, and the
+// tile is only 8 KB, too small for the TMA unit's per-copy cost to amortise. Both variants pass the same parity tests.
+#define XRT_TMA_STAGE 0
+#endif
+
 namespace XRT_NS {
 
 constexpr bool kExact = (XRT_EXACT != 0);

@@ -623,10 +623,51 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
     const int kind = w.integrator;
     uint32_t nClosest = 0, nShadow = 0;
-    // The queue entries of the CTA's NEXT tile are copied into shared memory with cp.async while the current tile is being
-    // worked on (each thread stages and later reads only its own 4 x 16 B, so no barrier is needed, just its own wait_group):
-    // the HBM latency of the four queue loads at the head of every tile's dependency chain is hidden behind a whole tile of work.
-    __shared__ float4 s_stage[2][4][kBlock];
+    // The queue entries of the CTA's NEXT tile are copied into shared memory while the current tile is being worked on: the HBM
+    // latency of the four queue loads at the head of every tile's dependency chain is hidden behind a whole tile of work.
+    // kTmaStage: ONE thread issues four bulk copies (cp.async.bulk, the TMA unit: 4 x 2 KB contiguous rows of the SoA queues) that
+    // complete on an mbarrier; otherwise every thread stages its own 4 x 16 B with cp.async (LDGSTS) and waits for its own group.
+    __shared__ __align__(128) float4 s_stage[2][4][kBlock];
+#if XRT_TMA_STAGE
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            const uint32_t bar = uint32_t(__cvta_generic_to_shared(&s_bar[b]));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phaseBits = 0; // bit b = parity the next wait on s_bar[b] expects
+    auto stage = [&](int buf, uint64_t tile) {
+        const uint64_t e0 = tile * kBlock;
+        if (threadIdx.x == 0 && e0 < n) {
+            // (the previous readers of this buffer are behind the CTA barriers of the last tile's append)
+            const uint32_t bytes = uint32_t(min(uint64_t(kBlock), uint64_t(n) - e0)) * 16u;
+            const uint32_t bar = uint32_t(__cvta_generic_to_shared(&s_bar[buf]));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
+            const float4* src[4] = {hitsIn + e0, in0 + e0, in1 + e0, in2 + e0};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const uint32_t dst = uint32_t(__cvta_generic_to_shared(&s_stage[buf][a][0]));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src[a]), "r"(bytes), "r"(bar)
+                             : "memory");
+            }
+        }
+    };
+    auto stageWait = [&](int buf) {
+        const uint32_t bar = uint32_t(__cvta_generic_to_shared(&s_bar[buf])), parity = (phaseBits >> buf) & 1u;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@!p bra WAIT_%=;\n"
+            "}\n" ::"r"(bar), "r"(parity)
+            : "memory");
+        phaseBits ^= 1u << buf;
+    };
+#else
     auto stage = [&](int buf, uint64_t tile) {
         const uint64_t e = tile * kBlock + threadIdx.x;
         if (e < n) {
@@ -639,13 +680,15 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto stageWait = [&](int) { asm volatile("cp.async.wait_group 1;" ::: "memory"); }; // everything but the group just committed has landed
+#endif
     stage(0, blockIdx.x);
     int buf = 0;
     for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x, buf ^= 1) {
         const uint32_t i = tile * kBlock + threadIdx.x;
         const bool live = i < n;
         stage(buf ^ 1, uint64_t(tile) + gridDim.x);
-        asm volatile("cp.async.wait_group 1;" ::: "memory"); // everything but the group just committed has landed
+        stageWait(buf);
         // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
         V3 d = mk(0.f), T = mk(0.f);
         uint32_t pid = 0, ctr = 0;

@@ -296,6 +296,8 @@ typedef struct xrtg_tuning {
     int32_t ploc_radius;     /* creation time only: PLOC neighbour-search radius (default 16)                                 */
     int32_t ploc_ct_x16;     /* creation time only: SAH traversal-step cost of the PLOC leaf decision, in 1/16 (default 16)   */
     int32_t ploc_top;        /* creation time only: clusters at which PLOC hands over to the top-level sweep SAH (default 1024) */
+    int32_t grid_texture;    /* creation time only: density grids also live in a 3-D texture (1, default) that the throughput
+                                instantiation samples with hardware trilinear filtering; 0 = global-memory lookups only              */
     int32_t ploc_weight;     /* creation time only: top-level sweep SAH weighs a side by its triangles (0) or clusters (1, default) */
 } xrtg_tuning;
 

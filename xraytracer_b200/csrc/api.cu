@@ -79,9 +79,13 @@ int uploadAll(xrtg_scene* s, bool materialize)
         if (m->bytes && m->h) CU(cudaMemcpyAsync(m->d, m->h, m->bytes, cudaMemcpyHostToDevice, s->stream));
         total += m->bytes;
     }
-    for (auto& g : s->gridData) {
+    for (size_t i = 0; i < s->gridData.size(); ++i) {
+        Mirror* g = s->gridData[i].get();
         CU(cudaMemcpyAsync(g->d, g->h, g->bytes, cudaMemcpyHostToDevice, s->stream));
         total += g->bytes;
+        // the 3-D texture copy is refreshed from the array that just arrived (device to device: the voxels cross PCIe once)
+        if (i < s->gridTex.size() && s->gridTex[i])
+            if (int rc = s->gridTex[i]->fill(g->d, cudaMemcpyDeviceToDevice, s->stream)) return rc;
     }
     s->info.upload_bytes = total;
     return 0;
@@ -122,7 +126,7 @@ const TuningKey kTuningKeys[] = {
     {"leaf_threshold", &xrtg_tuning::leaf_threshold}, {"thr_vol", &xrtg_tuning::thr_vol}, {"spv_vol", &xrtg_tuning::spv_vol},
     {"wide_bvh", &xrtg_tuning::wide_bvh}, {"primary_masks", &xrtg_tuning::primary_masks}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
     {"stage_dump", &xrtg_tuning::stage_dump}, {"gpu_build", &xrtg_tuning::gpu_build}, {"ploc_radius", &xrtg_tuning::ploc_radius},
-    {"ploc_ct_x16", &xrtg_tuning::ploc_ct_x16}, {"ploc_top", &xrtg_tuning::ploc_top}, {"ploc_weight", &xrtg_tuning::ploc_weight}};
+    {"ploc_ct_x16", &xrtg_tuning::ploc_ct_x16}, {"ploc_top", &xrtg_tuning::ploc_top}, {"ploc_weight", &xrtg_tuning::ploc_weight}, {"grid_texture", &xrtg_tuning::grid_texture}};
 constexpr int kGpuBuildMinTris = 1024;   // below this the device build is refused: the host path is faster than its launches and synchronisations
 constexpr int kGpuBuildAutoTris = 65536; // from here on the device build is the default
 
@@ -595,7 +599,15 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         G[i].voxel = g.voxel_size;
         G[i].invVoxel = 1.0f / g.voxel_size;
         G[i].background = g.background;
+        G[i].tex = 0ull;
         s->gridData.push_back(std::move(m));
+        s->gridTex.emplace_back();
+        if (g.background == 0.0f && tv(s->tuning.t.grid_texture, 1) != 0) {
+            auto t = std::make_unique<GridTexture>();
+            if (int rc = t->create(g.nx, g.ny, g.nz)) return rc;
+            G[i].tex = (unsigned long long)t->tex;
+            s->gridTex.back() = std::move(t);
+        }
     }
     if (int rc = s->media.alloc(sizeof(DMedium) * size_t(std::max(d->n_media, 1)))) return rc;
     DMedium* M = static_cast<DMedium*>(s->media.h);

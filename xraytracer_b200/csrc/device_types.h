@@ -43,6 +43,8 @@ struct DGrid {
     float origin[3];
     float voxel, background;
     float invVoxel; // 1 / voxel (throughput instantiation; the exact one divides like grid.h:71-77)
+    unsigned long long tex; // cudaTextureObject_t over a 3-D cudaArray copy of `data` (linear filtering, border = 0), or 0: the
+                            // throughput instantiation's lookups go through the texture unit when background == 0
 };
 
 // Everything the kernels need to know about the scene; passed by value (fits the 4 KB param space).

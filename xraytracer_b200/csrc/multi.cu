@@ -148,7 +148,16 @@ int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out)
     if (primary->grids.bytes) {
         std::memcpy(r->grids.h, primary->grids.h, primary->grids.bytes);
         DGrid* G = static_cast<DGrid*>(r->grids.h);
-        for (size_t i = 0; i < r->gridData.size(); ++i) G[i].data = static_cast<const float*>(r->gridData[i]->d);
+        for (size_t i = 0; i < r->gridData.size(); ++i) {
+            G[i].data = static_cast<const float*>(r->gridData[i]->d);
+            r->gridTex.emplace_back();
+            if (G[i].tex) { // the primary has a 3-D texture copy of this grid: so does the replica, on its own device
+                auto t = std::make_unique<GridTexture>();
+                if (int rc = t->create(G[i].nx, G[i].ny, G[i].nz)) return rc;
+                G[i].tex = (unsigned long long)t->tex;
+                r->gridTex.back() = std::move(t);
+            }
+        }
     }
     r->ds = primary->ds;
     rebindPointers(r.get());

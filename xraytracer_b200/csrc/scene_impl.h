@@ -86,6 +86,46 @@ struct Mirror {
     ~Mirror() { release(); }
 };
 
+// 3-D texture copy of a density grid (throughput instantiation): cudaArray (the driver's tiled 3-D layout: the eight voxels of a
+// trilinear lookup share one or two cache lines instead of four rows 1 KB / 256 KB apart) + a texture object with linear
+// filtering, unnormalised coordinates and border addressing (outside = 0 = the grid's background).
+struct GridTexture {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t tex = 0;
+    int nx = 0, ny = 0, nz = 0;
+    int create(int nx_, int ny_, int nz_)
+    {
+        nx = nx_; ny = ny_; nz = nz_;
+        const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
+        CU(cudaMalloc3DArray(&array, &fmt, make_cudaExtent(size_t(nx), size_t(ny), size_t(nz))));
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = array;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        return 0;
+    }
+    int fill(const void* src, cudaMemcpyKind kind, cudaStream_t st) // src = nx*ny*nz floats, x fastest (host or device)
+    {
+        cudaMemcpy3DParms p{};
+        p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), size_t(nx) * sizeof(float), size_t(nx), size_t(ny));
+        p.dstArray = array;
+        p.extent = make_cudaExtent(size_t(nx), size_t(ny), size_t(nz));
+        p.kind = kind;
+        CU(cudaMemcpy3DAsync(&p, st));
+        return 0;
+    }
+    ~GridTexture()
+    {
+        if (tex) cudaDestroyTextureObject(tex);
+        if (array) cudaFreeArray(array);
+    }
+};
+
 // Device workspace buffer with GUARD BANDS: kGuardBytes of a known pattern before and after the usable range, verified on demand
 // (xrtg_scene_check_guards; the GPU tests check them after every render). compute-sanitizer is closed on this pool, so an
 // out-of-bounds queue write is caught by its footprint instead: every queue / counter / radiance buffer of the wave scheduler
@@ -158,6 +198,7 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     // scene arrays (pinned host copy + device copy)
     xrt::Mirror nodes, nodes4, nodes8, tris, trisId, ftris, ftrisId, ftris8, smallBlock, prims, spheres, boxes, lights, dlights, media, grids;
     std::vector<std::unique_ptr<xrt::Mirror>> gridData;
+    std::vector<std::unique_ptr<xrt::GridTexture>> gridTex; // one per grid (entries may be null: no texture for that grid)
     xrt::DScene ds{};
     xrtg_scene_info info{};
     xrt::Tuning tuning;

@@ -940,7 +940,10 @@ Pipeline choosePipeline(const xrtg_scene* s, int integ, int nIter, bool exact, b
     P.spv = tv(t.steps_per_vote, P.deep ? (eight ? 2 : 4) : 1);
     P.leafThr = tv(t.leaf_threshold, 4); // lanes that must stand at a leaf before the warp runs the triangle tests (k_trace)
     P.thrVol = tv(t.thr_vol, 16);
-    P.spvVol = tv(t.spv_vol, 2);
+    // (bits 8.. of spv_vol = refill + prologue rounds per outer iteration of k_volume_paths; 1 = measured best: a second round hands the
+    //  lanes whose path ended in volumePre a fresh path before the walk, but runs refill + prologue at ~20 % of the lanes — c5 12.95 -> 12.16)
+    P.spvVol = tv(t.spv_vol, 3);
+    if ((P.spvVol >> 8) == 0) P.spvVol |= 1 << 8;
     P.small = !P.deep && s->ds.nBruteTris > 0 && s->ds.nBruteTris <= 64;
     P.bruteSecondary = tv(t.brute_secondary, P.small ? 1 : 0) != 0;
     P.bruteShadow = tv(t.brute_shadow, P.small ? 1 : 0) != 0;

@@ -558,7 +558,7 @@ def run_workload(rig: Rig, name, wl, args, headline):
                        "parallelism": f"spp split over {rig.world} GPU(s), scene replicated; reduce = {red.mode}" +
                                       (" (one fused peer-memory pull + `image /= spp` kernel per rank over CUDA IPC, two 4-byte NCCL all-reduces as stream-ordered rendezvous)"
                                        if red.mode == "ipc" else (" (one NCCL reduce(sum) + divide)" if red.mode == "nccl" else "")),
-                       "l2_policy": "per-wave working set (ray + hit queues and the per-path radiance of 8.3M paths, 0.5-1.5 GB) exceeds the 126 MB L2; no flush needed",
+                       "l2_policy": "per-wave working set (ray + hit queues and the per-path radiance of up to 66M paths = 32 samples of every pixel, several GB) exceeds the 126 MB L2; no flush needed",
                        "triangles": info["n_triangles"], "bvh_nodes": info["n_bvh_nodes"], "wide_arity": info["wide_arity"], "wide_nodes": info["n_wide_nodes"]},
             "mrays_per_s": rays / (ms * 1e-3) / 1e6, "mrays_traced_per_s": st_all["rays_traced"] / (ms * 1e-3) / 1e6,
             "rays_per_sample": rays / samples, "rays_traced": int(st_all["rays_traced"] / steps), "rays_reference_equivalent": int(rays / steps),

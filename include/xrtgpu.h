@@ -289,7 +289,7 @@ typedef struct xrtg_tuning {
     int32_t thr_vol, spv_vol;              /* k_volume_paths lockstep-walk threshold / steps per vote                         */
     int32_t wide_bvh;        /* deep scenes: 8 = eight-child quantised nodes, 4 = four-child nodes, 2 = two-child nodes       */
     int32_t max_leaf;        /* creation time only (XRT_TUNING): triangles per leaf of the host SAH builder, 1..4             */
-    int32_t workspace_mb;    /* byte budget of the per-wave queues (default 6144); small values force pixel-tiled waves       */
+    int32_t workspace_mb;    /* byte budget of the per-wave queues (default 16384); small values force pixel-tiled waves       */
     int32_t stage_dump;      /* print every stage's CUDA-event time to stderr (with XRTG_FLAG_STAGE_TIMES)                    */
     int32_t primary_masks;   /* small scenes: screen-space candidate masks for the primary rays (1) or the BVH walk (0)       */
     int32_t gpu_build;       /* creation time only (XRT_TUNING): 1 = as if XRTG_BUILD_GPU were passed, 0 = never build on the device */

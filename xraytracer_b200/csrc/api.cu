@@ -997,11 +997,14 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
     // A wave is `S` samples of a range of `tile` pixels. Workspace per path: 2 x 48 B ping-pong ray queue + 16 B hit + 16 B
     // radiance, plus — in the three-kernel pipeline only — 48 B per shadow-queue entry x one entry per area (or delta) light:
     // an emissive mesh of a few hundred triangle lights needs tens of KB per path, so the wave shrinks (down to a range of
-    // pixels at one sample each) instead of the allocation failing. Default budget 6 GiB, ~8 M paths at most.
+    // pixels at one sample each) instead of the allocation failing. Default budget 16 GiB, 64 M paths at most (32 samples of every
+    // pixel at 1080p). BIG waves pay: every launch of a persistent queue kernel ends in a tail where the refill thresholds can no
+    // longer be met, and 180 GB of HBM make the queues cheap — measured against waves of 4 samples (the round-1 default, 8 M paths):
+    // c4 1.99 -> 2.54, c5 13.4 -> 16.0, c3 9.28 -> 9.69 Gsamples/s (profiles/r02_notes.md).
     const size_t shadowPerPath = (hasShadow && !P.fusedBounce) ? size_t(s->maxShadowPerPath) : 0;
     const size_t bytesPerPath = 128 + 48 * shadowPerPath;
-    const size_t budget = size_t(tv(s->tuning.t.workspace_mb, 6144)) << 20;
-    uint64_t maxPaths = std::min<uint64_t>(8u << 20, std::max<uint64_t>(budget / bytesPerPath, 1024));
+    const size_t budget = size_t(tv(s->tuning.t.workspace_mb, 16384)) << 20;
+    uint64_t maxPaths = std::min<uint64_t>(64u << 20, std::max<uint64_t>(budget / bytesPerPath, 1024));
     uint32_t S = 1, tile = nPixels; // exact: one sample per wave (the mt19937 stream of a pixel is sequential across its samples)
     if (!exact) {
         if (p->samples_per_wave > 0) S = std::min<uint32_t>(uint32_t(p->samples_per_wave), uint32_t(p->spp));

@@ -739,15 +739,17 @@ struct StageTimer {
 int ensureWorkspace(xrtg_scene* s, uint32_t nPixels, uint32_t maxPaths, size_t maxShadow, int maxIter, bool exact)
 {
     const size_t f4b = sizeof(float4);
+    // (+ the unused tails of k_bounce_small's warp-private output chunks: at most kAppendChunk - 1 slots per warp that had a tile)
+    const size_t nQueue = size_t(maxPaths) + std::min<size_t>(kAppendSlack, (size_t(maxPaths) / 128 + 1) * 4 * kAppendChunk);
     for (int k = 0; k < 2; ++k) {
-        if (int rc = s->q0[k].ensure(f4b * maxPaths)) return rc;
-        if (int rc = s->q1[k].ensure(f4b * maxPaths)) return rc;
-        if (int rc = s->q2[k].ensure(f4b * maxPaths)) return rc;
+        if (int rc = s->q0[k].ensure(f4b * nQueue)) return rc;
+        if (int rc = s->q1[k].ensure(f4b * nQueue)) return rc;
+        if (int rc = s->q2[k].ensure(f4b * nQueue)) return rc;
     }
-    if (int rc = s->hits.ensure(f4b * maxPaths)) return rc;
+    if (int rc = s->hits.ensure(f4b * nQueue)) return rc;
     // shadow queue: one entry per (path, light) in the three-kernel pipeline; s0 doubles as the second hit buffer of the fused
     // bounce kernel, so it is never smaller than the ray queue
-    const size_t nShadow = std::max<size_t>(maxShadow, maxPaths);
+    const size_t nShadow = std::max<size_t>(maxShadow, nQueue);
     if (int rc = s->s0.ensure(f4b * nShadow)) return rc;
     if (int rc = s->s1.ensure(f4b * std::max<size_t>(maxShadow, 1))) return rc;
     if (int rc = s->s2.ensure(f4b * std::max<size_t>(maxShadow, 1))) return rc;

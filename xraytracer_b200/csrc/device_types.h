@@ -95,6 +95,12 @@ struct DQueues {
     uint32_t* ctrl;                // per bounce b: ctrl[8b+0]=#rays  +1=#shadow  +2..+4 = work-fetch cursors
 };
 
+// k_bounce_small appends survivors per warp from warp-private chunks of kAppendChunk output slots; the slots a warp has not used at
+// the end of a launch are marked with kDeadPath in the path word. The queues therefore hold up to (kAppendChunk - 1) x resident
+// warps entries more than there are paths: 148 SMs x 16 CTAs x 4 warps x 63 < kAppendSlack.
+constexpr uint32_t kAppendChunk = 64;
+constexpr uint32_t kDeadPath = 0xffffffffu;
+constexpr uint32_t kAppendSlack = 1u << 20;
 enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
 
 // device-side statistics (uint64 each)

@@ -41,6 +41,12 @@ namespace xrt {
 #define XRT_TMA_STAGE 0
 #endif
 
+// k_bounce_small: survivors appended per warp from warp-private chunks of output slots, no CTA barrier in the tile loop (1), or
+// per CTA with one atomic and three barriers per tile (0).
+#ifndef XRT_WARP_APPEND
+#define XRT_WARP_APPEND 1
+#endif
+
 namespace XRT_NS {
 
 constexpr bool kExact = (XRT_EXACT != 0);

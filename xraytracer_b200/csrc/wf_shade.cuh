@@ -623,6 +623,10 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
     const int kind = w.integrator;
     uint32_t nClosest = 0, nShadow = 0;
+#if XRT_WARP_APPEND
+    const uint32_t lane = laneId();
+    uint32_t resNext = 0, resEnd = 0, nEntries = 0; // this warp's reservation of output slots; live entries consumed
+#endif
     // The queue entries of the CTA's NEXT tile are copied into shared memory while the current tile is being worked on: the HBM
     // latency of the four queue loads at the head of every tile's dependency chain is hidden behind a whole tile of work.
     // kTmaStage: ONE thread issues four bulk copies (cp.async.bulk, the TMA unit: 4 x 2 KB contiguous rows of the SoA queues) that
@@ -686,9 +690,11 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     int buf = 0;
     for (uint32_t tile = blockIdx.x; uint64_t(tile) * kBlock < n; tile += gridDim.x, buf ^= 1) {
         const uint32_t i = tile * kBlock + threadIdx.x;
-        const bool live = i < n;
+        bool live = i < n;
         stage(buf ^ 1, uint64_t(tile) + gridDim.x);
         stageWait(buf);
+        // (warp-chunked appends leave up to kAppendChunk - 1 unused slots per warp at the end of the previous launch: marked dead)
+        if (XRT_WARP_APPEND && live && __float_as_uint(s_stage[buf][3][threadIdx.x].y) == kDeadPath) live = false;
         // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
         V3 d = mk(0.f), T = mk(0.f);
         uint32_t pid = 0, ctr = 0;
@@ -700,6 +706,9 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         Surf s = {};
         bool shadeLights = false, shadeDelta = false, bsdf = false;
         if (live) {
+#if XRT_WARP_APPEND
+            ++nEntries;
+#endif
             const float4 hv = s_stage[buf][0][threadIdx.x], r0 = s_stage[buf][1][threadIdx.x], r1 = s_stage[buf][2][threadIdx.x], r2 = s_stage[buf][3][threadIdx.x];
             const V3 o = xyz(r0);
             d = xyz(r1);
@@ -798,7 +807,28 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
             ctr = rng.close();
             if (radDirty) q.radiance[pid] = rad;
         }
+#if XRT_WARP_APPEND
+        // Survivors are appended per WARP from a warp-private reservation of kAppendChunk output slots (one global atomic per
+        // kAppendChunk survivors of the warp): no CTA barrier anywhere in the tile loop, so the four warps of a CTA drift apart
+        // and hide each other's latencies. The slots a warp has not used when it runs out of tiles are marked dead (below).
+        uint32_t slot = 0;
+        {
+            const uint32_t mask = __ballot_sync(0xffffffffu, wantNext);
+            if (mask) {
+                const uint32_t cnt = __popc(mask), rank = __popc(mask & ((1u << lane) - 1u)), left = resEnd - resNext;
+                uint32_t nb = 0;
+                if (cnt > left) {
+                    if (lane == 0) nb = atomicAdd(nextCount, kAppendChunk);
+                    nb = __shfl_sync(0xffffffffu, nb, 0);
+                }
+                slot = rank < left ? resNext + rank : nb + (rank - left);
+                if (cnt > left) { resNext = nb + (cnt - left); resEnd = nb + kAppendChunk; }
+                else resNext += cnt;
+            }
+        }
+#else
         const uint32_t slot = blockAppend<kBlock / 32>(nextCount, wantNext, s_scratch);
+#endif
         if (wantNext) {
             out0[slot] = make_float4(no.x, no.y, no.z, nT.x);
             out1[slot] = make_float4(nd.x, nd.y, nd.z, nT.y);
@@ -806,7 +836,15 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
             hitsOut[slot] = make_float4(nh.t, nh.u, nh.v, __int_as_float(nh.prim));
         }
     }
+#if XRT_WARP_APPEND
+    for (uint32_t sl = resNext + lane; sl < resEnd; sl += 32u) { // the unused tail of this warp's last reservation
+        out2[sl] = make_float4(0.f, __uint_as_float(kDeadPath), 0.f, 0.f);
+        hitsOut[sl] = make_float4(FLT_MAX, 0.f, 0.f, __int_as_float(-1));
+    }
+    statAdd(stats, kStatBounceEntries, nEntries);
+#else
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatBounceEntries, (unsigned long long)n);
+#endif
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatShadow, nShadow);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatBounceEntries, (unsigned long long)n);
 }

@@ -46,6 +46,12 @@ namespace xrt {
 #ifndef XRT_WARP_APPEND
 #define XRT_WARP_APPEND 1
 #endif
+// The same for k_primary's compact bounce-0 queue (then every consumer of that queue skips the dead slots). Measured slightly
+// SLOWER on c3 (9 942 vs 10 017 Msamples/s): k_primary already pays one barrier round per 256 paths only, and the warp-private
+// chunks scatter neighbouring pixels' hits over the queue. Off.
+#ifndef XRT_WARP_APPEND_PRIMARY
+#define XRT_WARP_APPEND_PRIMARY 0
+#endif
 
 namespace XRT_NS {
 

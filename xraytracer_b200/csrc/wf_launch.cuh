@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kBlock) k_hook_fill_miss(float4* __restrict__ 
 __global__ void __launch_bounds__(kBlock) k_hook_scatter_hits(DQueues q, float4* __restrict__ out)
 {
     const uint32_t n = q.ctrl[kCtrlRays];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[__float_as_int(q.q2[0][i].y)] = q.hits[i];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!deadEntry(q.q2[0][i])) out[__float_as_int(q.q2[0][i].y)] = q.hits[i];
 }
 inline void launchScatterPrimaryHits(cudaStream_t st, const DQueues& q, float4* out, uint32_t nPaths)
 {

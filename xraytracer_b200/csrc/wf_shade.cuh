@@ -235,9 +235,11 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
         float4 r0, r1, r2, hv;
         r0 = r1 = r2 = hv = make_float4(0, 0, 0, 0);
         hv.w = __int_as_float(-1);
+        bool liveEntry = live;
         if (live) {
             hv = q.hits[i]; r2 = q.q2[src][i];
-            if (__float_as_int(hv.w) >= 0) { r0 = q.q0[src][i]; r1 = q.q1[src][i]; }
+            if (XRT_WARP_APPEND_PRIMARY && deadEntry(r2)) liveEntry = false; // (unused tail slot of k_primary's warp-private chunks)
+            else if (__float_as_int(hv.w) >= 0) { r0 = q.q0[src][i]; r1 = q.q1[src][i]; }
         }
         const V3 o = xyz(r0), d = xyz(r1);
         V3 T = mk(r0.w, r1.w, r2.x);
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
         Rng rng;
         bool shadeLights = false, shadeDelta = false;
         Surf s = {};
-        if (live) {
+        if (liveEntry) {
             rng.open(w, pid, uint32_t(__float_as_int(r2.w)));
             if (h.prim < 0) {
                 if (kind == XRTG_INT_DIRECT) addRadiance(q, pid, mk(float(0.18)));
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
             nd = nextDir;
             wantRay = (depth + 1 < w.maxDepth);
         }
-        if (live) ctr = rng.close();
+        if (liveEntry) ctr = rng.close();
         if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch);
     }
 }
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         stage(buf ^ 1, uint64_t(tile) + gridDim.x);
         stageWait(buf);
         // (warp-chunked appends leave up to kAppendChunk - 1 unused slots per warp at the end of the previous launch: marked dead)
-        if (XRT_WARP_APPEND && live && __float_as_uint(s_stage[buf][3][threadIdx.x].y) == kDeadPath) live = false;
+        if (XRT_WARP_APPEND && live && deadEntry(s_stage[buf][3][threadIdx.x])) live = false;
         // ---- phase 1: load the path, rebuild the surface, emitter test of depth 0 ----
         V3 d = mk(0.f), T = mk(0.f);
         uint32_t pid = 0, ctr = 0;
@@ -814,17 +816,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         uint32_t slot = 0;
         {
             const uint32_t mask = __ballot_sync(0xffffffffu, wantNext);
-            if (mask) {
-                const uint32_t cnt = __popc(mask), rank = __popc(mask & ((1u << lane) - 1u)), left = resEnd - resNext;
-                uint32_t nb = 0;
-                if (cnt > left) {
-                    if (lane == 0) nb = atomicAdd(nextCount, kAppendChunk);
-                    nb = __shfl_sync(0xffffffffu, nb, 0);
-                }
-                slot = rank < left ? resNext + rank : nb + (rank - left);
-                if (cnt > left) { resNext = nb + (cnt - left); resEnd = nb + kAppendChunk; }
-                else resNext += cnt;
-            }
+            if (mask) slot = warpReserve(nextCount, __popc(mask), resNext, resEnd).at(__popc(mask & ((1u << lane) - 1u)));
         }
 #else
         const uint32_t slot = blockAppend<kBlock / 32>(nextCount, wantNext, s_scratch);
@@ -837,10 +829,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         }
     }
 #if XRT_WARP_APPEND
-    for (uint32_t sl = resNext + lane; sl < resEnd; sl += 32u) { // the unused tail of this warp's last reservation
-        out2[sl] = make_float4(0.f, __uint_as_float(kDeadPath), 0.f, 0.f);
-        hitsOut[sl] = make_float4(FLT_MAX, 0.f, 0.f, __int_as_float(-1));
-    }
+    warpMarkDead(out2, hitsOut, resNext, resEnd); // the unused tail of this warp's last reservation
     statAdd(stats, kStatBounceEntries, nEntries);
 #else
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatBounceEntries, (unsigned long long)n);

@@ -468,6 +468,36 @@ __device__ __forceinline__ void blockAppend2(uint32_t* counter, bool wantA, bool
     slotB = base + __popc(ma) + __popc(mb & below);
     __syncthreads(); // scratch may be reused by the next call
 }
+// Warp-private output chunks (k_primary, k_bounce_small): a warp owns a reservation [resNext, resEnd) of kAppendChunk consecutive queue
+// slots and takes a new one with ONE global atomic when its `cnt` new entries do not fit; entries that still fit go to the old
+// chunk, so the only unused slots are the tail of a warp's LAST chunk, which warpMarkDead() flags with kDeadPath in the path word
+// (every consumer of such a queue skips those). No CTA barrier, no shared memory; must be called by all 32 lanes.
+struct WarpSlots {
+    uint32_t base0, left, base1;
+    __device__ __forceinline__ uint32_t at(uint32_t rank) const { return rank < left ? base0 + rank : base1 + (rank - left); }
+};
+__device__ __forceinline__ WarpSlots warpReserve(uint32_t* counter, uint32_t cnt, uint32_t& resNext, uint32_t& resEnd)
+{
+    WarpSlots s{resNext, resEnd - resNext, 0u};
+    if (cnt > s.left) {
+        uint32_t nb = 0;
+        if (laneId() == 0) nb = atomicAdd(counter, kAppendChunk);
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        s.base1 = nb;
+        resNext = nb + (cnt - s.left);
+        resEnd = nb + kAppendChunk;
+    }
+    else resNext += cnt;
+    return s;
+}
+__device__ __forceinline__ void warpMarkDead(float4* __restrict__ pathWords, float4* __restrict__ hits, uint32_t resNext, uint32_t resEnd)
+{
+    for (uint32_t sl = resNext + laneId(); sl < resEnd; sl += 32u) {
+        pathWords[sl] = make_float4(0.f, __uint_as_float(kDeadPath), 0.f, 0.f);
+        hits[sl] = make_float4(FLT_MAX, 0.f, 0.f, __int_as_float(-1));
+    }
+}
+__device__ __forceinline__ bool deadEntry(const float4& pathWord) { return __float_as_uint(pathWord.y) == kDeadPath; }
 // ---------------------------------------------------------------------------------------------------------
 // primary: ray generation (renderer.cpp:42-52, camera.h:49-60) FUSED with the bounce-0 closest hit. Primary rays are
 // coherent and most of them miss in the benchmark views (59 % Cornell, 86 % volume), so instead of writing 8.3 M rays,
@@ -541,6 +571,8 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     const uint32_t n = w.nPaths;
     TraceCounters tc;
     uint32_t nHits = 0, nScissored = 0;
+    uint32_t resNext = 0, resEnd = 0; // this warp's reservation of slots in the compact bounce-0 queue (XRT_WARP_APPEND_PRIMARY)
+    (void)resNext; (void)resEnd;
     // one path: ray generation, scissor, closest hit; misses are resolved here
     auto path = [&](uint32_t pid, V3& d, Hit& h, uint32_t& ctr) -> bool {
         if (pid >= n) return false;
@@ -602,11 +634,23 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
         const bool hitA = path(pidA, dA, hA, cA);
         const bool hitB = path(pidB, dB, hB, cB);
         uint32_t slotA, slotB;
+#if XRT_WARP_APPEND_PRIMARY
+        {
+            const uint32_t ma = __ballot_sync(0xffffffffu, hitA), mb = __ballot_sync(0xffffffffu, hitB), below = (1u << laneId()) - 1u;
+            const WarpSlots ws = warpReserve(q.ctrl + kCtrlRays, __popc(ma) + __popc(mb), resNext, resEnd);
+            slotA = ws.at(__popc(ma & below));
+            slotB = ws.at(__popc(ma) + __popc(mb & below));
+        }
+#else
         blockAppend2<kBlock / 32>(q.ctrl + kCtrlRays, hitA, hitB, s_scratch, slotA, slotB);
+#endif
         nHits += (hitA ? 1u : 0u) + (hitB ? 1u : 0u);
         if (hitA) emit(slotA, pidA, dA, hA, cA);
         if (hitB) emit(slotB, pidB, dB, hB, cB);
     }
+#if XRT_WARP_APPEND_PRIMARY
+    warpMarkDead(q.q2[0], q.hits, resNext, resEnd);
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
     statAdd(stats, kStatPrimaryHits, nHits);
     statAdd(stats, kStatScissored, nScissored); // reference-equivalent rays that were never traced

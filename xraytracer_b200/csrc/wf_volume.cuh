@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
         V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
         uint32_t pid = 0, ctr = 0;
         int depth = 0;
-        if (i < n) {
+        if (i < n && !(XRT_WARP_APPEND_PRIMARY && deadEntry(q.q2[src][i]))) {
             const float4 r0 = q.q0[src][i], r1 = q.q1[src][i], r2 = q.q2[src][i], hv = q.hits[i];
             pid = uint32_t(__float_as_int(r2.y));
             depth = __float_as_int(r2.z);
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
                 const uint32_t i = rank < left ? resNext + rank : nb + (rank - left);
                 if (nNeed > left) { resNext = nb + (nNeed - left); resEnd = nb + 32u; }
                 else resNext += nNeed;
-                if (state == kLaneIdle && i < n) {
+                if (state == kLaneIdle && i < n && !(XRT_WARP_APPEND_PRIMARY && deadEntry(q.q2[0][i]))) {
                     const float4 r0 = q.q0[0][i], r1 = q.q1[0][i], r2 = q.q2[0][i], hv = q.hits[i];
                     pid = uint32_t(__float_as_int(r2.y));
                     depth = __float_as_int(r2.z);

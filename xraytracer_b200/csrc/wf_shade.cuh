@@ -182,9 +182,9 @@ struct ShadeOut {
     int dst;
 };
 
-__device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, V3 d, float tmax, uint32_t pid, V3 c, uint32_t* scratch)
+__device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, V3 d, float tmax, uint32_t pid, V3 c, uint32_t (*scratch2)[kShadeWarps + 1], int& phase)
 {
-    const uint32_t slot = blockAppend(so.ctrlCur + kCtrlShadow, want, scratch);
+    const uint32_t slot = blockAppendAlt(so.ctrlCur + kCtrlShadow, want, scratch2, phase);
     if (want) {
         so.q.s0[slot] = make_float4(o.x, o.y, o.z, tmax);
         so.q.s1[slot] = make_float4(d.x, d.y, d.z, __int_as_float(int(pid)));
@@ -201,9 +201,9 @@ __device__ __forceinline__ void pushRayWarp(const ShadeOut& so, bool want, V3 o,
         so.q.q2[so.dst][slot] = make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr)));
     }
 }
-__device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 d, V3 T, uint32_t pid, int depth, uint32_t ctr, uint32_t* scratch)
+__device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 d, V3 T, uint32_t pid, int depth, uint32_t ctr, uint32_t (*scratch2)[kShadeWarps + 1], int& phase)
 {
-    const uint32_t slot = blockAppend(so.ctrlNext + kCtrlRays, want, scratch);
+    const uint32_t slot = blockAppendAlt(so.ctrlNext + kCtrlRays, want, scratch2, phase);
     if (want) {
         so.q.q0[so.dst][slot] = make_float4(o.x, o.y, o.z, T.x);
         so.q.q1[so.dst][slot] = make_float4(d.x, d.y, d.z, T.y);
@@ -215,7 +215,8 @@ __device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 
 // GI (:205-287), Whitted's Lambert/delta-light branch (:302-394). One thread per ray-queue entry of bounce b.
 __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQueues q, DWave w, int src, int bounce)
 {
-    __shared__ uint32_t s_scratch[kShadeWarps + 1];
+    __shared__ uint32_t s_scratch[2][kShadeWarps + 1]; // two buffers used alternately: two barriers per append (blockAppendAlt)
+    int appendPhase = 0;
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
                     }
                 }
                 const float bias = 0.01f;
-                pushShadow(so, want, s.pos + s.ng * bias, wi, tmax - bias, pid, c, s_scratch);
+                pushShadow(so, want, s.pos + s.ng * bias, wi, tmax - bias, pid, c, s_scratch, appendPhase);
             }
         }
         // ---- Whitted diffuse term over delta lights (integrator.h:328-343; PointLight/DistantLight light.cpp:120-142)
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
                     c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
                     want = true;
                 }
-                pushShadow(so, want, s.pos + s.ng * float(0.1), wi, tmax, pid, c, s_scratch);
+                pushShadow(so, want, s.pos + s.ng * float(0.1), wi, tmax, pid, c, s_scratch, appendPhase);
             }
         }
         // ---- BSDF bounce (integrator.h:271-283) ----
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
             wantRay = (depth + 1 < w.maxDepth);
         }
         if (liveEntry) ctr = rng.close();
-        if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch);
+        if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch, appendPhase);
     }
 }
 

@@ -448,6 +448,26 @@ __device__ __forceinline__ uint32_t blockAppend(uint32_t* counter, bool want, ui
     __syncthreads(); // scratch may be reused by the next call
     return slot;
 }
+// The same with TWO scratch buffers used alternately (`phase` flips on every call): the barriers of the next call protect the
+// previous call's buffer, so the third barrier goes away — two barriers per append instead of three.
+template <int NWARPS = kShadeWarps>
+__device__ __forceinline__ uint32_t blockAppendAlt(uint32_t* counter, bool want, uint32_t (*scratch2)[NWARPS + 1], int& phase)
+{
+    uint32_t* scratch = scratch2[phase];
+    phase ^= 1;
+    const uint32_t mask = __ballot_sync(0xffffffffu, want);
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    if (lane == 0) scratch[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) { const uint32_t c = scratch[w]; scratch[w] = total; total += c; }
+        scratch[NWARPS] = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    return scratch[NWARPS] + scratch[warp] + __popc(mask & ((1u << lane) - 1u));
+}
 // Two candidates per thread, one atomic and one barrier round per CTA: slots of a warp are laid out as [its A entries][its B entries].
 template <int NWARPS>
 __device__ __forceinline__ void blockAppend2(uint32_t* counter, bool wantA, bool wantB, uint32_t* scratch, uint32_t& slotA, uint32_t& slotB)

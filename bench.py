@@ -360,7 +360,7 @@ STAT_KEYS = ["closest_rays", "shadow_rays", "kernel_launches", "extend_ms", "sha
              "connect_launches", "dropped_samples"]
 
 
-def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src):
+def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src, wave_paths=0):
     """Roofline object of the workload's dominant kernel. `st` = rank 0's stage times and unit counts summed over the steps of
     the instrumented pass; `cst` = one pass with the node / triangle counters on."""
     ms_total = st["render_ms"]
@@ -370,14 +370,21 @@ def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src):
     is_volume = wl["integrator"].startswith("volume")
     tp = ROOT / "profiles" / (f"bounce_traffic_{name}.json" if st["bounce_entries"] > 0 else
                               (f"volume_traffic_{name}.json" if is_volume else f"extend_traffic_{name}.json"))
+    traffic_note = None
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("dram_bytes_per_launch")
+            # the ncu capture renders a smaller wave than the bench does (replaying a 10 GB wave 40 times per kernel is slow): the queue
+            # traffic is proportional to the paths of a wave, so the per-launch figure is scaled to this run's wave size
+            if traffic is not None and tj.get("wave_paths") and wave_paths:
+                traffic = traffic * wave_paths / tj["wave_paths"]
+                traffic_note = f"ncu capture of a wave of {tj['wave_paths']} paths, scaled linearly to this run's {wave_paths} paths per wave"
         except Exception:
             traffic = None
     n_cl = max(cst["closest_rays"], 1)
     nodes_per_ray, tris_per_ray = cst["nodes_visited"] / n_cl, cst["tris_tested"] / n_cl
-    common = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": traffic, "peak_source": peak_src, "share_of_step": share,
+    common = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "share_of_step": share,
               "timing": "CUDA events around every launch of the kernel (XRTG_FLAG_STAGE_TIMES) in an instrumented pass of the same K steps, "
                         "run right after the timed region; the timed region itself carries no instrumentation"}
     if st["bounce_entries"] > 0:
@@ -563,7 +570,7 @@ def run_workload(rig: Rig, name, wl, args, headline):
             "mrays_per_s": rays / (ms * 1e-3) / 1e6, "mrays_traced_per_s": st_all["rays_traced"] / (ms * 1e-3) / 1e6,
             "rays_per_sample": rays / samples, "rays_traced": int(st_all["rays_traced"] / steps), "rays_reference_equivalent": int(rays / steps),
             "gpu_launches": int(st_all["kernel_launches"]) + red.launches_per_step() * steps * rig.world,
-            "clocks": clk, "roofline": roofline_for(name, wl, info, st0, cst, paths_r0, peak, peak_src), "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": clk, "roofline": roofline_for(name, wl, info, st0, cst, paths_r0, peak, peak_src, wave_paths=min(my_spp, max(1, (64 << 20) // (W * H))) * W * H), "cpu_baseline": cpu, "e2e": e2e,
             "scene_build_ms": info["build_ms"], "bvh_build_ms": info["bvh_build_ms"], "scene_upload_ms": info["upload_ms"], "scene_create_call_ms": create_ms,
             "bvh_builder": ["host binned SAH", "GPU LBVH", "GPU ingest + PLOC + sweep-SAH top levels + eight-child collapse (csrc/gpu_build.cu)"][info["bvh_builder"]],
             "truncated_paths": int(st_all["truncated_paths"] / steps), "dropped_samples": int(st_all["dropped_samples"] / steps),

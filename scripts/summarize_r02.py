@@ -1,9 +1,10 @@
 """Turns the round-2 measurement artefacts in gpurun_out/ into the tracked summaries under profiles/ (needs no GPU).
 usage: python scripts/summarize_r02.py
 
-  gpurun_out/r2m_bench.json, r2m_bench_ref.json        -> profiles/r02_bench_n1.json, r02_bench_reference_arm.json
-  gpurun_out/r2m_launches_c3.csv                        -> profiles/r02_launches_c3.csv (+ _summary.csv)
-  gpurun_out/r2_prof_{c3,c4}_final.ncu-rep, r2_prof_c5_a.ncu-rep
+  (produced by `gpurun -- bash scripts/profile_pass.sh r2f`)
+  gpurun_out/r2f_bench.json, r2f_bench_ref.json        -> profiles/r02_bench_n1.json, r02_bench_reference_arm.json
+  gpurun_out/r2f_launches_c3.csv                        -> profiles/r02_launches_c3.csv (+ _summary.csv)
+  gpurun_out/r2f_prof_{c3,c3_primary,c4,c5}.ncu-rep
                                                         -> profiles/r02_ncu_full_{c3,c4,c5}.csv, the *_traffic_*.json files bench.py reads,
                                                            profiles/r02_budget_{bounce_small,primary,trace8,volume_paths}.md (phase budgets)
 """
@@ -37,11 +38,11 @@ def budget(rep, regex, index, symbol, phases, units=None):
     return subprocess.run(cmd, capture_output=True, text=True).stdout
 
 
-for src, dst in (("r2m_bench.json", "r02_bench_n1.json"), ("r2m_bench_ref.json", "r02_bench_reference_arm.json"), ("r2g_bench_n2.json", "r02_bench_n2_early.json")):
+for src, dst in (("r2f_bench.json", "r02_bench_n1.json"), ("r2f_bench_ref.json", "r02_bench_reference_arm.json"), ("r2f_bench_short.json", "r02_bench_short_for_launch_list.json")):
     if (G / src).exists():
         (P / dst).write_text(last_json(G / src) + "\n")
 
-f = G / "r2m_launches_c3.csv"
+f = G / "r2f_launches_c3.csv"
 if f.exists():
     rows = list(csv.reader(open(f)))
     start = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -57,7 +58,7 @@ if f.exists():
         a[0] += 1
         a[1] += v
     tot = sum(v[1] for v in agg.values())
-    out = ["# ncu launch list summary — bench.py --steps 2 --warmup 3 --spp 16 --side '' --no-cpu-baseline --no-e2e (workload c3), round 2 final build",
+    out = ["# ncu launch list summary — bench.py --steps 2 --warmup 3 --spp 64 --side= --no-cpu-baseline --no-e2e (workload c3, two waves of 32 spp per step), round 2 final build",
            "# ncu --metrics gpu__time_duration.sum --clock-control none; per-launch times are cold-cache and serialised: compare SHARES",
            f"# launches captured: {sum(v[0] for v in agg.values())}, total {tot / 1e3:.2f} ms", "kernel,launches,total_us,share"]
     out += [f"{k},{v[0]},{v[1]:.1f},{v[1] / tot:.4f}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
@@ -65,9 +66,9 @@ if f.exists():
     (P / "r02_launches_c3.csv").write_bytes(f.read_bytes())
     print("\n".join(out[2:9]))
 
-WL = {"c3": ("r2_prof_c3_final.ncu-rep", ("k_bounce_small",), "bounce_traffic", "scripts/profile_step.py c3 8: k_primary, then k_bounce_small at bounce 0, 1, 2 (two waves)"),
-      "c4": ("r2_prof_c4_final.ncu-rep", ("k_trace8<(bool)0",), "extend_traffic", "scripts/profile_step.py c4 4: k_raygen, then k_trace8 closest (<0,..>) / k_shade_surface / k_trace8 any-hit (<1,..>) at bounce 0, 1, 2"),
-      "c5": ("r2_prof_c5_a.ncu-rep", ("k_volume_paths",), "volume_traffic", "scripts/profile_step.py c5 8: k_volume_paths (every volume path to completion)")}
+WL = {"c3": ("r2f_prof_c3.ncu-rep", ("k_bounce_small",), "bounce_traffic", "scripts/profile_step.py c3 8 (one wave of 8 spp = 16.6 M paths): k_bounce_small at bounce 0, 1, 2"),
+      "c4": ("r2f_prof_c4.ncu-rep", ("k_trace8<(bool)0",), "extend_traffic", "scripts/profile_step.py c4 8 (one wave of 8 spp): k_raygen, then k_trace8 closest (<0,..>) / k_shade_surface / k_trace8 any-hit (<1,..>) at bounce 0, 1, 2"),
+      "c5": ("r2f_prof_c5.ncu-rep", ("k_volume_paths",), "volume_traffic", "scripts/profile_step.py c5 8 (one wave of 8 spp): k_volume_paths (every volume path to completion)")}
 for wl, (repname, pats, stem, title) in WL.items():
     rep = G / repname
     if not rep.exists():
@@ -94,40 +95,40 @@ for wl, (repname, pats, stem, title) in WL.items():
             tot.append(b)
     if tot:
         json.dump({"workload": wl, "kernel": pats[0], "dram_bytes_per_launch": sum(tot) / len(tot), "launches_captured": len(tot), "per_launch_bytes": tot,
+                   "wave_paths": 8 * 1920 * 1080,   # the capture renders one wave of 8 spp at 1080p; bench.py scales to its own wave size
                    "source": f"ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, {title}, round 2"},
                   open(P / f"{stem}_{wl}.json", "w"), indent=1)
 
 # ---- phase budgets ----
-rep = G / "r2_prof_c3_final.ncu-rep"
+rep = G / "r2f_prof_c3.ncu-rep"
 if rep.exists():
     md = ["# k_bounce_small — per-phase instruction budget (round 2, final build)\n",
-          "Source: `ncu --set full --clock-control none --import-source on` on `scripts/profile_step.py c3 8` (Cornell GI depth 3, 1080p, waves of 4 spp = 8.29 M paths),",
+          "Source: `ncu --set full --clock-control none --import-source on` on `scripts/profile_step.py c3 8` (Cornell GI depth 3, 1080p, one wave of 8 spp = 16.6 M paths),",
           "joined per SASS instruction with `nvdisasm -gi` line info by `scripts/ncu_phase_budget.py` (phase = source line ranges in `profiles/phases/k_bounce_small.json`).",
           "`warp instr` = `Instructions Executed` summed over the phase's SASS instructions; `per unit` = per warp-tile of 32 queue entries.\n"]
-    # (the capture window starts one launch early: launches 2, 3, 4 of the capture are bounce 0, 1, 2 of one wave)
-    for i, (b, entries) in enumerate(((0, None), (1, None), (2, None)), start=2):
+    for i, (b, entries) in enumerate(((0, None), (1, None), (2, None)), start=1):
         md.append(f"## bounce {b}\n")
         md.append(budget(rep, "k_bounce_small", i, "4fast14k_bounce_smallILb1", "k_bounce_small.json"))
     (P / "r02_budget_bounce_small.md").write_text("\n".join(md))
-rep = G / "r2_prof_c3_primary.ncu-rep"
+rep = G / "r2f_prof_c3_primary.ncu-rep"
 if rep.exists():
     md = ["# k_primary — per-phase instruction budget (round 2, final build: screen-space candidate masks)\n",
-          "Source: `ncu --set full` on `scripts/profile_step.py c3 8`, one wave of 4 spp = 8.29 M paths (36 % of them outside the scissor).\n",
-          budget(rep, "k_primary<", 1, "4fast9k_primaryILb0ELb0", "k_primary.json")]
+          "Source: `ncu --set full` on `scripts/profile_step.py c3 8`, one wave of 8 spp = 16.6 M paths (36 % of them outside the scissor).\n",
+          budget(rep, "k_primary", 1, "4fast9k_primaryILb0ELb0", "k_primary.json")]
     (P / "r02_budget_primary.md").write_text("\n".join(md))
-rep = G / "r2_prof_c4_final.ncu-rep"
+rep = G / "r2f_prof_c4.ncu-rep"
 if rep.exists():
     md = ["# k_trace8 — per-phase instruction budget on the 999,698-triangle scene (round 2, final build)\n",
-          "Source: `ncu --set full` on `scripts/profile_step.py c4 4` (one wave of 4 spp = 8.29 M paths), bounce 0 / 1 closest hit and the bounce-1 any-hit launch.\n"]
+          "Source: `ncu --set full` on `scripts/profile_step.py c4 8` (one wave of 8 spp = 16.6 M paths, device-built PLOC tree), bounce 0 / 1 closest hit and the bounce-1 any-hit launch.\n"]
     for title, rx, i, sym in (("closest hit, bounce 0 (coherent primary rays)", r"k_trace8<\(bool\)0", 1, "k_trace8ILb0ELb0ELi8"),
                               ("closest hit, bounce 1 (incoherent)", r"k_trace8<\(bool\)0", 2, "k_trace8ILb0ELb0ELi8"),
                               ("any hit, bounce 1 (shadow rays)", r"k_trace8<\(bool\)1", 2, "k_trace8ILb1ELb0ELi8")):
         md.append(f"## {title}\n")
         md.append(budget(rep, rx, i, sym, "k_trace8.json"))
     (P / "r02_budget_trace8.md").write_text("\n".join(md))
-rep = G / "r2_prof_c5_a.ncu-rep"
+rep = G / "r2f_prof_c5.ncu-rep"
 if rep.exists():
     md = ["# k_volume_paths — per-phase instruction budget on workload c5 (round 2)\n",
-          "Source: `ncu --set full` on `scripts/profile_step.py c5 8`.\n", budget(rep, "k_volume_paths", 1, "4fast14k_volume_pathsILb0ELi4", "k_volume_paths.json")]
+          "Source: `ncu --set full` on `scripts/profile_step.py c5 8` (one wave of 8 spp, 3-D texture lookups).\n", budget(rep, "k_volume_paths", 1, "4fast14k_volume_pathsILb0ELi4", "k_volume_paths.json")]
     (P / "r02_budget_volume_paths.md").write_text("\n".join(md))
 print("written:", sorted(p.name for p in P.glob("r02_*")))

@@ -271,13 +271,14 @@ __device__ __forceinline__ V3 transmittance(const DScene& sc, const DMedium& m, 
 //   trackStep  : see above.
 //   volumePost : NEE through the medium (VolumePathTracingNEE), next ray. Returns true if the path continues.
 enum { kVolEnd = 0, kVolTrack = 1, kVolSampled = 2 };
-__device__ __forceinline__ int volumePre(const DScene& sc, const DMedium* media, const DGrid* grids, bool nee, V3 o, V3 d, V3& T, const Hit& h, int depth,
+// (prims: the shading records, sc.prims or a shared-memory copy of them — read through a generic pointer)
+__device__ __forceinline__ int volumePre(const DScene& sc, const float4* prims, const DMedium* media, const DGrid* grids, bool nee, V3 o, V3 d, V3& T, const Hit& h, int depth,
                                          Rng& rng, int& mi, TrackState& ts, TrackResult& r, bool& hasContrib, V3& contrib)
 {
     hasContrib = false;
     if (h.prim < 0) return kVolEnd; // a miss adds throughput*background*(depth!=0) = 0
     Surf s;
-    makeSurf(sc, o, d, h, s);
+    makeSurfT<true>(sc, prims, o, d, h, s);
     if (depth > 0) {
         const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
         if (rng.next() >= p) return kVolEnd;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
             int mi = -1;
             TrackState ts;
             TrackResult r;
-            const int what = volumePre(sc, sc.media, sc.grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
+            const int what = volumePre(sc, sc.prims, sc.media, sc.grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
             if (hasContrib) addRadiance(q, pid, contrib);
             if (what != kVolEnd) {
                 if (what == kVolTrack) {
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_volume(DScene sc, DQueues q, D
 //   kLaneIdle  : refilled from the compact bounce-0 queue (one atomic per 32 entries per warp)
 // One launch per wave, no host round trip.
 enum { kLaneIdle = 0, kLanePre, kLaneTrack, kLaneWalked, kLanePost };
+constexpr int kVolPrimsSmem = 16; // shading records (64 B each) k_volume_paths stages in shared memory
 constexpr int kMediaSmem = 8; // media / grids staged in shared memory by k_volume_paths (the host falls back to the wavefront form above that)
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueues q, DWave w, int brute, int maxIter, int threshold, int stepsPerVote, unsigned long long* stats)
@@ -424,8 +426,13 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
     __shared__ int s_stack[kStackSmem * kBlock];
     __shared__ DMedium s_media[kMediaSmem];
     __shared__ DGrid s_grids[kMediaSmem];
+    __shared__ float4 s_prims[4 * kVolPrimsSmem]; // the shading records of a scene with few primitives (a box, a light, a few walls)
     if (int(threadIdx.x) < min(sc.nMedia, kMediaSmem)) s_media[threadIdx.x] = sc.media[threadIdx.x];
     if (int(threadIdx.x) < min(sc.nGrids, kMediaSmem)) s_grids[threadIdx.x] = sc.grids[threadIdx.x];
+    const bool primsInSmem = sc.nPrims <= kVolPrimsSmem;
+    if (primsInSmem)
+        for (int k = threadIdx.x; k < 4 * sc.nPrims; k += blockDim.x) s_prims[k] = sc.prims[k];
+    const float4* prims = primsInSmem ? s_prims : sc.prims;
     __syncthreads();
     const DMedium* media = s_media;
     const DGrid* grids = s_grids;
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_volume_paths(DScene sc, DQueue
             if (state == kLanePre) {
                 V3 contrib;
                 bool hasContrib;
-                const int what = volumePre(sc, media, grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
+                const int what = volumePre(sc, prims, media, grids, nee, o, d, T, h, depth, rng, mi, ts, r, hasContrib, contrib);
                 if (hasContrib) add(contrib);
                 if (what == kVolEnd) finish();
                 else state = what == kVolTrack ? kLaneTrack : kLanePost;

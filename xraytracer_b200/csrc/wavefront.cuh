@@ -53,12 +53,17 @@ namespace xrt {
 #define XRT_WARP_APPEND_PRIMARY 0
 #endif
 
+#ifndef XRT_VOL_MINB
+#define XRT_VOL_MINB 4 // resident CTAs per SM k_volume_paths is compiled for (register budget 65536 / (128 x this))
+#endif
+
 namespace XRT_NS {
 
 constexpr bool kExact = (XRT_EXACT != 0);
 constexpr int kBlock = 128;          // threads per CTA of the traversal kernels (the surface shade kernel uses kShadeBlock)
 constexpr int kStackSmem = 24;       // traversal stack entries kept in shared memory per thread
 constexpr int kStackLocal = 40;      // overflow entries (local memory) of the run-to-completion walks; host builder depth limit is 56
+constexpr int kVolMinBlocks = XRT_VOL_MINB;
 constexpr int kStackLocalDeep = 104; // ... of k_trace, the kernel of deep trees: two-child trees of up to 120 levels (device-built
                                      // PLOC trees are deeper than top-down SAH ones: 41-53 levels on the 1 M-triangle scene)
 constexpr float kPI = 3.14159265359; // geometry.h:10

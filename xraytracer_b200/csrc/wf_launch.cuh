@@ -149,8 +149,8 @@ inline void launchShadeVolume(cudaStream_t st, const DScene& sc, const DQueues& 
 inline void launchVolumePaths(cudaStream_t st, const DScene& sc, const DQueues& q, const DWave& w, bool brute, int maxIter, int threshold, int stepsPerVote, bool count,
                               unsigned long long* stats)
 {
-    if (count) k_volume_paths<true, 4><<<gridFor((const void*)k_volume_paths<true, 4>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
-    else k_volume_paths<false, 4><<<gridFor((const void*)k_volume_paths<false, 4>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    if (count) k_volume_paths<true, kVolMinBlocks><<<gridFor((const void*)k_volume_paths<true, kVolMinBlocks>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
+    else k_volume_paths<false, kVolMinBlocks><<<gridFor((const void*)k_volume_paths<false, kVolMinBlocks>), kBlock, 0, st>>>(sc, q, w, brute, maxIter, threshold, stepsPerVote, stats);
 }
 inline void launchAccumulate(cudaStream_t st, const DQueues& q, const DWave& w, float* accum, unsigned long long* stats)
 {

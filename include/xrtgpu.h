@@ -399,6 +399,12 @@ int xrtg_scene_selfcheck(xrtg_scene* scene, int* n_errors);
  * Returns 0 if the tree is valid, a negative xrtg_status otherwise; the out parameters may be NULL. */
 int xrtg_bvh_selftest(const float* tris9, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost);
 
+/* Host-only structural check of the sweep-SAH builder that splits the top levels of a device-built tree (csrc/gpu_build.cu:
+ * TopBuilder; no CUDA device needed): n clusters given by their boxes (lo3 / hi3 = n * 3 floats) and triangle counts (NULL = 1
+ * each) — every cluster referenced exactly once, every node's box the union of its children's, counts adding up. *depth = depth of
+ * the tree (coincident boxes must give a logarithmic depth: equal-cost splits take the most balanced one). */
+int xrtg_top_sah_selftest(const float* lo3, const float* hi3, const uint32_t* counts, int n, int by_clusters, int* depth);
+
 /* Host-only check of the plane-paired triangle block that scenes of at most 64 triangles are traced from (no CUDA device
  * needed): builds the block over n triangles (9 floats each; emitter_flags[i] & 1 marks emitter proxies, may be NULL) and
  * verifies that every triangle sits in exactly one record of the closest-hit section, every non-emitter in exactly one

@@ -141,7 +141,7 @@ GPU_SYMBOLS = ["xrtg_abi_version", "xrtg_device_count", "xrtg_last_error", "xrtg
                "xrtg_scene_get_info", "xrtg_scene_destroy", "xrtg_render", "xrtg_render_device", "xrtg_trace_primary",
                "xrtg_trace_rays", "xrtg_image_to_u8", "xrtg_bvh_selftest", "xrtg_small_scene_selftest", "xrtg_scene_create_multi",
                "xrtg_scene_device_count", "xrtg_scene_set_tuning", "xrtg_exchange_buffer", "xrtg_ipc_export", "xrtg_ipc_open",
-               "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8", "xrtg_scene_check_guards", "xrtg_scene_selfcheck"]
+               "xrtg_ipc_close", "xrtg_reduce_finalize", "xrtg_render_u8", "xrtg_scene_check_guards", "xrtg_scene_selfcheck", "xrtg_top_sah_selftest"]
 
 GPU_LIB = Path(os.environ["XRT_GPU_LIB"]) if os.environ.get("XRT_GPU_LIB") else PKG / "csrc" / "libxrtgpu.so"   # (override: A/B builds)
 HOST_LIB = PKG / "host" / "libxrthost.so"
@@ -190,6 +190,7 @@ def gpu():
     lib.xrtg_scene_set_tuning.argtypes = [VP, P(Tuning)]
     lib.xrtg_scene_check_guards.argtypes = [VP, P(C.c_int)]
     lib.xrtg_scene_selfcheck.argtypes = [VP, P(C.c_int)]
+    lib.xrtg_top_sah_selftest.argtypes = [VP, VP, VP, C.c_int, C.c_int, P(C.c_int)]
     lib.xrtg_exchange_buffer.argtypes = [VP, C.c_int, C.c_size_t, P(VP)]
     lib.xrtg_ipc_export.argtypes = [VP, VP]
     lib.xrtg_ipc_open.argtypes = [VP, VP, P(VP)]

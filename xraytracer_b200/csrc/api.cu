@@ -1319,6 +1319,15 @@ int xrtg_scene_selfcheck(xrtg_scene* s, int* n_errors)
     return 0;
 }
 
+int xrtg_top_sah_selftest(const float* lo3, const float* hi3, const uint32_t* counts, int n, int by_clusters, int* depth)
+{
+    if (n < 1 || !lo3 || !hi3) return fail(XRTG_ERR_INVALID, "bad selftest arguments");
+    const int d = topSahSelftest(lo3, hi3, counts, n, by_clusters);
+    if (depth) *depth = d;
+    if (d < 0) return fail(XRTG_ERR_INVALID, "selftest: inconsistent top-level tree");
+    return 0;
+}
+
 int xrtg_bvh_selftest(const float* tri, int n, int max_leaf, int* n_nodes, int* depth, float* sah_cost)
 {
     if (n < 0 || (n > 0 && !tri) || max_leaf < 1 || max_leaf > 4) return fail(XRTG_ERR_INVALID, "bad selftest arguments");

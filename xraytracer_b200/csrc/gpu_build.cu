@@ -626,6 +626,52 @@ void launchIngest(const xrtg_triangle* dRaw, const MeshRange* dRanges, int nRang
     k_ingest<<<(nTris + 127) / 128, 128, 0, st>>>(dRaw, dRanges, nRanges, nTris, trisId, ftrisId, prims);
 }
 
+// Host-only check of the top-level builder: splits `n` clusters (boxes lo/hi, triangle counts) and verifies that every cluster is
+// referenced exactly once, that every node's box is the union of its children's, that counts add up and that the depth stays
+// logarithmic on coincident boxes. Returns the depth of the tree, or -1 on an inconsistency.
+int topSahSelftest(const float* lo3, const float* hi3, const uint32_t* counts, int n, int byClusters)
+{
+    if (n < 1) return -1;
+    TopBuilder T;
+    T.byClusters = byClusters != 0;
+    T.nodes.resize(static_cast<size_t>(n));
+    T.order.resize(static_cast<size_t>(n));
+    for (int k = 0; k < n; ++k) {
+        TopCluster& c = T.nodes[size_t(k)];
+        for (int a = 0; a < 3; ++a) { c.lo[a] = lo3[3 * k + a]; c.hi[a] = hi3[3 * k + a]; }
+        c.count = counts ? counts[k] : 1u;
+        c.cost = TopBuilder::harea(c.lo, c.hi) * float(c.count);
+        c.leaf = c.count <= 4;
+        c.id = k;
+        T.order[size_t(k)] = k;
+    }
+    T.nodes.reserve(2 * size_t(n));
+    const int root = T.build(0, n);
+    if (int(T.children.size()) != n - 1 || root != int(T.nodes.size()) - 1) return -1;
+    std::vector<int> seen(static_cast<size_t>(n), 0);
+    int maxDepth = 0;
+    bool ok = true;
+    struct Item { int node, depth; };
+    std::vector<Item> stack{{root, 1}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        maxDepth = std::max(maxDepth, it.depth);
+        if (it.node < n) { seen[size_t(it.node)]++; continue; }
+        const int2 ch = T.children[size_t(it.node - n)];
+        const TopCluster &N = T.nodes[size_t(it.node)], &L = T.nodes[size_t(ch.x)], &R = T.nodes[size_t(ch.y)];
+        if (ch.x >= it.node || ch.y >= it.node) ok = false; // children are created before their parent
+        if (N.count != L.count + R.count) ok = false;
+        for (int a = 0; a < 3; ++a)
+            if (N.lo[a] != std::min(L.lo[a], R.lo[a]) || N.hi[a] != std::max(L.hi[a], R.hi[a])) ok = false;
+        stack.push_back({ch.x, it.depth + 1});
+        stack.push_back({ch.y, it.depth + 1});
+    }
+    for (int k = 0; k < n; ++k)
+        if (seen[size_t(k)] != 1) ok = false;
+    return ok ? maxDepth : -1;
+}
+
 void launchScatterPrims(const float4* dRecs, const int* dIds, int count, float4* prims, cudaStream_t st)
 {
     if (count > 0) k_scatter_prims<<<(count + 127) / 128, 128, 0, st>>>(dRecs, dIds, count, prims);

@@ -29,6 +29,9 @@ void launchIngest(const xrtg_triangle* dRaw, const MeshRange* dRanges, int nRang
 // prims[4 * ids[k] .. +4) = recs[4 * k .. +4): shading records of the analytic spheres / boxes (built on the host, there are few).
 void launchScatterPrims(const float4* dRecs, const int* dIds, int count, float4* prims, cudaStream_t st);
 
+// Host-only structural check of the top-level sweep-SAH builder (no CUDA device needed); returns the depth of the tree or -1.
+int topSahSelftest(const float* lo3, const float* hi3, const uint32_t* counts, int n, int byClusters);
+
 struct PlocParams {
     int radius = 16;          // neighbour-search window on each side of a cluster in Morton order
     float traversalCost = 1.f; // SAH: cost of one node step relative to one triangle test (leaf decision)

@@ -778,6 +778,7 @@ DQueues makeQueues(xrtg_scene* s)
     q.s2 = static_cast<float4*>(s->s2.p);
     q.radiance = static_cast<float4*>(s->radiance.p);
     q.ctrl = static_cast<uint32_t*>(s->ctrl.p);
+    q.stats = static_cast<unsigned long long*>(s->stats.p);
     return q;
 }
 

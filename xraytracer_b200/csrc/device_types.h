@@ -93,6 +93,7 @@ struct DQueues {
     float4 *s0, *s1, *s2;          // shadow queue
     float4* radiance;              // per path id: rgb | unused
     uint32_t* ctrl;                // per bounce b: ctrl[8b+0]=#rays  +1=#shadow  +2..+4 = work-fetch cursors
+    unsigned long long* stats;     // device-side statistics (kStat*), for kernels that take no separate pointer
 };
 
 // k_bounce_small appends survivors per warp from warp-private chunks of kAppendChunk output slots; the slots a warp has not used at

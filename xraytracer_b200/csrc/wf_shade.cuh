@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
 {
     __shared__ uint32_t s_scratch[2][kShadeWarps + 1]; // two buffers used alternately: two barriers per append (blockAppendAlt)
     int appendPhase = 0;
+    uint32_t nUntraced = 0;
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
@@ -307,6 +308,11 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
                         const V3 fr = evalBxDF(s);
                         c = T * (fr * Lr * cs / pdf);
                         want = true;
+                        // Throughput instantiation: a contribution that is exactly zero (surface facing away from the light: cs = 0,
+                        // or the light's back side: Lr = 0) cannot change the image whatever Scene::occluded (scene.cpp:202-211)
+                        // returns, so the shadow ray is counted as the reference's call but not traced (NaN contributions compare
+                        // unequal to zero and keep their ray). On the 1 M-triangle scene that is a quarter of the shadow rays.
+                        if (!kExact && c.x == 0.f && c.y == 0.f && c.z == 0.f) { want = false; ++nUntraced; }
                     }
                 }
                 const float bias = 0.01f;
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
                     else { wi = -xyz(L.p_kind); pdf = 1.0f; tmax = FLT_MAX; }
                     c = evalBxDF(s) * xyz(L.L) * smax(0.f, dot(s.ns, wi)) / pdf;
                     want = true;
+                    if (!kExact && c.x == 0.f && c.y == 0.f && c.z == 0.f) { want = false; ++nUntraced; } // (as above)
                 }
                 pushShadow(so, want, s.pos + s.ng * float(0.1), wi, tmax, pid, c, s_scratch, appendPhase);
             }
@@ -347,6 +354,9 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
         }
         if (liveEntry) ctr = rng.close();
         if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch, appendPhase);
+    }    if (!kExact) { // reference-equivalent shadow rays that were not traced: counted as calls, subtracted from rays_traced
+        statAdd(q.stats, kStatShadow, nUntraced);
+        statAdd(q.stats, kStatScissored, nUntraced);
     }
 }
 
@@ -511,6 +521,7 @@ struct SmallTracer {
     __device__ __forceinline__ bool occluded(const DScene& sc, bool want, V3 o, V3 d, float tmax, bool outsideHull = false) const
     {
         if constexpr (GROUPED) {
+            if (!__any_sync(0xffffffffu, want)) return false; // (e.g. a warp of paths that all face away from the light)
             const bool full = __any_sync(0xffffffffu, want && outsideHull);
             bool occ = groupedAnyHit(full ? secOccFull : secOcc, o, d, want ? tmax : -1.f);
             if (want && !occ)
@@ -625,7 +636,7 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
     float4* __restrict__ out1 = src ? q.q1[0] : q.q1[1];
     float4* __restrict__ out2 = src ? q.q2[0] : q.q2[1];
     const int kind = w.integrator;
-    uint32_t nClosest = 0, nShadow = 0;
+    uint32_t nClosest = 0, nShadow = 0, nUntraced = 0;
 #if XRT_WARP_APPEND
     const uint32_t lane = laneId();
     uint32_t resNext = 0, resEnd = 0, nEntries = 0; // this warp's reservation of output slots; live entries consumed
@@ -749,6 +760,9 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
                         c = T * (fr * Lr * cs / pdf);
                         want = true;
                         ++nShadow;
+                        // an exactly-zero contribution needs no shadow ray (see k_shade_surface); a warp whose lanes all face away
+                        // from the light skips the occluder loop altogether, and the plane votes see fewer reachable planes
+                        if (!kExact && c.x == 0.f && c.y == 0.f && c.z == 0.f) { want = false; ++nUntraced; }
                     }
                 }
                 const float bias = 0.01f;
@@ -837,4 +851,5 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
 #endif
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatShadow, nShadow);
+    if (!kExact) statAdd(stats, kStatScissored, nUntraced); // counted as the reference's calls, not traced
 }

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
 {
     __shared__ uint32_t s_scratch[2][kShadeWarps + 1]; // two buffers used alternately: two barriers per append (blockAppendAlt)
     int appendPhase = 0;
-    uint32_t nUntraced = 0;
+    uint32_t nUntraced = 0, nUntracedClosest = 0;
     uint32_t* ctrl = q.ctrl + bounce * kCtrlStride;
     const uint32_t n = ctrl[kCtrlRays];
     ShadeOut so{q, ctrl + kCtrlStride, ctrl, src ^ 1};
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
                 }
                 else { // Indirect / GI
                     bool alive = true;
-                    if (depth > 0) { // russian roulette (integrator.h:223-231)
+                    if (kExact && depth > 0) { // russian roulette (integrator.h:223-231); throughput instantiation: already applied, see below
                         const float p = smin((T.x + T.y + T.z) / 3.0f, 1.0f);
                         if (rng.next() >= p) alive = false;
                         else T = T / mk(p);
@@ -351,12 +351,23 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
             no = s.pos + s.ng * 0.01f;
             nd = nextDir;
             wantRay = (depth + 1 < w.maxDepth);
+            // Throughput instantiation: the Russian roulette of depth + 1 (integrator.h:223-231) is decided HERE, before the ray is
+            // traced. The reference intersects first and rolls afterwards, but a path that loses the roll contributes nothing more
+            // whatever it hit (the background of these integrators is black), and the roll is the next draw of this path's own
+            // counter stream either way — same draws, same decisions, same image; the rays of the losers (a third of the
+            // bounce >= 1 rays on the 1 M-triangle scene) are counted as the reference's Scene::intersect calls but never traced.
+            if (!kExact && wantRay) {
+                const float p = smin((nT.x + nT.y + nT.z) / 3.0f, 1.0f);
+                if (rng.next() >= p) { wantRay = false; ++nUntracedClosest; }
+                else nT = nT / mk(p);
+            }
         }
         if (liveEntry) ctr = rng.close();
         if (kind == XRTG_INT_INDIRECT || kind == XRTG_INT_GI) pushRay(so, wantRay, no, nd, nT, pid, depth + 1, ctr, s_scratch, appendPhase);
-    }    if (!kExact) { // reference-equivalent shadow rays that were not traced: counted as calls, subtracted from rays_traced
+    }    if (!kExact) { // reference-equivalent rays that were not traced: counted as calls, subtracted from rays_traced
         statAdd(q.stats, kStatShadow, nUntraced);
-        statAdd(q.stats, kStatScissored, nUntraced);
+        statAdd(q.stats, kStatClosest, nUntracedClosest);
+        statAdd(q.stats, kStatScissored, nUntraced + nUntracedClosest);
     }
 }
 

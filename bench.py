@@ -357,7 +357,7 @@ class FusedReduce:
 
 STAT_KEYS = ["closest_rays", "shadow_rays", "kernel_launches", "extend_ms", "shade_ms", "connect_ms", "extend_launches", "tracking_steps",
              "primary_hits", "bounce_entries", "bounce_launches", "shade_launches", "rays_traced", "truncated_paths", "other_ms", "render_ms",
-             "connect_launches", "dropped_samples"]
+             "connect_launches", "dropped_samples", "untraced_closest", "untraced_shadow"]
 
 
 def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src, wave_paths=0):
@@ -382,7 +382,7 @@ def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src, wave_paths=0
                 traffic_note = f"ncu capture of a wave of {tj['wave_paths']} paths, scaled linearly to this run's {wave_paths} paths per wave"
         except Exception:
             traffic = None
-    n_cl = max(cst["closest_rays"], 1)
+    n_cl = max(cst["closest_rays"] - cst.get("untraced_closest", 0), 1)   # closest-hit rays the kernels TRACED in the counter pass
     nodes_per_ray, tris_per_ray = cst["nodes_visited"] / n_cl, cst["tris_tested"] / n_cl
     common = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "share_of_step": share,
               "timing": "CUDA events around every launch of the kernel (XRTG_FLAG_STAGE_TIMES) in an instrumented pass of the same K steps, "
@@ -423,19 +423,20 @@ def roofline_for(name, wl, info, st, cst, paths_r0, peak, peak_src, wave_paths=0
     # deep BVH: closest-hit traversal stage (k_trace on the wide tree). COMPULSORY HBM bytes: 32 B ray read + 16 B hit write per
     # ray + the tree and triangle arrays once per launch; node / triangle re-fetches are served by L1/L2 and reported as `fetch`
     # = rays x (node bytes x nodes visited + triangle bytes x triangles tested) / time (SURVEY §8(d)'s B_ray).
-    ext_ms, ext_launches, closest = st["extend_ms"], max(st["extend_launches"], 1), st["closest_rays"]
+    # (rays TRACED by the stage: the reference-equivalent count minus the extension rays of Russian-roulette losers / scissored primaries)
+    ext_ms, ext_launches, closest = st["extend_ms"], max(st["extend_launches"], 1), st["closest_rays"] - st.get("untraced_closest", 0)
     node_bytes = {8: 80.0, 4: 128.0}.get(info["wide_arity"], 64.0)
     n_nodes = info["n_wide_nodes"] if info["wide_arity"] else info["n_bvh_nodes"]
     bvh_bytes = node_bytes * n_nodes + 64.0 * info["n_triangles"]
     if st["primary_hits"] > 0:   # fused primary kernel in use (shallow BVHs)
-        hbm_bytes = paths_r0 * 16.0 + st["primary_hits"] * 64.0 + (closest - paths_r0) * 48.0 + ext_launches * bvh_bytes
+        hbm_bytes = paths_r0 * 16.0 + st["primary_hits"] * 64.0 + max(st["closest_rays"] - paths_r0 - st.get("untraced_closest", 0), 0) * 48.0 + ext_launches * bvh_bytes
     else:
         hbm_bytes = closest * 48.0 + ext_launches * bvh_bytes
     fetch_bytes = closest * (node_bytes * nodes_per_ray + 64.0 * tris_per_ray)
     achieved = hbm_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
     return dict(common, kernel="closest-hit stage (k_trace: resumable traversal of the wide BVH, plane-equation triangle records)",
                 achieved=achieved, frac=achieved / peak, algorithmic_bytes_per_launch=hbm_bytes / ext_launches,
-                bytes_per_ray_hbm=hbm_bytes / max(closest, 1.0), bvh_bytes=bvh_bytes,
+                bytes_per_ray_hbm=hbm_bytes / max(closest, 1.0), bvh_bytes=bvh_bytes, rays_traced_by_stage=int(closest),
                 fetch={"achieved": fetch_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0, "unit": "GB/s",
                        "level": f"L1/L2 (node + triangle fetches, {int(node_bytes)} B and 64 B records)",
                        "bytes_per_ray": node_bytes * nodes_per_ray + 64.0 * tris_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,

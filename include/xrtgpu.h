@@ -248,6 +248,9 @@ typedef struct xrtg_stats {
                                 scattering event; the reference's loop (integrator.h:418) is unbounded. 0 on every shipped scene */
     float reduce_ms;         /* multi-GPU scenes: the fused peer-memory reduce + finalize (CUDA events on device 0)            */
     int32_t n_devices;       /* devices that took part in the render                                                           */
+    uint64_t untraced_closest; /* of closest_rays: counted as the reference's Scene::intersect calls but not traced — primary samples
+                                  outside the screen-space scissor, extension rays of paths that lost the next Russian roulette     */
+    uint64_t untraced_shadow;  /* of shadow_rays: NEE samples whose contribution is exactly zero (throughput instantiation)           */
 } xrtg_stats;
 
 /* Closest-hit record of the parity hooks. prim = global primitive id (-1 = miss). */

@@ -67,7 +67,7 @@ if f.exists():
     print("\n".join(out[2:9]))
 
 WL = {"c3": ("r2f_prof_c3.ncu-rep", ("k_bounce_small",), "bounce_traffic", "scripts/profile_step.py c3 8 (one wave of 8 spp = 16.6 M paths): k_bounce_small at bounce 0, 1, 2"),
-      "c4": ("r2f_prof_c4.ncu-rep", ("k_trace8<(bool)0",), "extend_traffic", "scripts/profile_step.py c4 8 (one wave of 8 spp): k_raygen, then k_trace8 closest (<0,..>) / k_shade_surface / k_trace8 any-hit (<1,..>) at bounce 0, 1, 2"),
+      "c4": ("r2f_prof_c4.ncu-rep", ("k_trace8<(bool)0", "k_trace8<0"), "extend_traffic", "scripts/profile_step.py c4 8 (one wave of 8 spp): k_raygen, then k_trace8 closest (<0,..>) / k_shade_surface / k_trace8 any-hit (<1,..>) at bounce 0, 1, 2"),
       "c5": ("r2f_prof_c5.ncu-rep", ("k_volume_paths",), "volume_traffic", "scripts/profile_step.py c5 8 (one wave of 8 spp): k_volume_paths (every volume path to completion)")}
 for wl, (repname, pats, stem, title) in WL.items():
     rep = G / repname

@@ -87,7 +87,8 @@ class Stats(C.Structure):
                 ("extend_ms", C.c_float), ("connect_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("primary_hits", C.c_uint64),
                 ("bounce_entries", C.c_uint64), ("bounce_launches", C.c_uint64), ("rays_traced", C.c_uint64),
-                ("truncated_paths", C.c_uint64), ("reduce_ms", C.c_float), ("n_devices", C.c_int32)]
+                ("truncated_paths", C.c_uint64), ("reduce_ms", C.c_float), ("n_devices", C.c_int32),
+                ("untraced_closest", C.c_uint64), ("untraced_shadow", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -105,7 +105,7 @@ constexpr uint32_t kAppendSlack = 1u << 20;
 enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kCtrlFetchShade = 3, kCtrlFetchConnect = 4 };
 
 // device-side statistics (uint64 each)
-enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatScissored, kStatTruncated, kStatCount };
+enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatScissored, kStatTruncated, kStatUntracedClosest, kStatUntracedShadow, kStatCount };
 
 struct DWave {
     int width, height;

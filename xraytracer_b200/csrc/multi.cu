@@ -287,6 +287,7 @@ int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params*
             t.extend_launches += a.extend_launches; t.shade_launches += a.shade_launches; t.connect_launches += a.connect_launches;
             t.primary_hits += a.primary_hits; t.bounce_entries += a.bounce_entries; t.bounce_launches += a.bounce_launches;
             t.rays_traced += a.rays_traced; t.truncated_paths += a.truncated_paths;
+            t.untraced_closest += a.untraced_closest; t.untraced_shadow += a.untraced_shadow;
             t.render_ms = std::max(t.render_ms, a.render_ms); // devices run concurrently: the slowest one sets the time
             t.extend_ms = std::max(t.extend_ms, a.extend_ms); t.connect_ms = std::max(t.connect_ms, a.connect_ms);
             t.shade_ms = std::max(t.shade_ms, a.shade_ms); t.other_ms = std::max(t.other_ms, a.other_ms);

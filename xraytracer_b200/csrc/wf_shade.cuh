@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
             }
         }
         // ---- BSDF bounce (integrator.h:271-283) ----
+        if (!kExact && depth + 1 >= w.maxDepth) wantRay = false; // (last depth: nothing follows the BSDF sample on the path's counter stream)
         if (wantRay) {
             float pdf = 1.0f;
             V3 nextDir = mk(0.f);
@@ -368,6 +369,8 @@ __global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQu
         statAdd(q.stats, kStatShadow, nUntraced);
         statAdd(q.stats, kStatClosest, nUntracedClosest);
         statAdd(q.stats, kStatScissored, nUntraced + nUntracedClosest);
+        statAdd(q.stats, kStatUntracedShadow, nUntraced);
+        statAdd(q.stats, kStatUntracedClosest, nUntracedClosest);
     }
 }
 
@@ -548,6 +551,8 @@ struct SmallTracer {
     }
     __device__ __forceinline__ void closest(const DScene& sc, bool want, V3 o, V3 d, Hit& h) const
     {
+        // (no lane has a ray — the LAST bounce of a path never traces its BSDF ray: that loop was 43 % of the last launch's instructions)
+        if (GROUPED && !__any_sync(0xffffffffu, want)) return;
         if constexpr (GROUPED) {
             h.t = FLT_MAX; h.u = 0.f; h.v = 0.f; h.prim = 0x7fffffff;
             groupedClosest(secAll, o, d, want, h);
@@ -804,7 +809,9 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
         bool wantNext = false, trace = false;
         V3 no = mk(0.f), nd = mk(0.f), nT = mk(0.f);
         Hit nh{FLT_MAX, 0.f, 0.f, -1};
-        if (bsdf) {
+        // (throughput instantiation: at the last depth the BSDF sample is not even drawn — nothing follows it on the path's counter
+        //  stream; the exact one must consume the draws, the next sample of the pixel continues the same mt19937 stream)
+        if (bsdf && (kExact || bounce + 1 < w.maxDepth)) {
             float pdf = 1.0f;
             V3 nextDir = mk(0.f);
             const V3 fr = sampleBxDF(s, rng, nextDir, pdf);
@@ -862,5 +869,5 @@ __global__ void __launch_bounds__(kBlock, 5) k_bounce_small(DScene sc, DQueues q
 #endif
     statAdd(stats, kStatClosest, nClosest);
     statAdd(stats, kStatShadow, nShadow);
-    if (!kExact) statAdd(stats, kStatScissored, nUntraced); // counted as the reference's calls, not traced
+    if (!kExact) { statAdd(stats, kStatScissored, nUntraced); statAdd(stats, kStatUntracedShadow, nUntraced); } // counted as the reference's calls, not traced
 }

@@ -674,5 +674,6 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + kStatClosest, (unsigned long long)n);
     statAdd(stats, kStatPrimaryHits, nHits);
     statAdd(stats, kStatScissored, nScissored); // reference-equivalent rays that were never traced
+    statAdd(stats, kStatUntracedClosest, nScissored);
     if (COUNT) { statAdd(stats, kStatNodes, tc.nodes); statAdd(stats, kStatTris, tc.tris); }
 }

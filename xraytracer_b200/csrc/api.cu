@@ -1033,6 +1033,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
 
     DWave w{};
     w.width = p->width; w.height = p->height; w.nPixels = nPixels;
+    w.byWidth = makeFastDiv(uint32_t(p->width));
     w.integrator = integ; w.maxDepth = p->max_depth; w.seed = p->seed;
     w.flags = 0;
     w.sx0 = 0; w.sy0 = 0; w.sx1 = p->width; w.sy1 = p->height;
@@ -1063,6 +1064,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         const uint32_t sw = std::min<uint32_t>(S, uint32_t(p->spp) - done);
         w.pixelBase = pix0;
         w.wavePixels = std::min<uint32_t>(tile, nPixels - pix0);
+        w.byWavePixels = makeFastDiv(w.wavePixels);
         w.samplesThisWave = sw;
         w.nPaths = sw * w.wavePixels;
         w.sampleBase = uint32_t(p->sample_offset) + done;
@@ -1603,6 +1605,7 @@ int xrtg_trace_primary(xrtg_scene* s, const xrtg_camera* cam, int width, int hei
     cudaStream_t st = s->stream;
     DWave w{};
     w.width = width; w.height = height; w.nPixels = nPixels; w.pixelBase = 0; w.wavePixels = nPixels; w.nPaths = uint32_t(nPaths);
+    w.byWidth = makeFastDiv(uint32_t(width)); w.byWavePixels = makeFastDiv(uint32_t(nPixels));
     w.samplesThisWave = uint32_t(spp); w.sampleBase = 0; w.integrator = XRTG_INT_NORMAL; w.maxDepth = 1;
     w.sx0 = 0; w.sy0 = 0; w.sx1 = width; w.sy1 = height;
     w.mt = static_cast<uint32_t*>(s->mt.p);

@@ -107,6 +107,31 @@ enum { kCtrlStride = 8, kCtrlRays = 0, kCtrlShadow = 1, kCtrlFetchExtend = 2, kC
 // device-side statistics (uint64 each)
 enum { kStatClosest = 0, kStatShadow, kStatDropped, kStatNodes, kStatTris, kStatNodesAny, kStatTrisAny, kStatSteps, kStatPrimaryHits, kStatBounceEntries, kStatScissored, kStatTruncated, kStatUntracedClosest, kStatUntracedShadow, kStatCount };
 
+// Exact unsigned division by a run-time constant (Granlund & Montgomery): q = (t + ((n - t) >> sh1)) >> sh2 with t = umulhi(m, n).
+// Path ids are split into (sample, pixel) and pixels into (row, column) by every kernel that opens a path's RNG; the compiler's
+// 32-bit division is ~20 instructions, this is 4 (k_primary spent 18 % of its instructions on three divisions per path).
+struct FastDiv {
+    uint32_t m, sh1, sh2, d;
+#ifdef __CUDACC__
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { const uint32_t t = uint32_t((uint64_t(m) * uint64_t(n)) >> 32); return (t + ((n - t) >> sh1)) >> sh2; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+#endif
+};
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline FastDiv makeFastDiv(uint32_t d)
+{
+    FastDiv f{};
+    f.d = d ? d : 1u;
+    uint32_t l = 0;
+    while ((1ull << l) < f.d) ++l; // ceil(log2 d)
+    f.m = uint32_t(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1ull);
+    f.sh1 = l < 1u ? l : 1u;
+    f.sh2 = l > 0u ? l - 1u : 0u;
+    return f;
+}
+
 struct DWave {
     int width, height;
     uint32_t nPixels;       // pixels of the whole image (stride of the per-pixel mt19937 state)
@@ -114,6 +139,7 @@ struct DWave {
     // per-path workspace is so large (hundreds of area lights -> shadow-queue entries per path) that one sample of every pixel
     // would not fit the workspace budget. Path id = s * wavePixels + (pixel - pixelBase).
     uint32_t pixelBase, wavePixels;
+    FastDiv byWavePixels, byWidth; // exact division by wavePixels / width (kept in step with them by setWave())
     uint32_t nPaths;        // wavePixels * samplesThisWave
     uint32_t sampleBase;    // index of the first sample of this wave (sample_offset + done so far)
     uint32_t samplesThisWave;

@@ -60,14 +60,16 @@ struct Rng {
 
     __device__ __forceinline__ void open(const DWave& w, uint32_t pid, uint32_t counter)
     {
-        pix = w.pixelBase + pid % w.wavePixels;
+        uint32_t s, lp;
+        w.byWavePixels.divmod(pid, s, lp);
+        pix = w.pixelBase + lp;
         if constexpr (kExact) {
             mt = w.mt; mti = w.mti; stride = w.nPixels;
             idx = mti[pix];
         }
         else {
             k0 = w.seed; k1 = pix;
-            sample = w.sampleBase + pid / w.wavePixels;
+            sample = w.sampleBase + s;
             ctr = counter;
             bufBlock = 0xffffffffu;
         }
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kBlock) k_gen_jitter(DWave w, int spp, float* 
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < w.nPixels; p += gridDim.x * blockDim.x) {
         DWave w1 = w;
-        w1.samplesThisWave = 1; w1.pixelBase = 0; w1.wavePixels = w.nPixels;
+        w1.samplesThisWave = 1; w1.pixelBase = 0; w1.wavePixels = w.nPixels; w1.byWavePixels = makeFastDiv(w.nPixels);
         for (int s = 0; s < spp; ++s) {
             Rng rng;
             w1.sampleBase = w.sampleBase + uint32_t(s);

@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DQueues q, DWave
 {
     const uint32_t n = w.nPaths;
     for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n; pid += gridDim.x * blockDim.x) {
-        const uint32_t pix = w.pixelBase + pid % w.wavePixels, s = pid / w.wavePixels;
-        const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+        uint32_t s, lp, i, j;
+        w.byWavePixels.divmod(pid, s, lp);
+        const uint32_t pix = w.pixelBase + lp;
+        w.byWidth.divmod(pix, i, j);
         float r0, r1;
         uint32_t ctr = 0;
         if (jitter) {
@@ -596,8 +598,10 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
     // one path: ray generation, scissor, closest hit; misses are resolved here
     auto path = [&](uint32_t pid, V3& d, Hit& h, uint32_t& ctr) -> bool {
         if (pid >= n) return false;
-        const uint32_t pix = w.pixelBase + pid % w.wavePixels;
-        const uint32_t i = pix / uint32_t(w.width), j = pix % uint32_t(w.width);
+        uint32_t smp, lp, i, j;
+        w.byWavePixels.divmod(pid, smp, lp);
+        const uint32_t pix = w.pixelBase + lp;
+        w.byWidth.divmod(pix, i, j);
         const bool inView = int(j) >= w.sx0 && int(j) < w.sx1 && int(i) >= w.sy0 && int(i) < w.sy1;
         bool hit = false;
         // small scenes: the triangles that can be seen through this warp's pixels (one mask per 32 pixels; OR over the warp's
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
         if (inView) { // (outside: the pixel cannot see the scene's bounding box, every sample is a miss, no ray needed)
             float r0, r1;
             if constexpr (JITTER) { // parity hook (xrtg_trace_primary): caller-supplied jitter, laid out [(pixel * spp + s) * 2]
-                const size_t k = (size_t(pix) * w.samplesThisWave + pid / w.wavePixels) * 2;
+                const size_t k = (size_t(pix) * w.samplesThisWave + smp) * 2;
                 r0 = jitter[k]; r1 = jitter[k + 1];
             }
             else {

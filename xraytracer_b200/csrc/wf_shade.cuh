@@ -213,7 +213,7 @@ __device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 
 
 // Surface integrators: Normal (integrator.h:29-36), furnace (:59-66), Direct (:82-119), Indirect (:129-186),
 // GI (:205-287), Whitted's Lambert/delta-light branch (:302-394). One thread per ray-queue entry of bounce b.
-__global__ void __launch_bounds__(kShadeBlock, 4) k_shade_surface(DScene sc, DQueues q, DWave w, int src, int bounce)
+__global__ void __launch_bounds__(kShadeBlock, XRT_SHADE_MINB) k_shade_surface(DScene sc, DQueues q, DWave w, int src, int bounce)
 {
     __shared__ uint32_t s_scratch[2][kShadeWarps + 1]; // two buffers used alternately: two barriers per append (blockAppendAlt)
     int appendPhase = 0;

@@ -87,7 +87,10 @@ __device__ __forceinline__ void addRadiance(const DQueues& q, uint32_t pid, V3 c
 }
 
 constexpr int kSentinel = 0x7fffffff;
-constexpr uint32_t kFetchChunk = 64;  // queue entries a warp reserves per atomic (256 costs up to 16 % in tail imbalance)
+#ifndef XRT_FETCH_CHUNK
+#define XRT_FETCH_CHUNK 64
+#endif
+constexpr uint32_t kFetchChunk = XRT_FETCH_CHUNK;  // queue entries a warp reserves per atomic (256 costs up to 16 % in tail imbalance)
 
 struct RayState {
     V3 o, d, idir, ood;
@@ -430,6 +433,9 @@ __global__ void __launch_bounds__(kBlock) k_connect_simple(DScene sc, DQueues q,
 // Block-aggregated append: ONE global atomic per CTA per call (same-address L2 atomics retire at ~1/ns; with one atomic per
 // warp the three queue counters were the whole duration of the bounce-0 shade launch). Must be called by every thread of
 // the CTA; `scratch` is kShadeWarps + 1 words of shared memory owned by this call site.
+#ifndef XRT_SHADE_MINB
+#define XRT_SHADE_MINB 4
+#endif
 constexpr int kShadeBlock = 256;
 constexpr int kShadeWarps = kShadeBlock / 32;
 template <int NWARPS = kShadeWarps>

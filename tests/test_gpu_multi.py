@@ -60,14 +60,23 @@ def test_multi_gpu_volume_and_deep_scenes():
     vol = scenes.volume_scene(n=24)           # grid descriptors carry per-device voxel pointers
     d = vol.flatten()
     a, sa = api.GpuScene(d, 0).render(cam, W, H, 16, capi.INT_VOLUME, 8, seed=2)
-    b, sb = api.GpuScene(d, devices=devs).render(cam, W, H, 16, capi.INT_VOLUME, 8, seed=2)
+    mv = api.GpuScene(d, devices=devs)
+    b, sb = mv.render(cam, W, H, 16, capi.INT_VOLUME, 8, seed=2)
     assert np.allclose(a, b, rtol=3e-6, atol=1e-6) and sa["tracking_steps"] == sb["tracking_steps"] > 0
+    # re-upload: host -> device 0 once, then the broadcast tree of peer copies (voxels, their 3-D texture copies, every array)
+    mv.upload()
+    b2, sb2 = mv.render(cam, W, H, 16, capi.INT_VOLUME, 8, seed=2)
+    assert np.array_equal(b2, b) and sb2["tracking_steps"] == sb["tracking_steps"]
     extra = lambda h: h.add_mesh("tess", scenes.displaced_sphere_tris((278, 200, 280), 150, 40, 40), (0.75, 0.75, 0.75))
     deep = scenes.cornell_box("quad", extra=extra)
     d = deep.flatten()
     a, sa = api.GpuScene(d, 0).render(cam, W, H, 8, capi.INT_GI, 3, seed=2)
-    b, sb = api.GpuScene(d, devices=devs).render(cam, W, H, 8, capi.INT_GI, 3, seed=2)
+    md = api.GpuScene(d, devices=devs)
+    b, sb = md.render(cam, W, H, 8, capi.INT_GI, 3, seed=2)
     assert np.allclose(a, b, rtol=3e-5, atol=1e-5) and sa["closest_rays"] == sb["closest_rays"]
+    md.upload()
+    b2, _ = md.render(cam, W, H, 8, capi.INT_GI, 3, seed=2)
+    assert np.array_equal(b2, b)
 
 
 def test_reduce_finalize_kernel_and_exchange_buffers(cornell):

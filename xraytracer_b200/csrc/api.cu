@@ -51,6 +51,7 @@ xrtg_scene::~xrtg_scene()
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : stageEvents) cudaEventDestroy(e);
     if (doneEvent) cudaEventDestroy(doneEvent);
+    if (uploadEvent) cudaEventDestroy(uploadEvent);
     if (pullEvent) cudaEventDestroy(pullEvent);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -690,10 +691,14 @@ int xrtg_scene_upload(xrtg_scene* s)
         for (int k = 0; k < kSceneArrays; ++k)
             if (dst[k] != &r->grids) dst[k]->shareHost(*src[k]); // (every replica owns its table of grid descriptors: device pointers)
     }
-    for (xrtg_scene* r : all) { // every replica's copies are enqueued before the first one is waited for
-        CU(cudaSetDevice(r->device));
-        if (int rc = uploadAll(r, false)) return rc;
-    }
+    bool viaPeers = false;
+    if (all.size() > 1)
+        if (int rc = broadcastUpload(s, &viaPeers)) return rc;
+    if (!viaPeers)
+        for (xrtg_scene* r : all) { // every replica's copies are enqueued before the first one is waited for
+            CU(cudaSetDevice(r->device));
+            if (int rc = uploadAll(r, false)) return rc;
+        }
     size_t total = 0;
     for (xrtg_scene* r : all) {
         CU(cudaSetDevice(r->device));

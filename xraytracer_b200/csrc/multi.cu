@@ -191,6 +191,59 @@ static bool enablePeerAccess(xrtg_scene* s)
     return all;
 }
 
+// xrtg_scene_upload on a multi-device handle: the scene arrays cross PCIe ONCE (pinned host -> device 0) and reach the other
+// replicas over NVLink in a binomial tree of peer copies (replica k pulls from replica k minus its highest set bit, as soon as
+// that one's copy has landed: log2(G) rounds, every device sends and receives at most one array set per round) instead of G
+// concurrent host-to-device uploads of the same bytes. Only the small table of grid descriptors (device pointers) comes from each
+// replica's own host copy. *done = false (nothing enqueued) when some pair of devices cannot map each other's memory.
+int broadcastUpload(xrtg_scene* s, bool* done)
+{
+    *done = false;
+    const int G = int(s->replicas.size());
+    if (G < 2) return 0;
+    if (!s->peerChecked) { s->peerAll = enablePeerAccess(s); s->peerChecked = true; }
+    if (!s->peerAll) return 0;
+    for (xrtg_scene* r : s->replicas) {
+        CU(cudaSetDevice(r->device));
+        if (!r->uploadEvent) CU(cudaEventCreateWithFlags(&r->uploadEvent, cudaEventDisableTiming));
+    }
+    xrtg_scene* root = s->replicas[0];
+    CU(cudaSetDevice(root->device));
+    if (int rc = uploadAll(root, false)) return rc;
+    CU(cudaEventRecord(root->uploadEvent, root->stream));
+    size_t h2d = root->info.upload_bytes;
+    for (int k = 1; k < G; ++k) {
+        int top = 1;
+        while (top * 2 <= k) top *= 2;
+        xrtg_scene* parent = s->replicas[size_t(k - top)];
+        xrtg_scene* r = s->replicas[size_t(k)];
+        CU(cudaSetDevice(r->device));
+        CU(cudaStreamWaitEvent(r->stream, parent->uploadEvent, 0));
+        Mirror *src[kSceneArrays], *dst[kSceneArrays];
+        sceneArrays(parent, src);
+        sceneArrays(r, dst);
+        for (int a = 0; a < kSceneArrays; ++a) {
+            if (dst[a] == &r->grids) { // this replica's own table of grid descriptors
+                if (r->grids.bytes) CU(cudaMemcpyAsync(r->grids.d, r->grids.h, r->grids.bytes, cudaMemcpyHostToDevice, r->stream));
+                h2d += r->grids.bytes;
+                continue;
+            }
+            if (dst[a]->bytes && dst[a]->bytes == src[a]->bytes)
+                CU(cudaMemcpyPeerAsync(dst[a]->d, r->device, src[a]->d, parent->device, dst[a]->bytes, r->stream));
+        }
+        for (size_t g = 0; g < r->gridData.size() && g < parent->gridData.size(); ++g) {
+            CU(cudaMemcpyPeerAsync(r->gridData[g]->d, r->device, parent->gridData[g]->d, parent->device, r->gridData[g]->bytes, r->stream));
+            if (g < r->gridTex.size() && r->gridTex[g])
+                if (int rc = r->gridTex[g]->fill(r->gridData[g]->d, cudaMemcpyDeviceToDevice, r->stream)) return rc;
+        }
+        CU(cudaEventRecord(r->uploadEvent, r->stream));
+        r->info.upload_bytes = 0; // (nothing of this replica's arrays crossed PCIe)
+    }
+    root->info.upload_bytes = h2d;
+    *done = true;
+    return 0;
+}
+
 int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgbHost, xrtg_stats* stats)
 {
     const int G = int(s->replicas.size());

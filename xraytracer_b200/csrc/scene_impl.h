@@ -216,6 +216,7 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     // multi-GPU (multi.cu): replicas of this scene on further devices; empty for a single-device scene. Replica 0 is `this`.
     std::vector<xrtg_scene*> replicas;
     cudaEvent_t doneEvent = nullptr; // recorded on `stream` when this device's share of a multi-GPU render is complete
+    cudaEvent_t uploadEvent = nullptr; // ... when this replica holds the scene arrays of the current xrtg_scene_upload (NVLink broadcast tree)
     cudaEvent_t pullEvent = nullptr; // ... when its slice of the fused reduce + finalize has been stored into device 0's image
     bool peerChecked = false, peerAll = false;
     xrt::DevBuf multiOut;            // device 0: the final image of a multi-GPU render
@@ -243,5 +244,6 @@ int checkParams(const xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_p
 int checkGuards(xrtg_scene* s, int* violations);
 int createReplica(const xrtg_scene* primary, int device, xrtg_scene** out);
 int renderMulti(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_params* p, float* rgbHost, xrtg_stats* stats);
+int broadcastUpload(xrtg_scene* s, bool* done); // multi-device handles: host -> device 0 once, then a binomial tree of peer copies
 void launchReduceFinalize(cudaStream_t st, const float* const* parts, int nParts, float* out, size_t n0, size_t n1, float divisor);
 } // namespace xrt

@@ -577,3 +577,26 @@ def test_double_run_bitwise_determinism_of_every_pipeline():
                 assert np.array_equal(bits(a), bits(b)), (name, flags, arity)
                 for k in ("closest_rays", "shadow_rays", "tracking_steps", "dropped_samples", "primary_hits", "bounce_entries", "rays_traced"):
                     assert sa[k] == sb[k], (name, flags, k)
+
+
+def test_wave_size_does_not_change_the_image():
+    """Samples are rendered in waves of S samples of every pixel (default: as many as a 16 GiB / 64 M-path budget allows, 32 at
+    1080p) and summed per pixel in sample order (renderer.cpp:57-75), so the wave size must not change a single bit of the image
+    nor a ray count — on the fused small-scene pipeline (warp-chunked appends with dead slots), the three-kernel wavefront on a
+    deep BVH (Russian roulette before the trace, untraced zero-contribution shadow rays) and the volume path kernel."""
+    require_gpu()
+    W, H, spp = 160, 90, 40
+    cam = scenes.make_camera(W, H)
+    extra = lambda h: h.add_mesh("tess", scenes.displaced_sphere_tris((278, 200, 280), 150, 40, 40), (0.75, 0.75, 0.75))
+    cases = [(scenes.cornell_box("quad"), capi.INT_GI, 3), (scenes.cornell_box("quad", extra=extra), capi.INT_GI, 3),
+             (scenes.cornell_box("triangle"), capi.INT_DIRECT, 1), (scenes.volume_scene(n=24), capi.INT_VOLUME, 8)]
+    for host, integ, depth in cases:
+        gpu = api.GpuScene(host.flatten(), 0)
+        base, sb = gpu.render(cam, W, H, spp, integ, depth, seed=9)
+        assert sb["rays_traced"] <= sb["closest_rays"] + sb["shadow_rays"]
+        assert sb["rays_traced"] == sb["closest_rays"] + sb["shadow_rays"] - sb["untraced_closest"] - sb["untraced_shadow"]
+        for S in (1, 4, 7, 40):
+            img, st = gpu.render(cam, W, H, spp, integ, depth, seed=9, samples_per_wave=S)
+            assert np.array_equal(bits(img), bits(base)), (integ, S)
+            for k in ("closest_rays", "shadow_rays", "rays_traced", "tracking_steps", "dropped_samples"):
+                assert st[k] == sb[k], (integ, S, k)

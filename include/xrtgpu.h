@@ -301,6 +301,7 @@ typedef struct xrtg_tuning {
     int32_t ploc_top;        /* creation time only: clusters at which PLOC hands over to the top-level sweep SAH (default 1024) */
     int32_t grid_texture;    /* creation time only: density grids also live in a 3-D texture (1, default) that the throughput
                                 instantiation samples with hardware trilinear filtering; 0 = global-memory lookups only              */
+    int32_t overlap_connect; /* three-kernel pipeline: any hit of bounce b on a side stream, concurrently with the closest hit of bounce b+1 */
     int32_t ploc_weight;     /* creation time only: top-level sweep SAH weighs a side by its triangles (0) or clusters (1, default) */
 } xrtg_tuning;
 

@@ -112,7 +112,7 @@ class SceneInfo(C.Structure):
 
 TUNING_KEYS = ["fused_bounce", "volume_paths", "scissor", "brute_secondary", "brute_shadow", "thr_ext0", "thr_ext", "thr_con",
                "steps_per_vote", "leaf_threshold", "thr_vol", "spv_vol", "wide_bvh", "max_leaf", "workspace_mb", "stage_dump", "primary_masks",
-               "gpu_build", "ploc_radius", "ploc_ct_x16", "ploc_top", "grid_texture", "ploc_weight"]
+               "gpu_build", "ploc_radius", "ploc_ct_x16", "ploc_top", "grid_texture", "overlap_connect", "ploc_weight"]
 
 
 class Tuning(C.Structure):

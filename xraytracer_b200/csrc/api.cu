@@ -52,6 +52,9 @@ xrtg_scene::~xrtg_scene()
     for (auto& e : stageEvents) cudaEventDestroy(e);
     if (doneEvent) cudaEventDestroy(doneEvent);
     if (uploadEvent) cudaEventDestroy(uploadEvent);
+    if (evShaded) cudaEventDestroy(evShaded);
+    if (evConnected) cudaEventDestroy(evConnected);
+    if (sideStream) cudaStreamDestroy(sideStream);
     if (pullEvent) cudaEventDestroy(pullEvent);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -127,7 +130,8 @@ const TuningKey kTuningKeys[] = {
     {"leaf_threshold", &xrtg_tuning::leaf_threshold}, {"thr_vol", &xrtg_tuning::thr_vol}, {"spv_vol", &xrtg_tuning::spv_vol},
     {"wide_bvh", &xrtg_tuning::wide_bvh}, {"primary_masks", &xrtg_tuning::primary_masks}, {"max_leaf", &xrtg_tuning::max_leaf}, {"workspace_mb", &xrtg_tuning::workspace_mb},
     {"stage_dump", &xrtg_tuning::stage_dump}, {"gpu_build", &xrtg_tuning::gpu_build}, {"ploc_radius", &xrtg_tuning::ploc_radius},
-    {"ploc_ct_x16", &xrtg_tuning::ploc_ct_x16}, {"ploc_top", &xrtg_tuning::ploc_top}, {"ploc_weight", &xrtg_tuning::ploc_weight}, {"grid_texture", &xrtg_tuning::grid_texture}};
+    {"ploc_ct_x16", &xrtg_tuning::ploc_ct_x16}, {"ploc_top", &xrtg_tuning::ploc_top}, {"ploc_weight", &xrtg_tuning::ploc_weight}, {"grid_texture", &xrtg_tuning::grid_texture},
+    {"overlap_connect", &xrtg_tuning::overlap_connect}};
 constexpr int kGpuBuildMinTris = 1024;   // below this the device build is refused: the host path is faster than its launches and synchronisations
 constexpr int kGpuBuildAutoTris = 65536; // from here on the device build is the default
 
@@ -1047,6 +1051,15 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
 
     StageTimer tm{s, st, count || (p->flags & XRTG_FLAG_STAGE_TIMES) != 0};
     const int missMode = integ == XRTG_INT_DIRECT ? 1 : (integ == XRTG_INT_WHITTED ? 2 : 0);
+    // Three-kernel pipeline with shadow rays: any hit (bounce b) and closest hit (bounce b + 1) are independent — run them on two
+    // streams. Not with per-stage timers (their events assume one stream) and not for the fused / volume pipelines (no such pair).
+    const bool overlapConnect = hasShadow && !volume && !P.fusedBounce && !tm.on && nIter > 1 && tv(s->tuning.t.overlap_connect, 1) != 0;
+    bool connectPending = false;
+    if (overlapConnect) {
+        if (!s->sideStream) CU(cudaStreamCreateWithFlags(&s->sideStream, cudaStreamNonBlocking));
+        if (!s->evShaded) CU(cudaEventCreateWithFlags(&s->evShaded, cudaEventDisableTiming));
+        if (!s->evConnected) CU(cudaEventCreateWithFlags(&s->evConnected, cudaEventDisableTiming));
+    }
     const bool dump = tv(s->tuning.t.stage_dump, 0) != 0;
     if (P.scissor) {
         int sc4[4];
@@ -1106,15 +1119,27 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
             else K.extend(st, ds, q, src, b, brute ? 1 : ((P.bruteSecondary && b > 0) ? 2 : 0), count, dstats, b == 0 ? P.thrExt0 : P.thrExt, P.spv, P.leafThr);
             ++launches; ++nExtend;
             tm.end();
+            // (the shade kernel rewrites the shadow queue: the any-hit pass of the previous bounce must be through with it)
+            if (overlapConnect && connectPending) { CU(cudaStreamWaitEvent(st, s->evConnected, 0)); connectPending = false; }
             tm.begin(kStageShade);
             if (volume) K.shadeVolume(st, ds, q, w, src, b, brute, count, dstats);
             else K.shadeSurface(st, ds, q, w, src, b);
             ++launches; ++nShade;
             tm.end();
             if (hasShadow) {
-                tm.begin(kStageConnect);
-                K.connect(st, ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
-                tm.end();
+                if (overlapConnect) {
+                    // any hit of bounce b on the side stream, concurrently with the closest hit of bounce b + 1 on the main one
+                    CU(cudaEventRecord(s->evShaded, st));
+                    CU(cudaStreamWaitEvent(s->sideStream, s->evShaded, 0));
+                    K.connect(s->sideStream, ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
+                    CU(cudaEventRecord(s->evConnected, s->sideStream));
+                    connectPending = true;
+                }
+                else {
+                    tm.begin(kStageConnect);
+                    K.connect(st, ds, q, b, brute ? 1 : (P.bruteShadow ? 2 : 0), count, dstats, P.thrCon, P.spv, P.leafThr); ++launches; ++nConnect;
+                    tm.end();
+                }
             }
             if (volume) {
                 // the number of loop iterations of integrator.h:418 is data dependent: poll the next queue size
@@ -1124,6 +1149,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
                 if (b + 1 == nIter) truncatedHost += s->ctrlHost[0]; // paths still alive at the iteration bound
             }
         }
+        if (overlapConnect && connectPending) { CU(cudaStreamWaitEvent(st, s->evConnected, 0)); connectPending = false; } // radiance complete
         tm.begin(kStageOther);
         K.accumulate(st, q, w, accum, dstats); ++launches;
         tm.end();

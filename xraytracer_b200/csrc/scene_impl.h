@@ -211,6 +211,10 @@ struct __attribute__((visibility("hidden"))) xrtg_scene { // (the C header forwa
     unsigned long long* statsHost = nullptr; // pinned
     uint32_t* ctrlHost = nullptr;            // pinned (volume queue polling)
     cudaEvent_t ev[4] = {};
+    // three-kernel pipeline: the shadow rays of bounce b (any hit) are traced on a side stream while the main stream already traces
+    // the extension rays of bounce b + 1 — two independent persistent kernels, so the tail of one overlaps the other
+    cudaStream_t sideStream = nullptr;
+    cudaEvent_t evShaded = nullptr, evConnected = nullptr;
     std::vector<cudaEvent_t> stageEvents; // pairs, with COUNTERS
     std::vector<int> stageKinds;
     // multi-GPU (multi.cu): replicas of this scene on further devices; empty for a single-device scene. Replica 0 is `this`.

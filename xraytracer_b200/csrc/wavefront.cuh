@@ -53,11 +53,18 @@ namespace xrt {
 #define XRT_WARP_APPEND_PRIMARY 0
 #endif
 
+// Deep scenes: queue entries are read once and written once per launch — loaded / stored with the streaming (evict-first) cache
+// hint so that the GBs of queue traffic do not push the tree and the triangle records (78 MB on c4) out of the 126 MB L2.
+#ifndef XRT_STREAM_HINTS
+#define XRT_STREAM_HINTS 1
+#endif
 #ifndef XRT_VOL_MINB
 #define XRT_VOL_MINB 4 // resident CTAs per SM k_volume_paths is compiled for (register budget 65536 / (128 x this))
 #endif
 
 namespace XRT_NS {
+__device__ __forceinline__ float4 qload(const float4* p) { return XRT_STREAM_HINTS ? __ldcs(p) : *p; }
+__device__ __forceinline__ void qstore(float4* p, float4 v) { if (XRT_STREAM_HINTS) __stcs(p, v); else *p = v; }
 
 constexpr bool kExact = (XRT_EXACT != 0);
 constexpr int kBlock = 128;          // threads per CTA of the traversal kernels (the surface shade kernel uses kShadeBlock)

@@ -186,9 +186,9 @@ __device__ __forceinline__ void pushShadow(const ShadeOut& so, bool want, V3 o, 
 {
     const uint32_t slot = blockAppendAlt(so.ctrlCur + kCtrlShadow, want, scratch2, phase);
     if (want) {
-        so.q.s0[slot] = make_float4(o.x, o.y, o.z, tmax);
-        so.q.s1[slot] = make_float4(d.x, d.y, d.z, __int_as_float(int(pid)));
-        so.q.s2[slot] = make_float4(c.x, c.y, c.z, 0.f);
+        qstore(so.q.s0 + slot, make_float4(o.x, o.y, o.z, tmax));
+        qstore(so.q.s1 + slot, make_float4(d.x, d.y, d.z, __int_as_float(int(pid))));
+        qstore(so.q.s2 + slot, make_float4(c.x, c.y, c.z, 0.f));
     }
 }
 // warp-aggregated variant (one atomic per warp) for the volume kernel, whose warps run independently
@@ -205,9 +205,9 @@ __device__ __forceinline__ void pushRay(const ShadeOut& so, bool want, V3 o, V3 
 {
     const uint32_t slot = blockAppendAlt(so.ctrlNext + kCtrlRays, want, scratch2, phase);
     if (want) {
-        so.q.q0[so.dst][slot] = make_float4(o.x, o.y, o.z, T.x);
-        so.q.q1[so.dst][slot] = make_float4(d.x, d.y, d.z, T.y);
-        so.q.q2[so.dst][slot] = make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr)));
+        qstore(so.q.q0[so.dst] + slot, make_float4(o.x, o.y, o.z, T.x));
+        qstore(so.q.q1[so.dst] + slot, make_float4(d.x, d.y, d.z, T.y));
+        qstore(so.q.q2[so.dst] + slot, make_float4(T.z, __int_as_float(int(pid)), __int_as_float(depth), __int_as_float(int(ctr))));
     }
 }
 
@@ -239,9 +239,9 @@ __global__ void __launch_bounds__(kShadeBlock, XRT_SHADE_MINB) k_shade_surface(D
         hv.w = __int_as_float(-1);
         bool liveEntry = live;
         if (live) {
-            hv = q.hits[i]; r2 = q.q2[src][i];
+            hv = qload(q.hits + i); r2 = qload(q.q2[src] + i);
             if (XRT_WARP_APPEND_PRIMARY && deadEntry(r2)) liveEntry = false; // (unused tail slot of k_primary's warp-private chunks)
-            else if (__float_as_int(hv.w) >= 0) { r0 = q.q0[src][i]; r1 = q.q1[src][i]; }
+            else if (__float_as_int(hv.w) >= 0) { r0 = qload(q.q0[src] + i); r1 = qload(q.q1[src] + i); }
         }
         const V3 o = xyz(r0), d = xyz(r1);
         V3 T = mk(r0.w, r1.w, r2.x);

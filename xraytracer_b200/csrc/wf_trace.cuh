@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DCamera cam, DQueues q, DWave
         const float v = (float(i) + r1) / float(uint32_t(w.height));
         V3 o, d;
         cameraRay(cam, u, v, o, d);
-        q.q0[0][pid] = make_float4(o.x, o.y, o.z, 1.0f);
-        q.q1[0][pid] = make_float4(d.x, d.y, d.z, 1.0f);
-        q.q2[0][pid] = make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr)));
-        q.radiance[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qstore(q.q0[0] + pid, make_float4(o.x, o.y, o.z, 1.0f));
+        qstore(q.q1[0] + pid, make_float4(d.x, d.y, d.z, 1.0f));
+        qstore(q.q2[0] + pid, make_float4(1.0f, __int_as_float(int(pid)), __int_as_float(0), __int_as_float(int(ctr))));
+        qstore(q.radiance + pid, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) q.ctrl[kCtrlRays] = n;
 }

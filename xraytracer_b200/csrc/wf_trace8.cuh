@@ -134,14 +134,14 @@ __global__ void __launch_bounds__(kBlock, MINB) k_trace8(DScene sc, DQueues q, i
                 r.qidx = i;
                 r.done = false;
                 if (ANY) {
-                    const float4 s0 = q.s0[i], s1 = q.s1[i];
+                    const float4 s0 = qload(q.s0 + i), s1 = qload(q.s1 + i);
                     r.o = xyz(s0); r.d = xyz(s1);
                     r.h.t = s0.w; r.h.u = 0.f; r.h.v = 0.f; r.h.prim = 0; // prim = occluded flag
                     r.minId = -1;
                     if (sc.nBoxes > 0) { r.h.prim = 1; r.done = true; } // BoxMesh::occluded is always true
                 }
                 else {
-                    const float4 r0 = q.q0[src][i], r1 = q.q1[src][i];
+                    const float4 r0 = qload(q.q0[src] + i), r1 = qload(q.q1[src] + i);
                     r.o = xyz(r0); r.d = xyz(r1);
                     r.h.t = FLT_MAX; r.h.u = 0.f; r.h.v = 0.f; r.h.prim = kSentinel;
                     r.minId = -1;
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_trace8(DScene sc, DQueues q, i
                         }
                         if (anyOut) anyOut[r.qidx] = make_float4(0.f, 0.f, 0.f, __int_as_float(r.h.prim));
                         else if (r.h.prim == 0) {
-                            const float4 c = q.s2[r.qidx];
-                            float* rad = reinterpret_cast<float*>(q.radiance + __float_as_int(q.s1[r.qidx].w));
+                            const float4 c = qload(q.s2 + r.qidx);
+                            float* rad = reinterpret_cast<float*>(q.radiance + __float_as_int(qload(q.s1 + r.qidx).w));
                             atomicAdd(rad + 0, c.x); atomicAdd(rad + 1, c.y); atomicAdd(rad + 2, c.z);
                         }
                     }
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_trace8(DScene sc, DQueues q, i
                             if (meta.x > r.minId && sphereT(cr, r.o, r.d, t)) consider(r.h, t, 0.f, 0.f, meta.x);
                         }
                         const int prim = r.h.prim == kSentinel ? -1 : r.h.prim;
-                        q.hits[r.qidx] = make_float4(prim >= 0 ? r.h.t : FLT_MAX, r.h.u, r.h.v, __int_as_float(prim));
+                        qstore(q.hits + r.qidx, make_float4(prim >= 0 ? r.h.t : FLT_MAX, r.h.u, r.h.v, __int_as_float(prim)));
                     }
                     active = false;
                 }

@@ -561,10 +561,7 @@ def run_workload(rig: Rig, name, wl, args, headline):
         peak, peak_src = measured_peak_hbm()
         paths_r0 = float(W) * H * my_spp * steps
         rays = st_all["closest_rays"] + st_all["shadow_rays"]
-        cpu = None
-        if not args.no_cpu_baseline and rig.world == 1:
-            cpu = cpu_baseline(wl)
-            cpu.pop("seconds", None)
+        cpu = None   # filled in by main() after ALL GPU measurements (see there)
         result = {
             "metric": "Msamples/s, " + wl["desc"], "value": samples / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "n_gpus": rig.world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
@@ -652,6 +649,14 @@ def main():
                                                    "roofline", "cpu_baseline", "e2e", "config", "clocks", "gpu_launches", "scene_build_ms", "bvh_build_ms",
                                                    "scene_upload_ms", "scene_create_call_ms", "scene_build_ms_repeat", "bvh_builder", "truncated_paths", "dropped_samples")}
     exact = run_exact_mode(rig, args) if "exact" in side else None
+    # The CPU baselines (the compiled reference on every host core, a few seconds each) run AFTER every GPU measurement of the
+    # process: scene creations that followed one inside the same process were occasionally 10-30x slower than on a quiet process
+    # (22 ms -> 50-700 ms for the device build of c4), and nothing on the GPU side should be billed for that.
+    if rig.rank == 0 and not args.no_cpu_baseline and rig.world == 1:
+        for name, res in [(args.workload, line)] + list(extra.items()):
+            cpu = cpu_baseline(dict(WORKLOADS[name], **({"spp": args.spp} if (args.spp and name == args.workload) else {})))
+            cpu.pop("seconds", None)
+            res["cpu_baseline"] = cpu
     if rig.rank == 0:
         if extra:
             line["workloads"] = extra

@@ -298,7 +298,7 @@ typedef struct xrtg_tuning {
     int32_t gpu_build;       /* creation time only (XRT_TUNING): 1 = as if XRTG_BUILD_GPU were passed, 0 = never build on the device */
     int32_t ploc_radius;     /* creation time only: PLOC neighbour-search radius (default 16)                                 */
     int32_t ploc_ct_x16;     /* creation time only: SAH traversal-step cost of the PLOC leaf decision, in 1/16 (default 16)   */
-    int32_t ploc_top;        /* creation time only: clusters at which PLOC hands over to the top-level sweep SAH (default 1024) */
+    int32_t ploc_top;        /* creation time only: clusters at which PLOC hands over to the top-level sweep SAH (default 8) */
     int32_t grid_texture;    /* creation time only: density grids also live in a 3-D texture (1, default) that the throughput
                                 instantiation samples with hardware trilinear filtering; 0 = global-memory lookups only              */
     int32_t overlap_connect; /* three-kernel pipeline: any hit of bounce b on a side stream, concurrently with the closest hit of bounce b+1 */
@@ -319,7 +319,8 @@ enum {
      * returns what the reference's brute-force loops return). */
     XRTG_BUILD_LBVH_GPU = 1u << 0,
     /* Ingest AND build on the device (csrc/gpu_build.cu): the raw triangle array is copied up once; the per-triangle records,
-     * a PLOC tree (parallel locally-ordered clustering over 63-bit Morton order, SAH-decided leaves of up to four triangles) and
+     * a PLOC tree (parallel locally-ordered clustering over 63-bit Morton order down to the last 8 clusters, SAH-decided leaves of
+     * up to four triangles) and
      * its collapse into eight-child quantised nodes are produced in HBM. Tens of milliseconds for a million triangles instead of
      * the host path's ~0.5-1.3 s, and a tree that traverses like the host SAH one. No pinned staging copies are made until
      * xrtg_scene_upload or a multi-GPU replica asks for them. This is the DEFAULT for scenes of 65536 mesh triangles or more; the

@@ -13,8 +13,8 @@ desc = host.flatten()
 cam = scenes.make_camera(wl["width"], wl["height"])
 import os
 variants = [("host SAH", capi.BUILD_HOST, ""), ("GPU LBVH", capi.BUILD_LBVH_GPU, "")]
-for r, ct, top, w in ((16, 16, 1024, 0), (16, 16, 1024, 1), (16, 16, 4096, 0), (16, 16, 4096, 1), (16, 16, 2048, 0), (16, 16, 2048, 1), (16, 16, 512, 1),
-                      (16, 16, 256, 0), (16, 16, 256, 1), (16, 12, 1024, 0), (16, 12, 1024, 1), (24, 16, 1024, 0), (24, 16, 1024, 1)):
+for r, ct, top, w in ((16, 16, 1, 1), (16, 16, 4, 1), (16, 16, 8, 1), (16, 16, 16, 1), (16, 16, 32, 1), (16, 16, 128, 1), (16, 16, 8, 0), (16, 16, 16, 0), (16, 16, 32, 0),
+                      (16, 16, 1024, 1), (24, 16, 16, 1), (12, 16, 16, 1)):
     variants.append((f"GPU PLOC r={r} ct={ct / 16:g} top={top} w={w}", capi.BUILD_GPU, f"ploc_radius={r},ploc_ct_x16={ct},ploc_top={top},ploc_weight={w}"))
 only = os.environ.get("AB_ONLY")
 for name, flags, tuning in variants:

@@ -214,10 +214,20 @@ __device__ __forceinline__ unsigned long long pairKey(int a, int b)
     return ((unsigned long long)h << 32) | (unsigned long long)(lo * 128u + (hi - lo));
 }
 
+// The loop state lives in device memory so that several rounds can be enqueued without a host round trip: state[r & 1] =
+// (clusters m, next node id) read by round r, state[(r + 1) & 1] written by it. A round that finds m <= top does nothing but
+// carry the state (and the cluster list) forward, so enqueueing a few rounds too many is harmless.
+struct PlocState {
+    int m, nodeBase, rounds, pad;
+};
+
 // nearest neighbour of cluster i among clusters i-R..i+R: smallest surface area of the merged box, ties by pairKey
-__global__ void k_ploc_nn(const int* __restrict__ cid, int m, const float4* __restrict__ lo, const float4* __restrict__ hi, int R, int* __restrict__ nn)
+__global__ void k_ploc_nn(const int* __restrict__ cid, const PlocState* __restrict__ stIn, int top, const float4* __restrict__ lo,
+                          const float4* __restrict__ hi, int R, int* __restrict__ nn)
 {
     extern __shared__ float sbox[]; // 6 x (kB + 2R)
+    const int m = stIn->m;
+    if (m <= top || int(blockIdx.x) * kB >= m) return;
     const int W = kB + 2 * R;
     const int base = blockIdx.x * kB - R;
     for (int t = threadIdx.x; t < W; t += kB) {
@@ -253,27 +263,43 @@ __global__ void k_ploc_nn(const int* __restrict__ cid, int m, const float4* __re
     nn[i] = bestJ;
 }
 
-// packed[i] = (cluster i survives the round) | (cluster i is the lower half of a mutual pair, i.e. creates a node) << 32
-__global__ void k_ploc_flag(const int* __restrict__ nn, int m, unsigned long long* __restrict__ packed)
+// packed[i] = (cluster i survives the round) | (cluster i is the lower half of a mutual pair, i.e. creates a node) << 32;
+// 0 beyond the live clusters (the scan runs over the host's upper bound of m)
+__global__ void k_ploc_flag(const int* __restrict__ nn, const PlocState* __restrict__ stIn, int top, int mUpper, unsigned long long* __restrict__ packed)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    if (i >= mUpper) return;
+    const int m = stIn->m;
+    if (m <= top) return; // (nothing reads packed / incl in a carried-forward round)
+    if (i >= m) { packed[i] = 0ull; return; }
     const int j = nn[i];
     const bool mutual = nn[j] == i;
     const unsigned long long valid = (mutual && i > j) ? 0ull : 1ull, merge = (mutual && i < j) ? 1ull : 0ull;
     packed[i] = valid | (merge << 32);
 }
 
-__global__ void k_ploc_emit(const int* __restrict__ cid, const int* __restrict__ nn, const unsigned long long* __restrict__ incl, int m, int nodeBase,
-                            float ct, int maxLeaf, float4* __restrict__ lo, float4* __restrict__ hi, int2* __restrict__ child, int* __restrict__ parent,
-                            int* __restrict__ cidOut)
+__global__ void k_ploc_emit(const int* __restrict__ cid, const int* __restrict__ nn, const unsigned long long* __restrict__ incl,
+                            const PlocState* __restrict__ stIn, PlocState* __restrict__ stOut, int top, int mUpper, float ct, int maxLeaf,
+                            float4* __restrict__ lo, float4* __restrict__ hi, int2* __restrict__ child, int* __restrict__ parent, int* __restrict__ cidOut)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mUpper) return;
+    const int m = stIn->m, nodeBase = stIn->nodeBase;
+    if (m <= top) { // converged: carry the state and the cluster list forward
+        if (i < m) cidOut[i] = cid[i];
+        if (i == 0) *stOut = *stIn;
+        return;
+    }
     if (i >= m) return;
+    const unsigned long long s = incl[i];
+    if (i == m - 1) { // the totals of the round = the inclusive sums at the last live cluster
+        PlocState o;
+        o.m = int(uint32_t(s)); o.nodeBase = nodeBase + int(uint32_t(s >> 32)); o.rounds = stIn->rounds + 1; o.pad = 0;
+        *stOut = o;
+    }
     const int j = nn[i];
     const bool mutual = nn[j] == i;
     if (mutual && i > j) return; // absorbed by its partner
-    const unsigned long long s = incl[i];
     const int pos = int(uint32_t(s)) - 1;
     if (!mutual) { cidOut[pos] = cid[i]; return; }
     const int id = nodeBase + int(uint32_t(s >> 32)) - 1;
@@ -510,12 +536,14 @@ __global__ void k_gather4(const float4* __restrict__ src, const uint32_t* __rest
     for (int k = 0; k < 4; ++k) dst[4 * size_t(i) + k] = src[4 * s + k];
 }
 
-// ---- top levels on the host: full-sweep SAH over the (few thousand) clusters PLOC leaves standing ------------------------------
-// Agglomeration is weakest at the top of the tree: a handful of huge boxes (the walls of a room around a detailed mesh) are
-// absorbed one per round, which costs a round trip each and stacks up one tree level each (62 levels on the 1 M-triangle Cornell
-// scene). The top of the tree is also where split quality matters most — every ray walks it. So the last few thousand clusters are
-// split top-down with an exact sweep SAH (cost = area x triangle count on both sides, all three axes), which is what the host
-// builder does for whole scenes, at a cost of about a millisecond.
+// ---- the last merges on the host: full-sweep SAH over the clusters PLOC leaves standing ---------------------------------------
+// PLOC runs until `topClusters` clusters remain (default 8: essentially the whole tree is agglomerated on the device) and the
+// remaining ones — typically the handful of scene-sized boxes, e.g. the walls of a room around a detailed mesh — are split
+// top-down with an exact sweep SAH (cost = area x weight on both sides, all three axes) in a few microseconds. Handing over
+// EARLIER was measured and is worse: with 128..16384 clusters left to the sweep the 1 M-triangle scene traverses 4-5 % slower
+// (3.25-3.36 node fetches per ray against 2.87) — the agglomerated top follows the geometry, the sweep only sees cluster boxes.
+// Agglomerating to the root costs more rounds (137 instead of 55) and a deeper two-child tree (57-62 levels instead of 45), which
+// is why k_trace's stack holds 128 entries.
 struct TopCluster {
     float lo[3], hi[3], cost;
     uint32_t count;
@@ -693,6 +721,7 @@ cudaError_t buildPlocDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeaf
     unsigned long long *keys = nullptr, *keys2 = nullptr, *packed = nullptr, *incl = nullptr;
     int2 *child, *dIdParent;
     int *parent, *cidA, *cidB, *nn, *leafPos, *first, *stats;
+    PlocState* state;
     unsigned char* tmp;
     const size_t nNodes = 2 * size_t(n) - 1;
     const int topClusters = prm.topClusters < 1 ? 1 : prm.topClusters;
@@ -705,7 +734,7 @@ cudaError_t buildPlocDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeaf
     S.want(&packed, n); S.want(&incl, n); S.want(&child, nNodes); S.want(&parent, nNodes);
     S.want(&cidA, n); S.want(&cidB, n); S.want(&nn, n); S.want(&leafPos, n); S.want(&first, nNodes); S.want(&stats, 4);
     S.want(&tmp, sortBytes > scanBytes ? sortBytes : scanBytes);
-    S.want(&dTop, 2 * topCap); S.want(&dIdParent, 2 * topCap);
+    S.want(&dTop, 2 * topCap); S.want(&dIdParent, 2 * topCap); S.want(&state, 2);
     GB(S.commit());
     const uint32_t initB[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
     GB(cudaMemcpyAsync(bounds, initB, sizeof(initB), cudaMemcpyHostToDevice, st));
@@ -721,26 +750,38 @@ cudaError_t buildPlocDevice(const float4* dTrisId, uint32_t n, float4* dTrisLeaf
     const int R = prm.radius < 1 ? 1 : (prm.radius > 64 ? 64 : prm.radius);
     const int maxLeaf = prm.maxLeaf < 1 ? 1 : (prm.maxLeaf > 4 ? 4 : prm.maxLeaf);
     const size_t nnSmem = sizeof(float) * 6 * size_t(kB + 2 * R);
+    // Rounds are enqueued in batches of kRoundsPerSync with ONE read-back of the loop state per batch (a read-back per round made the
+    // build hostage to host scheduling: 137 synchronisations, 20 ms on a quiet box and 300 ms on a busy one). Grids and the scan are
+    // sized for the cluster count known at the last read-back; rounds past convergence only carry the state forward.
+    constexpr int kRoundsPerSync = 8;
     int m = int(n), nodeBase = int(n), iterations = 0;
     int *cid = cidA, *cidNext = cidB;
-    unsigned long long* totalsHost = nullptr;
-    GB(cudaMallocHost(&totalsHost, sizeof(unsigned long long)));
-    struct Unpin { unsigned long long* p; ~Unpin() { cudaFreeHost(p); } } unpin{totalsHost};
+    PlocState* stHost = nullptr;
+    GB(cudaMallocHost(&stHost, sizeof(PlocState)));
+    struct Unpin { PlocState* p; ~Unpin() { cudaFreeHost(p); } } unpin{stHost};
+    *stHost = PlocState{m, nodeBase, 0, 0};
+    GB(cudaMemcpyAsync(state, stHost, sizeof(PlocState), cudaMemcpyHostToDevice, st));
+    GB(cudaStreamSynchronize(st));
+    int round = 0;
     while (m > topClusters) {
-        const int g = (m + kB - 1) / kB;
-        k_ploc_nn<<<g, kB, nnSmem, st>>>(cid, m, lo, hi, R, nn);
-        k_ploc_flag<<<g, kB, 0, st>>>(nn, m, packed);
-        GB(cub::DeviceScan::InclusiveSum(tmp, scanBytes, packed, incl, m, st));
-        k_ploc_emit<<<g, kB, 0, st>>>(cid, nn, incl, m, nodeBase, prm.traversalCost, maxLeaf, lo, hi, child, parent, cidNext);
-        GB(cudaMemcpyAsync(totalsHost, incl + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        const int mUpper = m, g = (mUpper + kB - 1) / kB;
+        for (int k = 0; k < kRoundsPerSync; ++k, ++round) {
+            const PlocState* in = state + (round & 1);
+            PlocState* out = state + ((round + 1) & 1);
+            k_ploc_nn<<<g, kB, nnSmem, st>>>(cid, in, topClusters, lo, hi, R, nn);
+            k_ploc_flag<<<g, kB, 0, st>>>(nn, in, topClusters, mUpper, packed);
+            GB(cub::DeviceScan::InclusiveSum(tmp, scanBytes, packed, incl, mUpper, st));
+            k_ploc_emit<<<g, kB, 0, st>>>(cid, nn, incl, in, out, topClusters, mUpper, prm.traversalCost, maxLeaf, lo, hi, child, parent, cidNext);
+            int* t = cid; cid = cidNext; cidNext = t;
+        }
+        GB(cudaMemcpyAsync(stHost, state + (round & 1), sizeof(PlocState), cudaMemcpyDeviceToHost, st));
         GB(cudaStreamSynchronize(st));
-        const int valid = int(uint32_t(*totalsHost)), merges = int(uint32_t(*totalsHost >> 32));
-        if (merges <= 0 || valid != m - merges) return cudaErrorUnknown; // (cannot happen: the globally closest pair is always mutual)
-        if (prm.verbose && (iterations < 48 || iterations % 64 == 0)) std::fprintf(stderr, "ploc: round %d: %d clusters, %d merges\n", iterations, m, merges);
-        m = valid;
-        nodeBase += merges;
-        int* t = cid; cid = cidNext; cidNext = t;
-        if (++iterations > 4096) return cudaErrorNotSupported; // degenerate input (one merge per round): leave it to the host builder
+        if (stHost->m >= m && stHost->m > topClusters) return cudaErrorUnknown; // (cannot happen: the globally closest pair is always mutual)
+        if (prm.verbose) std::fprintf(stderr, "ploc: after %d rounds: %d clusters\n", stHost->rounds, stHost->m);
+        m = stHost->m;
+        nodeBase = stHost->nodeBase;
+        iterations = stHost->rounds;
+        if (iterations > 4096) return cudaErrorNotSupported; // degenerate input (one merge per round): leave it to the host builder
     }
     lap("clustering rounds");
     if (m > 1) {

@@ -629,6 +629,7 @@ int xrtg_scene_create2(const xrtg_scene_desc* d, int device, uint32_t build_flag
         M[i] = DMedium{};
         M[i].kind = m.kind; M[i].g = m.g; M[i].grid = m.grid; M[i].densityMul = m.density_mul;
         for (int k = 0; k < 3; ++k) { M[i].sigma_a[k] = m.sigma_a[k]; M[i].sigma_s[k] = m.sigma_s[k]; M[i].sigma_t[k] = m.sigma_a[k] + m.sigma_s[k]; }
+        M[i].grey = (m.sigma_a[0] == m.sigma_a[1] && m.sigma_a[1] == m.sigma_a[2] && m.sigma_s[0] == m.sigma_s[1] && m.sigma_s[1] == m.sigma_s[2]) ? 1 : 0;
         if (m.kind == XRTG_MEDIUM_HETEROGENEOUS) {
             // HeterogeneousMedium ctor, medium.cpp:5-17
             const float maxd = m.density_mul * d->grids[m.grid].max_density;

@@ -35,6 +35,7 @@ struct DMedium {
     float sigma_a[3], sigma_s[3], sigma_t[3];
     float densityMul, majorant, invMajorant;
     int grid;
+    int grey; // sigma_a and sigma_s are the same in all three channels (every medium of the reference's examples: nee.cpp:54, volume.cpp:49)
 };
 
 struct DGrid {

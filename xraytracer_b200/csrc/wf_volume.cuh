@@ -175,11 +175,29 @@ __device__ __forceinline__ void trackBegin(const DMedium& m, const DGrid& g, V3 
 // given step would otherwise run the long exit / scatter epilogues at 2-3 of 32 lanes inside the lockstep loop.
 __device__ __forceinline__ int trackStep(const DMedium& m, const DGrid& g, V3 o, V3 d, V3 rayT, TrackState& ts, Rng& rng, uint32_t& steps)
 {
+    ++steps;
+    rng.alignBlock(); // the three draws of one step come from one Philox block
+    if constexpr (!kExact) {
+        // Grey medium and a grey throughput (every medium of the reference's examples, and c5): the three channels of the spectral
+        // tracker behave alike — the wavelength pmf is (1/3, 1/3, 1/3) whatever channel is drawn, the scattering probability is one
+        // number, and the null-collision update sigma_n / (maj * sum(pmf * P_n)) collapses to (sigma_s + sigma_n) / maj. Same
+        // draws in the same order, one third of the arithmetic.
+        if (m.grey && rayT.x == rayT.y && rayT.y == rayT.z && ts.tt.x == ts.tt.y && ts.tt.y == ts.tt.z) {
+            (void)rng.next(); // the wavelength draw
+            ts.pmf = mk(1.0f / 3.0f);
+            ts.sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
+            ts.t += ts.sd;
+            if (ts.t > ts.t1 - kRayEps) return kTrackExit;
+            ts.density = m.densityMul * gridDensity(g, o + ts.t * d);
+            const float ss = m.sigma_s[0] * ts.density, sn = m.majorant - m.sigma_a[0] * ts.density - ss;
+            if (rng.next() < ss / (ss + sn)) return kTrackScatter;
+            ts.tt = ts.tt * ((ss + sn) * m.invMajorant);
+            return kTrackContinue;
+        }
+    }
     const V3 absC = v3(m.sigma_a), scatC = v3(m.sigma_s);
     const V3 maj = mk(m.majorant);
     V3 sigma_a = absC * ts.density;
-    ++steps;
-    rng.alignBlock(); // the three draws of one step come from one Philox block
     const uint32_t ch = sampleWavelength(rayT * ts.tt, (maj - sigma_a) * m.invMajorant, rng, ts.pmf);
     ts.sd = -logf(smax(1.0f - rng.next(), 0.0f)) * m.invMajorant;
     ts.t += ts.sd;

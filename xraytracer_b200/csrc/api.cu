@@ -1066,6 +1066,7 @@ int renderOnStream(xrtg_scene* s, const xrtg_camera* cam, const xrtg_render_para
         int sc4[4];
         computeScissor(s, cam, p->width, p->height, sc4);
         w.sx0 = sc4[0]; w.sy0 = sc4[1]; w.sx1 = sc4[2]; w.sy1 = sc4[3];
+        if (P.fusedPrimary) w.flags |= kWaveScissorSkip; // k_primary is the only writer of the initial radiance in these pipelines
     }
     uint64_t launches = 0, nExtend = 0, nShade = 0, nConnect = 0, nBounce = 0, truncatedHost = 0;
     CU(cudaEventRecord(s->ev[0], st));

@@ -133,6 +133,7 @@ inline FastDiv makeFastDiv(uint32_t d)
     return f;
 }
 
+constexpr uint32_t kWaveScissorSkip = 1u;
 struct DWave {
     int width, height;
     uint32_t nPixels;       // pixels of the whole image (stride of the per-pixel mt19937 state)
@@ -146,7 +147,7 @@ struct DWave {
     uint32_t samplesThisWave;
     int integrator, maxDepth;
     uint32_t seed;
-    uint32_t flags;         // development switches (none at present)
+    uint32_t flags;         // kWaveScissorSkip: out-of-scissor pixels carry no per-sample radiance (k_primary skips the write, k_accumulate the read)
     // Screen-space scissor [sx0, sx1) x [sy0, sy1): pixels outside it cannot see the scene's bounding box (every sample of such a
     // pixel is a miss), so the primary kernel resolves them without generating a ray. Full image when unknown.
     int sx0, sy0, sx1, sy1;

@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kBlock) k_primary(DScene sc, DCamera cam, DQue
             if (missMode == 1) c = mk(float(0.18));
             else if (missMode == 2) c = mk(1.f) * mk(float(0.235294), float(0.67451), float(0.843137));
         }
-        q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        if (inView || !(w.flags & kWaveScissorSkip)) q.radiance[pid] = make_float4(c.x, c.y, c.z, 0.f); // (see k_accumulate)
         return hit;
     };
     const V3 org = mk(cam.c2w[12], cam.c2w[13], cam.c2w[14]); // every primary ray starts at the camera position (camera.h:57)
